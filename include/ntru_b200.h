@@ -1,0 +1,125 @@
+/*
+ * ntru_b200.h -- C ABI of the B200-native batched NTRU engine (libntru_b200.so).
+ *
+ * Drop-in boundary for the hot path of numtel/ntru-circom.  The reference has no
+ * FFI of its own (it is one ES module, index.js); these entry points are what an
+ * N-API / ctypes binding for that path binds.  Each one names the reference
+ * interface it replaces (file:line relative to the reference repository).
+ *
+ * Conventions
+ *   - Polynomials are little-endian coefficient arrays, FIXED LENGTH and
+ *     un-trimmed: trimPolynomial / expandArray (index.js:218-221, 534-536) live in
+ *     the host-language wrapper, never here.
+ *   - mod-q coefficients are uint16_t, small coefficients (r, m, f, fp, mod-p
+ *     outputs) are one byte.  r carries -1 as p-1 = 2 (index.js:89); f is the raw
+ *     ternary key in {-1,0,1} (the witness value q-1 of index.js:112 is a wrapper
+ *     concern); fp is in [0,p).
+ *   - Host-buffer entry points take PACKED rows: pitch N for r, m, e, value and
+ *     N+1 for the witness arrays, exactly the reference's array lengths
+ *     (index.js:96-103, 123-131).  Any output pointer may be NULL (not produced).
+ *   - Device-buffer entry points (*_dev) take device pointers whose row pitch is
+ *     ntru_pitch(ctx) ELEMENTS for every array (a multiple of 16, >= N+1), run
+ *     asynchronously on the context's stream and copy nothing.
+ *   - Every function returns NTRU_OK (0) or a negative NTRU_E_* code;
+ *     ntru_last_error(ctx) gives the message.  There is no CPU fallback: without
+ *     a CUDA device every compute entry point fails with NTRU_E_CUDA.
+ *   - A context is single-caller (one host thread at a time), one per GPU.
+ */
+#ifndef NTRU_B200_H
+#define NTRU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ntru_ctx ntru_ctx;
+
+enum {
+  NTRU_OK = 0,
+  NTRU_E_PARAM = -1,       /* bad N/p/q/argument (reference: Error thrown by the constructor's users) */
+  NTRU_E_LENGTH = -2,      /* reference: RangeError from expandArray, index.js:98,126 */
+  NTRU_E_NOKEY = -3,       /* reference: TypeError on null h / f, index.js:90,112 */
+  NTRU_E_CUDA = -4,
+  NTRU_E_NCCL = -5,
+  NTRU_E_NOMEM = -6,
+  NTRU_E_UNSUPPORTED = -7
+};
+
+/* ntru_set_option keys */
+enum {
+  NTRU_OPT_PATH = 1,        /* 0 auto, 1 force CUDA-core schedule, 2 force tcgen05 tensor schedule (same-key only) */
+  NTRU_OPT_CHUNK_ROWS = 2   /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
+};
+
+/* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 32768], 8 <= N <= 1024. */
+int ntru_create(ntru_ctx **ctx, int N, int p, int q, int device);
+void ntru_destroy(ntru_ctx *ctx);
+const char *ntru_last_error(const ntru_ctx *ctx);
+const char *ntru_strerror(int code);
+int ntru_set_option(ntru_ctx *ctx, int key, long value);
+/* device row pitch, in elements, of every *_dev array: roundup(N+1, 16) */
+int ntru_pitch(const ntru_ctx *ctx);
+/* number of CUDA kernels this context has launched so far */
+uint64_t ntru_launch_count(const ntru_ctx *ctx);
+/* which schedule the last batch call used: 1 CUDA-core, 2 tcgen05 */
+int ntru_last_path(const ntru_ctx *ctx);
+
+/* this.h = ... (index.js:72-79 result, expanded to N entries in [0,q)) */
+int ntru_set_public_key(ntru_ctx *ctx, const uint16_t *h);
+/* this.f, this.fp (index.js:30-36): f in {-1,0,1}, fp expanded to N entries in [0,p) */
+int ntru_set_private_key(ntru_ctx *ctx, const int8_t *f, const uint8_t *fp);
+
+/* encryptBits, B messages under the context's public key -- index.js:87-110 with r injected.
+ * value = remainderE[0..N); quotientE/remainderE are the VerifyEncrypt witness (N+1 entries per row). */
+int ntru_encrypt_batch(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m,
+                       uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+/* same with messages whose coefficients do not fit a byte (m already reduced into [0,q)) -- index.js:91 */
+int ntru_encrypt_batch_wide(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint16_t *m,
+                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+/* encryptBits with a distinct public key per row: h is B x N */
+int ntru_encrypt_batch_keys(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const uint8_t *m,
+                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+
+/* decryptBits, B ciphertexts under the context's private key -- index.js:111-140.
+ * value = remainder2[0..N); quotient1/remainder1 (mod q) and quotient2/remainder2 (mod p) are the
+ * VerifyDecrypt witness (N+1 entries per row). */
+int ntru_decrypt_batch(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value,
+                       uint16_t *quotient1, uint16_t *remainder1, uint8_t *quotient2, uint8_t *remainder2);
+/* decryptBits with a distinct private key per row: f, fp are B x N */
+int ntru_decrypt_batch_keys(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, const uint16_t *e,
+                            uint8_t *value, uint16_t *quotient1, uint16_t *remainder1,
+                            uint8_t *quotient2, uint8_t *remainder2);
+
+/* fold of addPolynomials(.,.,q) over B ciphertexts -- index.js:235-244, test/reference.test.js:58.  out: N entries */
+int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
+
+/* ---- device-resident variants (pitch = ntru_pitch(ctx) elements; async on ntru_stream(ctx)) ---- */
+/* h_rows == NULL: context key (same-key schedule); else one key per row */
+int ntru_encrypt_dev(ntru_ctx *ctx, size_t B, const uint16_t *h_rows, const uint8_t *r, const uint8_t *m,
+                     uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+int ntru_decrypt_dev(ntru_ctx *ctx, size_t B, const int8_t *f_rows, const uint8_t *fp_rows, const uint16_t *e,
+                     uint8_t *value, uint16_t *quotient1, uint16_t *remainder1,
+                     uint8_t *quotient2, uint8_t *remainder2);
+/* partial[k] += sum_b e[b][k] over this call's rows (uint32 wrap-around is exact mod q); partial has pitch entries */
+int ntru_sum_partial_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial);
+/* out[k] = partial[k] mod q for k < N (and 0 up to pitch) */
+int ntru_sum_finalize_dev(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
+/* generateCustomArray(N, dr, dr).map(-1 -> p-1) for rows [row0, row0+B) -- index.js:89, 461-488:
+ * the same Fisher-Yates shuffle driven by a counter-based generator (seed, row, i) instead of WebCrypto */
+int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
+
+void *ntru_stream(ntru_ctx *ctx);              /* cudaStream_t */
+int ntru_set_stream(ntru_ctx *ctx, void *stream);
+int ntru_sync(ntru_ctx *ctx);
+
+/* pinned host memory for the host-buffer entry points (pageable memory works, but copies then serialise) */
+void *ntru_host_alloc(size_t bytes);
+void ntru_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTRU_B200_H */

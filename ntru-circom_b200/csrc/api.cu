@@ -1,0 +1,454 @@
+// C ABI of libntru_b200.so (include/ntru_b200.h): context, keys, host-buffer pipeline and
+// device-resident entry points.  No CPU compute path exists in this library.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "ntru_internal.cuh"
+
+namespace ntru {
+
+int fail(ntru_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int cuda_fail(ntru_ctx *ctx, cudaError_t e, const char *what) {
+  if (ctx) ctx->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return NTRU_E_CUDA;
+}
+
+namespace {
+
+// One array of a host-buffer call: packed on the host (row = width elements), pitched on the device.
+struct HostArr {
+  const void *in = nullptr;   // host source (inputs)
+  void *out = nullptr;        // host destination (outputs)
+  size_t elem = 1;            // bytes per element
+  size_t width = 0;           // packed elements per row on the host
+  bool used = false;
+};
+
+constexpr int kMaxArr = 10;
+
+// Runs `launch(rows, dev[])` over B rows in chunks, overlapping H2D, kernels and D2H on three streams.
+template <class Launch>
+int run_pipeline(ntru_ctx *ctx, size_t B, HostArr (&arr)[kMaxArr], Launch launch) {
+  const size_t chunk = ctx->chunk_rows;
+  const size_t P = (size_t)ctx->P;
+  const size_t rows_alloc = B < chunk ? B : chunk;
+  for (int s = 0; s < kNumSlots; ++s)
+    for (int a = 0; a < kMaxArr; ++a)
+      if (arr[a].used) NTRU_CUDA(ctx, ctx->slot_bufs[s][a].reserve(rows_alloc * P * arr[a].elem));
+  size_t ci = 0;
+  for (size_t row0 = 0; row0 < B; row0 += chunk, ++ci) {
+    const size_t rows = (B - row0) < chunk ? (B - row0) : chunk;
+    const int s = (int)(ci % kNumSlots);
+    void *dev[kMaxArr];
+    for (int a = 0; a < kMaxArr; ++a) dev[a] = arr[a].used ? ctx->slot_bufs[s][a].ptr : nullptr;
+    if (ci >= (size_t)kNumSlots) NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[s], 0));
+    for (int a = 0; a < kMaxArr; ++a) {
+      if (!arr[a].used || !arr[a].in) continue;
+      const size_t wb = arr[a].width * arr[a].elem;
+      NTRU_CUDA(ctx, cudaMemcpy2DAsync(dev[a], P * arr[a].elem, (const char *)arr[a].in + row0 * wb, wb, wb, rows,
+                                       cudaMemcpyHostToDevice, ctx->s_in));
+    }
+    NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
+    NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
+    if (ci >= (size_t)kNumSlots) NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));
+    int rc = launch(rows, dev);
+    if (rc != NTRU_OK) return rc;
+    NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+    NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[s], 0));
+    for (int a = 0; a < kMaxArr; ++a) {
+      if (!arr[a].used || !arr[a].out) continue;
+      const size_t wb = arr[a].width * arr[a].elem;
+      NTRU_CUDA(ctx, cudaMemcpy2DAsync((char *)arr[a].out + row0 * wb, wb, dev[a], P * arr[a].elem, wb, rows,
+                                       cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
+  }
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NTRU_OK;
+}
+
+void set_in(HostArr &a, const void *p, size_t elem, size_t width) {
+  a.in = p; a.elem = elem; a.width = width; a.used = p != nullptr;
+}
+void set_out(HostArr &a, void *p, size_t elem, size_t width) {
+  a.out = p; a.elem = elem; a.width = width; a.used = p != nullptr;
+}
+
+bool want_tensor(ntru_ctx *ctx, bool same_key, bool ready, int *rc) {
+  *rc = NTRU_OK;
+  if (ctx->opt_path == 1) return false;
+  const bool ok = same_key && ctx->tensor_ok && ready;
+  if (ctx->opt_path == 2 && !ok) {
+    *rc = fail(ctx, NTRU_E_UNSUPPORTED, "tensor schedule forced but not available for this call");
+    return false;
+  }
+  return ok;
+}
+
+int encrypt_dispatch(ntru_ctx *ctx, size_t B, const uint16_t *h_rows, const uint8_t *r, const void *m, int m_wide,
+                     uint16_t *value, uint16_t *quo, uint16_t *rem) {
+  int rc;
+  const bool same_key = h_rows == nullptr;
+  if (same_key && !ctx->has_pub) return fail(ctx, NTRU_E_NOKEY, "public key h is not set");
+  if (want_tensor(ctx, same_key && !m_wide, ctx->km_h.ready, &rc)) {
+    ctx->last_path = 2;
+    return umma_encrypt(ctx, B, r, (const uint8_t *)m, value, quo, rem);
+  }
+  if (rc != NTRU_OK) return rc;
+  ctx->last_path = 1;
+  return launch_encrypt_generic(ctx, B, same_key ? (const uint16_t *)ctx->d_h.ptr : h_rows,
+                                same_key ? 0 : (size_t)ctx->P, r, m, m_wide, value, quo, rem);
+}
+
+int decrypt_dispatch(ntru_ctx *ctx, size_t B, const int8_t *f_rows, const uint8_t *fp_rows, const uint16_t *e,
+                     uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2) {
+  int rc;
+  const bool same_key = f_rows == nullptr && fp_rows == nullptr;
+  if ((f_rows == nullptr) != (fp_rows == nullptr)) return fail(ctx, NTRU_E_PARAM, "f_rows and fp_rows must be given together");
+  if (same_key && !ctx->has_priv) return fail(ctx, NTRU_E_NOKEY, "private key f/fp is not set");
+  if (want_tensor(ctx, same_key, ctx->km_f.ready && ctx->km_fp.ready, &rc)) {
+    ctx->last_path = 2;
+    return umma_decrypt(ctx, B, e, value, q1, r1, q2, r2);
+  }
+  if (rc != NTRU_OK) return rc;
+  ctx->last_path = 1;
+  return launch_decrypt_generic(ctx, B, same_key ? (const int8_t *)ctx->d_f.ptr : f_rows,
+                                same_key ? (const uint8_t *)ctx->d_fp.ptr : fp_rows,
+                                same_key ? 0 : (size_t)ctx->P, e, value, q1, r1, q2, r2);
+}
+
+int check(ntru_ctx *ctx) {
+  if (!ctx) return NTRU_E_PARAM;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+  return NTRU_OK;
+}
+
+}  // namespace
+}  // namespace ntru
+
+using namespace ntru;
+
+extern "C" {
+
+const char *ntru_strerror(int code) {
+  switch (code) {
+    case NTRU_OK: return "ok";
+    case NTRU_E_PARAM: return "bad parameter";
+    case NTRU_E_LENGTH: return "bad length";
+    case NTRU_E_NOKEY: return "key not set";
+    case NTRU_E_CUDA: return "CUDA error";
+    case NTRU_E_NCCL: return "NCCL error";
+    case NTRU_E_NOMEM: return "out of memory";
+    case NTRU_E_UNSUPPORTED: return "unsupported";
+    default: return "unknown error";
+  }
+}
+
+const char *ntru_last_error(const ntru_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ntru_create(ntru_ctx **out, int N, int p, int q, int device) {
+  if (!out) return NTRU_E_PARAM;
+  *out = nullptr;
+  if (p != 3) return NTRU_E_PARAM;
+  if (N < 8 || N > kMaxN) return NTRU_E_PARAM;
+  if (q < 4 || q > 32768 || (q & (q - 1)) != 0) return NTRU_E_PARAM;
+  // fp32 exactness bound of the CUDA-core schedule: N * 2 * (q-1) < 2^24
+  if ((long long)N * 2 * (q - 1) >= (1ll << 24)) return NTRU_E_PARAM;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return NTRU_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return NTRU_E_CUDA;
+  ntru_ctx *ctx = new (std::nothrow) ntru_ctx();
+  if (!ctx) return NTRU_E_NOMEM;
+  ctx->N = N; ctx->p = p; ctx->q = q; ctx->device = device;
+  ctx->logq = 0;
+  while ((1 << ctx->logq) < q) ctx->logq++;
+  ctx->P = ((N + 1 + 15) / 16) * 16;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->own_stream = ok;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int s = 0; ok && s < kNumSlots; ++s) {
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_in[s], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_comp[s], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && ctx->d_h.reserve((size_t)ctx->P * 2) == cudaSuccess;
+  ok = ok && ctx->d_f.reserve((size_t)ctx->P) == cudaSuccess;
+  ok = ok && ctx->d_fp.reserve((size_t)ctx->P) == cudaSuccess;
+  ok = ok && ctx->d_partial.reserve((size_t)ctx->P * 4) == cudaSuccess;
+  if (!ok) {
+    ntru_destroy(ctx);
+    return NTRU_E_CUDA;
+  }
+  umma_init(ctx);
+  *out = ctx;
+  return NTRU_OK;
+}
+
+void ntru_destroy(ntru_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int s = 0; s < kNumSlots; ++s) {
+    if (ctx->ev_in[s]) cudaEventDestroy(ctx->ev_in[s]);
+    if (ctx->ev_comp[s]) cudaEventDestroy(ctx->ev_comp[s]);
+    if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
+    for (auto &b : ctx->slot_bufs[s]) b.release();
+  }
+  ctx->d_h.release(); ctx->d_f.release(); ctx->d_fp.release(); ctx->d_b.release(); ctx->d_partial.release();
+  ctx->km_h.mat.release(); ctx->km_f.mat.release(); ctx->km_fp.mat.release();
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  delete ctx;
+}
+
+int ntru_set_option(ntru_ctx *ctx, int key, long value) {
+  if (!ctx) return NTRU_E_PARAM;
+  switch (key) {
+    case NTRU_OPT_PATH:
+      if (value < 0 || value > 2) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_PATH must be 0, 1 or 2");
+      ctx->opt_path = (int)value;
+      return NTRU_OK;
+    case NTRU_OPT_CHUNK_ROWS:
+      if (value < 128) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_CHUNK_ROWS must be >= 128");
+      ctx->chunk_rows = (size_t)value;
+      return NTRU_OK;
+    default:
+      return fail(ctx, NTRU_E_PARAM, "unknown option");
+  }
+}
+
+int ntru_pitch(const ntru_ctx *ctx) { return ctx ? ctx->P : 0; }
+uint64_t ntru_launch_count(const ntru_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int ntru_last_path(const ntru_ctx *ctx) { return ctx ? ctx->last_path : 0; }
+
+int ntru_set_public_key(ntru_ctx *ctx, const uint16_t *h) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!h) return fail(ctx, NTRU_E_PARAM, "h is NULL");
+  uint16_t tmp[kMaxN + 32];
+  memset(tmp, 0, sizeof tmp);
+  for (int i = 0; i < ctx->N; ++i) {
+    if (h[i] >= ctx->q) return fail(ctx, NTRU_E_PARAM, "h coefficient outside [0,q)");
+    tmp[i] = h[i];
+  }
+  NTRU_CUDA(ctx, cudaMemcpy(ctx->d_h.ptr, tmp, (size_t)ctx->P * 2, cudaMemcpyHostToDevice));
+  ctx->has_pub = true;
+  ctx->km_h.ready = false;
+  if (ctx->tensor_ok) {
+    rc = umma_prepare_public(ctx);
+    if (rc) return rc;
+  }
+  return NTRU_OK;
+}
+
+int ntru_set_private_key(ntru_ctx *ctx, const int8_t *f, const uint8_t *fp) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!f || !fp) return fail(ctx, NTRU_E_PARAM, "f or fp is NULL");
+  int8_t tf[kMaxN + 32];
+  uint8_t tp[kMaxN + 32];
+  memset(tf, 0, sizeof tf);
+  memset(tp, 0, sizeof tp);
+  for (int i = 0; i < ctx->N; ++i) {
+    if (f[i] < -1 || f[i] > 1) return fail(ctx, NTRU_E_PARAM, "f coefficient outside {-1,0,1}");
+    if (fp[i] >= ctx->p) return fail(ctx, NTRU_E_PARAM, "fp coefficient outside [0,p)");
+    tf[i] = f[i];
+    tp[i] = fp[i];
+  }
+  NTRU_CUDA(ctx, cudaMemcpy(ctx->d_f.ptr, tf, (size_t)ctx->P, cudaMemcpyHostToDevice));
+  NTRU_CUDA(ctx, cudaMemcpy(ctx->d_fp.ptr, tp, (size_t)ctx->P, cudaMemcpyHostToDevice));
+  ctx->has_priv = true;
+  ctx->km_f.ready = ctx->km_fp.ready = false;
+  if (ctx->tensor_ok) {
+    rc = umma_prepare_private(ctx);
+    if (rc) return rc;
+  }
+  return NTRU_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+
+static int encrypt_host(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const void *m, int m_wide,
+                        uint16_t *value, uint16_t *quo, uint16_t *rem) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!r || !m) return fail(ctx, NTRU_E_PARAM, "r and m are required");
+  if (B == 0) return NTRU_OK;
+  const size_t N = (size_t)ctx->N;
+  HostArr arr[kMaxArr];
+  set_in(arr[0], h, 2, N);
+  set_in(arr[1], r, 1, N);
+  set_in(arr[2], m, m_wide ? 2 : 1, N);
+  set_out(arr[3], value, 2, N);
+  set_out(arr[4], quo, 2, N + 1);
+  set_out(arr[5], rem, 2, N + 1);
+  return run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
+    return encrypt_dispatch(ctx, rows, (const uint16_t *)dev[0], (const uint8_t *)dev[1], dev[2], m_wide,
+                            (uint16_t *)dev[3], (uint16_t *)dev[4], (uint16_t *)dev[5]);
+  });
+}
+
+int ntru_encrypt_batch(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m, uint16_t *value,
+                       uint16_t *quotientE, uint16_t *remainderE) {
+  return encrypt_host(ctx, B, nullptr, r, m, 0, value, quotientE, remainderE);
+}
+
+int ntru_encrypt_batch_wide(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint16_t *m, uint16_t *value,
+                            uint16_t *quotientE, uint16_t *remainderE) {
+  return encrypt_host(ctx, B, nullptr, r, m, 1, value, quotientE, remainderE);
+}
+
+int ntru_encrypt_batch_keys(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const uint8_t *m,
+                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE) {
+  if (!h) return fail(ctx, NTRU_E_PARAM, "h is NULL");
+  return encrypt_host(ctx, B, h, r, m, 0, value, quotientE, remainderE);
+}
+
+static int decrypt_host(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, const uint16_t *e,
+                        uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!e) return fail(ctx, NTRU_E_PARAM, "e is required");
+  if (B == 0) return NTRU_OK;
+  const size_t N = (size_t)ctx->N;
+  HostArr arr[kMaxArr];
+  set_in(arr[0], f, 1, N);
+  set_in(arr[1], fp, 1, N);
+  set_in(arr[2], e, 2, N);
+  set_out(arr[3], value, 1, N);
+  set_out(arr[4], q1, 2, N + 1);
+  set_out(arr[5], r1, 2, N + 1);
+  set_out(arr[6], q2, 1, N + 1);
+  set_out(arr[7], r2, 1, N + 1);
+  return run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
+    return decrypt_dispatch(ctx, rows, (const int8_t *)dev[0], (const uint8_t *)dev[1], (const uint16_t *)dev[2],
+                            (uint8_t *)dev[3], (uint16_t *)dev[4], (uint16_t *)dev[5], (uint8_t *)dev[6],
+                            (uint8_t *)dev[7]);
+  });
+}
+
+int ntru_decrypt_batch(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uint16_t *quotient1,
+                       uint16_t *remainder1, uint8_t *quotient2, uint8_t *remainder2) {
+  return decrypt_host(ctx, B, nullptr, nullptr, e, value, quotient1, remainder1, quotient2, remainder2);
+}
+
+int ntru_decrypt_batch_keys(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, const uint16_t *e,
+                            uint8_t *value, uint16_t *quotient1, uint16_t *remainder1, uint8_t *quotient2,
+                            uint8_t *remainder2) {
+  if (!f || !fp) return fail(ctx, NTRU_E_PARAM, "f or fp is NULL");
+  return decrypt_host(ctx, B, f, fp, e, value, quotient1, remainder1, quotient2, remainder2);
+}
+
+int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!e || !out) return fail(ctx, NTRU_E_PARAM, "e and out are required");
+  NTRU_CUDA(ctx, cudaMemsetAsync(ctx->d_partial.ptr, 0, (size_t)ctx->P * 4, ctx->stream));
+  if (B > 0) {
+    HostArr arr[kMaxArr];
+    set_in(arr[0], e, 2, (size_t)ctx->N);
+    // the kernel streams whole pitched rows; pad columns land in partial[k >= N], which finalize ignores
+    rc = run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
+      return launch_sum_partial(ctx, rows, (const uint16_t *)dev[0], (uint32_t *)ctx->d_partial.ptr);
+    });
+    if (rc) return rc;
+  }
+  NTRU_CUDA(ctx, ctx->slot_bufs[0][9].reserve((size_t)ctx->P * 2));
+  rc = launch_sum_finalize(ctx, (const uint32_t *)ctx->d_partial.ptr, (uint16_t *)ctx->slot_bufs[0][9].ptr);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaMemcpyAsync(out, ctx->slot_bufs[0][9].ptr, (size_t)ctx->N * 2, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NTRU_OK;
+}
+
+// ---- device-resident entry points -------------------------------------------------------------
+
+int ntru_encrypt_dev(ntru_ctx *ctx, size_t B, const uint16_t *h_rows, const uint8_t *r, const uint8_t *m,
+                     uint16_t *value, uint16_t *quotientE, uint16_t *remainderE) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!r || !m) return fail(ctx, NTRU_E_PARAM, "r and m are required");
+  return encrypt_dispatch(ctx, B, h_rows, r, m, 0, value, quotientE, remainderE);
+}
+
+int ntru_decrypt_dev(ntru_ctx *ctx, size_t B, const int8_t *f_rows, const uint8_t *fp_rows, const uint16_t *e,
+                     uint8_t *value, uint16_t *quotient1, uint16_t *remainder1, uint8_t *quotient2,
+                     uint8_t *remainder2) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!e) return fail(ctx, NTRU_E_PARAM, "e is required");
+  return decrypt_dispatch(ctx, B, f_rows, fp_rows, e, value, quotient1, remainder1, quotient2, remainder2);
+}
+
+int ntru_sum_partial_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!e || !partial) return fail(ctx, NTRU_E_PARAM, "e and partial are required");
+  return launch_sum_partial(ctx, B, e, partial);
+}
+
+int ntru_sum_finalize_dev(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!partial || !out) return fail(ctx, NTRU_E_PARAM, "partial and out are required");
+  return launch_sum_finalize(ctx, partial, out);
+}
+
+int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!r) return fail(ctx, NTRU_E_PARAM, "r is NULL");
+  // index.js:462-464
+  if (dr < 0 || 2 * dr > ctx->N) return fail(ctx, NTRU_E_PARAM, "The total of 1s and -1s cannot exceed the array length.");
+  return launch_sample_r(ctx, B, dr, seed, row0, r);
+}
+
+void *ntru_stream(ntru_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int ntru_set_stream(ntru_ctx *ctx, void *stream) {
+  if (!ctx) return NTRU_E_PARAM;
+  if (ctx->own_stream && ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  ctx->stream = (cudaStream_t)stream;
+  ctx->own_stream = false;
+  return NTRU_OK;
+}
+
+int ntru_sync(ntru_ctx *ctx) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NTRU_OK;
+}
+
+void *ntru_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void ntru_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

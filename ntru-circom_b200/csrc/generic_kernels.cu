@@ -1,0 +1,431 @@
+// CUDA-core schedule: one CTA per ciphertext, operands resident in shared memory.
+//
+// Used for distinct-key batches (every row brings its own h, or f and fp), for wide
+// messages, and as the on-GPU cross-check of the tcgen05 schedule.  Also holds the
+// HBM-streaming ciphertext sum and the device sampler for r.
+//
+// What is computed (closed form of the reference):
+//   encryptBits  (index.js:87-110):  c = lin(r,h) + m  mod q;  lo[k] = c[k], hi[k] = c[k+N]
+//       remainderE[k] = (lo[k] + hi[k]) mod q,  quotientE[k] = (-hi[k]) mod q
+//   decryptBits  (index.js:111-140): the same split for a = lin(f,e) mod q, then
+//       b[k] = (r1[k] + [r1[k] > q/2]) mod 3  (the reference's lift, index.js:117),
+//       and the same split for c = lin(fp,b) mod 3.
+//   dividePolynomials(., 1 - x^N, .) (index.js:358-401) is that lo/hi split: the quotient
+//       is -hi, the remainder is lo + hi; multiplyPolynomials (index.js:319-355) is the
+//       exact integer product (the float64 FFT's rounding margin is < 1e-4).
+//
+// Arithmetic: fp32 FMA on integer-valued operands.  Every partial sum is an integer of
+// magnitude <= N*2*(q-1) < 2^24 (N <= 1024, q <= 8192), so fp32 is exact; it runs on both
+// FMA pipes where IMAD has one.  (q = 16384/32768 would overflow 2^24: ntru_create rejects
+// them for this schedule.)
+//
+// Thread mapping: thread c owns outputs k = 8c .. 8c+7.  The i-loop runs over blocks of 8
+// multiplier coefficients; the window of 15 multiplicand values slides by 8 per block (two
+// LDS.128), the 8 multiplier values are a warp-wide broadcast.  Contributions with i <= k
+// belong to lo, with i > k (index k - i + N of the cyclic extension) to hi; the switch
+// happens inside block b == c, where the accumulator is snapshotted.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ntru_internal.cuh"
+
+namespace ntru {
+
+namespace {
+
+constexpr int T = 8;   // outputs per thread
+
+// lo[t] = sum_{i<=k} mul[i] * win[k-i],  hi[t] = sum_{i>k} mul[i] * win[k-i+N],  k = 8c+t.
+// S[y] = win[(y + 1 - 8NB) mod N] for y in [0,16NB);  mulS[i] = mul[i] (0 for i >= N), i in [0,8NB).
+__device__ __forceinline__ void conv8(const float *__restrict__ S, const float *__restrict__ mulS, int NB, int c,
+                                      float (&lo)[T], float (&hi)[T]) {
+  float acc[T], L[T], H[T], rv[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    acc[t] = 0.f;
+    lo[t] = 0.f;
+  }
+  int y0 = T * (c - 1 + NB);
+  {
+    const float4 a = *reinterpret_cast<const float4 *>(S + y0 + 8);
+    const float4 b = *reinterpret_cast<const float4 *>(S + y0 + 12);
+    H[0] = a.x; H[1] = a.y; H[2] = a.z; H[3] = a.w;
+    H[4] = b.x; H[5] = b.y; H[6] = b.z; H[7] = b.w;
+  }
+#pragma unroll 2
+  for (int b = 0; b < NB; ++b) {
+    {
+      const float4 a0 = *reinterpret_cast<const float4 *>(S + y0);
+      const float4 a1 = *reinterpret_cast<const float4 *>(S + y0 + 4);
+      L[0] = a0.x; L[1] = a0.y; L[2] = a0.z; L[3] = a0.w;
+      L[4] = a1.x; L[5] = a1.y; L[6] = a1.z; L[7] = a1.w;
+      const float4 r0 = *reinterpret_cast<const float4 *>(mulS + T * b);
+      const float4 r1 = *reinterpret_cast<const float4 *>(mulS + T * b + 4);
+      rv[0] = r0.x; rv[1] = r0.y; rv[2] = r0.z; rv[3] = r0.w;
+      rv[4] = r1.x; rv[5] = r1.y; rv[6] = r1.z; rv[7] = r1.w;
+    }
+    // window W[w] = w < 8 ? L[w] : H[w-8];  term (t, di) uses W[7 + t - di]
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int di = 0; di <= t; ++di) {
+        const int w = 7 + t - di;                 // 7..14
+        acc[t] = fmaf(rv[di], w < 8 ? L[w] : H[w - 8], acc[t]);
+      }
+    }
+    if (b == c) {                                  // i <= k ends here: snapshot lo, restart for hi
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        lo[t] = acc[t];
+        acc[t] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int di = t + 1; di < T; ++di) acc[t] = fmaf(rv[di], L[7 + t - di], acc[t]);   // w in 0..6
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) H[t] = L[t];
+    y0 -= T;
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) hi[t] = acc[t];
+}
+
+__device__ __forceinline__ uint32_t mod3_u16(uint32_t v) {   // v < 65536
+  return v - 3u * ((v * 0xAAABu) >> 17);
+}
+
+__device__ __forceinline__ uint4 pack8_u16(const uint32_t (&v)[T]) {
+  return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+
+__device__ __forceinline__ uint2 pack8_u8(const uint32_t (&v)[T]) {
+  return make_uint2(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24),
+                    v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24));
+}
+
+struct EncArgs {
+  int N, P, NB;
+  uint32_t qmask;
+  size_t B;
+  const uint16_t *h;
+  size_t h_stride;
+  const uint8_t *r;
+  const void *m;
+  uint16_t *value, *quo, *rem;
+};
+
+template <bool kWideM>
+__global__ void __launch_bounds__(160) k_encrypt_generic(const EncArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, P = a.P, NB = a.NB;
+  float *S = smem;
+  float *mulS = smem + 16 * NB;
+  const int c = threadIdx.x;
+  const bool active = c < NB && T * c < P;
+  for (size_t row = blockIdx.x; row < a.B; row += gridDim.x) {
+    const uint16_t *h = a.h + row * a.h_stride;
+    const uint8_t *r = a.r + row * (size_t)P;
+    for (int y = threadIdx.x; y < 16 * NB; y += blockDim.x) {
+      const int j = (y + 1 - 8 * NB + 2 * N) % N;
+      S[y] = (float)h[j];
+    }
+    for (int i = threadIdx.x; i < 8 * NB; i += blockDim.x) mulS[i] = i < N ? (float)r[i] : 0.f;
+    __syncthreads();
+    if (active) {
+      float lo[T], hi[T];
+      conv8(S, mulS, NB, c, lo, hi);
+      uint32_t mv[T];
+      if (kWideM) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(a.m) + row * (size_t)P + T * c);
+        mv[0] = w.x & 0xffff; mv[1] = w.x >> 16; mv[2] = w.y & 0xffff; mv[3] = w.y >> 16;
+        mv[4] = w.z & 0xffff; mv[5] = w.z >> 16; mv[6] = w.w & 0xffff; mv[7] = w.w >> 16;
+      } else {
+        const uint2 w = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a.m) + row * (size_t)P + T * c);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          mv[t] = (w.x >> (8 * t)) & 0xff;
+          mv[4 + t] = (w.y >> (8 * t)) & 0xff;
+        }
+      }
+      uint32_t rem[T], quo[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int k = T * c + t;
+        const int l = __float2int_rn(lo[t]) + (int)mv[t];
+        const int hh = __float2int_rn(hi[t]);
+        const bool in = k < N;
+        rem[t] = in ? ((uint32_t)(l + hh) & a.qmask) : 0u;
+        quo[t] = in ? ((uint32_t)(-hh) & a.qmask) : 0u;
+      }
+      const size_t off = row * (size_t)P + T * c;
+      if (a.value) *reinterpret_cast<uint4 *>(a.value + off) = pack8_u16(rem);
+      if (a.rem) *reinterpret_cast<uint4 *>(a.rem + off) = pack8_u16(rem);
+      if (a.quo) *reinterpret_cast<uint4 *>(a.quo + off) = pack8_u16(quo);
+    }
+    __syncthreads();
+  }
+}
+
+struct DecArgs {
+  int N, P, NB, q;
+  uint32_t qmask;
+  size_t B;
+  const int8_t *f;
+  const uint8_t *fp;
+  size_t key_stride;
+  const uint16_t *e;
+  uint8_t *value, *q2, *r2;
+  uint16_t *q1, *r1;
+};
+
+__global__ void __launch_bounds__(160) k_decrypt_generic(const DecArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = a.N, P = a.P, NB = a.NB;
+  float *S = smem;
+  float *mulS = smem + 16 * NB;
+  const int c = threadIdx.x;
+  const bool active = c < NB && T * c < P;
+  const uint32_t halfq = (uint32_t)a.q >> 1;
+  for (size_t row = blockIdx.x; row < a.B; row += gridDim.x) {
+    const int8_t *f = a.f + row * a.key_stride;
+    const uint8_t *fp = a.fp + row * a.key_stride;
+    const uint16_t *e = a.e + row * (size_t)P;
+    // product 1: a = lin(f, e) -- window = e, multiplier = f
+    for (int y = threadIdx.x; y < 16 * NB; y += blockDim.x) S[y] = (float)e[(y + 1 - 8 * NB + 2 * N) % N];
+    for (int i = threadIdx.x; i < 8 * NB; i += blockDim.x) mulS[i] = i < N ? (float)f[i] : 0.f;
+    __syncthreads();
+    float lo[T], hi[T];
+    uint32_t bv[T];
+    if (active) {
+      conv8(S, mulS, NB, c, lo, hi);
+      uint32_t rem[T], quo[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int k = T * c + t;
+        const int l = __float2int_rn(lo[t]);
+        const int hh = __float2int_rn(hi[t]);
+        const bool in = k < N;
+        rem[t] = in ? ((uint32_t)(l + hh) & a.qmask) : 0u;
+        quo[t] = in ? ((uint32_t)(-hh) & a.qmask) : 0u;
+        bv[t] = mod3_u16(rem[t] + (rem[t] > halfq ? 1u : 0u));   // index.js:117
+      }
+      const size_t off = row * (size_t)P + T * c;
+      if (a.r1) *reinterpret_cast<uint4 *>(a.r1 + off) = pack8_u16(rem);
+      if (a.q1) *reinterpret_cast<uint4 *>(a.q1 + off) = pack8_u16(quo);
+    }
+    __syncthreads();
+    // product 2: c = lin(fp, b) -- window = fp, multiplier = b
+    for (int y = threadIdx.x; y < 16 * NB; y += blockDim.x) S[y] = (float)fp[(y + 1 - 8 * NB + 2 * N) % N];
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) mulS[T * c + t] = (float)bv[t];
+    }
+    __syncthreads();
+    if (active) {
+      conv8(S, mulS, NB, c, lo, hi);
+      uint32_t rem[T], quo[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int k = T * c + t;
+        const uint32_t l3 = mod3_u16((uint32_t)__float2int_rn(lo[t]));
+        const uint32_t h3 = mod3_u16((uint32_t)__float2int_rn(hi[t]));
+        const bool in = k < N;
+        rem[t] = in ? mod3_u16(l3 + h3) : 0u;
+        quo[t] = in ? mod3_u16(3u - h3) : 0u;
+      }
+      const size_t off = row * (size_t)P + T * c;
+      if (a.value) *reinterpret_cast<uint2 *>(a.value + off) = pack8_u8(rem);
+      if (a.r2) *reinterpret_cast<uint2 *>(a.r2 + off) = pack8_u8(rem);
+      if (a.q2) *reinterpret_cast<uint2 *>(a.q2 + off) = pack8_u8(quo);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- homomorphic ciphertext sum: column sums of B x N uint16 rows -------------------------------
+// Pure HBM streaming (2N bytes per ciphertext).  Thread (vx, ry) owns the 8 columns of 16-byte
+// vector vx and rows ry, ry+RY, ...; uint32 accumulation wraps mod 2^32, which is exact mod q | 2^16.
+constexpr int kSumRows = 4;      // rows per CTA iteration (fewer when a row has > 128 vectors)
+constexpr int kSumUnroll = 4;    // independent 16-byte loads in flight per thread
+
+__global__ void __launch_bounds__(512) k_sum_partial(const uint16_t *__restrict__ e, size_t B, int P,
+                                                      uint32_t *__restrict__ partial) {
+  extern __shared__ __align__(16) uint32_t red[];
+  const int VX = P / 8;
+  const int vx = threadIdx.x, ry = threadIdx.y;
+  uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+  const int RY = blockDim.y;
+  const size_t step = (size_t)gridDim.x * RY;
+  size_t row = (size_t)blockIdx.x * RY + ry;
+  const uint4 *base = reinterpret_cast<const uint4 *>(e) + vx;
+  for (; row + (kSumUnroll - 1) * step < B; row += kSumUnroll * step) {
+    uint4 v[kSumUnroll];
+#pragma unroll
+    for (int u = 0; u < kSumUnroll; ++u) v[u] = __ldcs(base + (row + u * step) * (size_t)VX);
+#pragma unroll
+    for (int u = 0; u < kSumUnroll; ++u) {
+      lo[0] += v[u].x; hi[0] += v[u].x >> 16;
+      lo[1] += v[u].y; hi[1] += v[u].y >> 16;
+      lo[2] += v[u].z; hi[2] += v[u].z >> 16;
+      lo[3] += v[u].w; hi[3] += v[u].w >> 16;
+    }
+  }
+  for (; row < B; row += step) {
+    const uint4 v = __ldcs(base + row * (size_t)VX);
+    lo[0] += v.x; hi[0] += v.x >> 16;
+    lo[1] += v.y; hi[1] += v.y >> 16;
+    lo[2] += v.z; hi[2] += v.z >> 16;
+    lo[3] += v.w; hi[3] += v.w >> 16;
+  }
+  // low halves: only bits [0,16) of lo[] are meaningful (the high half holds the odd column's sum
+  // plus carries); hi[] are clean sums of the odd columns.
+  uint32_t *mine = red + ((size_t)ry * VX + vx) * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mine[2 * j] = lo[j] & 0xffffu;
+    mine[2 * j + 1] = hi[j];
+  }
+  __syncthreads();
+  if (ry == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t s = 0;
+      for (int y = 0; y < RY; ++y) s += red[((size_t)y * VX + vx) * 8 + j];
+      atomicAdd(partial + vx * 8 + j, s);
+    }
+  }
+}
+
+__global__ void k_sum_finalize(const uint32_t *__restrict__ partial, int N, int P, uint32_t qmask,
+                               uint16_t *__restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < P) out[k] = k < N ? (uint16_t)(partial[k] & qmask) : (uint16_t)0;
+}
+
+// ---- device sampler for r: generateCustomArray(N, dr, dr).map(-1 -> 2) -------------------------
+// Same algorithm as index.js:461-488 (dr ones, dr "minus ones", Fisher-Yates from the top with
+// j = rand32 % (i+1)); the WebCrypto draw is replaced by a counter-based generator so that any
+// shard of any batch is reproducible: rand32(seed,row,i) = splitmix64(seed + G*(row*2048+i)) >> 32.
+__device__ __host__ __forceinline__ uint32_t sampler_rand32(uint64_t seed, uint64_t row, uint32_t i) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (row * 2048ull + i);
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+
+constexpr int kSampleRows = 64;   // rows (threads) per CTA
+
+__global__ void __launch_bounds__(kSampleRows) k_sample_r(int N, int P, int dr, uint64_t seed, uint64_t row0,
+                                                          size_t B, uint8_t *__restrict__ r) {
+  extern __shared__ __align__(16) uint8_t arr[];
+  const int stride = P + 4;                       // bytes; (P+4)/4 is odd, so rows start in distinct banks
+  const size_t first = (size_t)blockIdx.x * kSampleRows;
+  const size_t row = first + threadIdx.x;
+  uint8_t *mine = arr + (size_t)threadIdx.x * stride;
+  if (row < B) {
+    for (int i = 0; i < P; ++i) mine[i] = i < dr ? 1 : (i < 2 * dr ? 2 : 0);
+    for (int i = N - 1; i > 0; --i) {
+      const uint32_t j = sampler_rand32(seed, row0 + row, (uint32_t)i) % (uint32_t)(i + 1);
+      const uint8_t a = mine[i], b = mine[j];
+      mine[i] = b;
+      mine[j] = a;
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out: 4-byte words, one row after another
+  const int wpr = P / 4;
+  const size_t rows_here = (B - first) < (size_t)kSampleRows ? (B - first) : (size_t)kSampleRows;
+  for (size_t idx = threadIdx.x; idx < rows_here * wpr; idx += blockDim.x) {
+    const size_t rr = idx / wpr;
+    const int w = (int)(idx % wpr);
+    reinterpret_cast<uint32_t *>(r + (first + rr) * (size_t)P)[w] =
+        *reinterpret_cast<const uint32_t *>(arr + rr * stride + 4 * w);
+  }
+}
+
+}  // namespace
+
+static int block_threads(int NB) { return ((NB + 31) / 32) * 32; }
+
+int launch_encrypt_generic(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r,
+                           const void *m, int m_wide, uint16_t *value, uint16_t *quo, uint16_t *rem) {
+  if (B == 0) return NTRU_OK;
+  EncArgs a;
+  a.N = ctx->N; a.P = ctx->P; a.NB = (ctx->N + 1 + T - 1) / T;
+  a.qmask = (uint32_t)ctx->q - 1; a.B = B; a.h = h; a.h_stride = h_stride; a.r = r; a.m = m;
+  a.value = value; a.quo = quo; a.rem = rem;
+  const int threads = block_threads(a.NB);
+  const size_t smem = (size_t)24 * a.NB * sizeof(float);
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  const unsigned grid = (unsigned)(B < cap ? B : cap);
+  if (m_wide)
+    k_encrypt_generic<true><<<grid, threads, smem, ctx->stream>>>(a);
+  else
+    k_encrypt_generic<false><<<grid, threads, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_decrypt_generic(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, size_t key_stride,
+                           const uint16_t *e, uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2,
+                           uint8_t *r2) {
+  if (B == 0) return NTRU_OK;
+  DecArgs a;
+  a.N = ctx->N; a.P = ctx->P; a.NB = (ctx->N + 1 + T - 1) / T; a.q = ctx->q;
+  a.qmask = (uint32_t)ctx->q - 1; a.B = B; a.f = f; a.fp = fp; a.key_stride = key_stride; a.e = e;
+  a.value = value; a.q1 = q1; a.r1 = r1; a.q2 = q2; a.r2 = r2;
+  const int threads = block_threads(a.NB);
+  const size_t smem = (size_t)24 * a.NB * sizeof(float);
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  const unsigned grid = (unsigned)(B < cap ? B : cap);
+  k_decrypt_generic<<<grid, threads, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial) {
+  if (B == 0) return NTRU_OK;
+  const int VX = ctx->P / 8;
+  const int RY = VX * kSumRows <= 512 ? kSumRows : 512 / VX;
+  dim3 block(VX, RY);
+  const size_t smem = (size_t)VX * RY * 8 * sizeof(uint32_t);
+  size_t blocks = (B + RY - 1) / RY;
+  const size_t cap = (size_t)ctx->sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  k_sum_partial<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, partial);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out) {
+  k_sum_finalize<<<(ctx->P + 255) / 256, 256, 0, ctx->stream>>>(partial, ctx->N, ctx->P, (uint32_t)ctx->q - 1, out);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r) {
+  if (B == 0) return NTRU_OK;
+  const size_t smem = (size_t)kSampleRows * (ctx->P + 4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NTRU_CUDA(ctx, cudaFuncSetAttribute(k_sample_r, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const size_t blocks = (B + kSampleRows - 1) / kSampleRows;
+  k_sample_r<<<(unsigned)blocks, kSampleRows, smem, ctx->stream>>>(ctx->N, ctx->P, dr, seed, row0, B, r);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+}  // namespace ntru

@@ -1,0 +1,99 @@
+// Internal declarations shared by the translation units of libntru_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ntru_b200.h"
+
+namespace ntru {
+
+constexpr int kMaxN = 1024;
+constexpr int kNumSlots = 2;   // double-buffered host<->device pipeline
+
+// One device allocation that only ever grows.
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+// Operand matrices of the tcgen05 schedule for one fixed key polynomial (see umma_kernels.cu).
+struct KeyMatrix {
+  DevBuf mat;            // [2*ncols_pad][klen] bytes, K-major
+  alignas(64) unsigned char tmap[128];   // CUtensorMap
+  bool ready = false;
+  int limbs = 0, klen = 0, nchunks = 0, chunk_cols = 0;
+};
+
+}  // namespace ntru
+
+struct ntru_ctx {
+  int N = 0, p = 0, q = 0, logq = 0, device = 0;
+  int P = 0;                       // row pitch (elements) of every device array
+  cudaStream_t stream = nullptr;   // compute stream
+  bool own_stream = false;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[ntru::kNumSlots] = {}, ev_comp[ntru::kNumSlots] = {}, ev_out[ntru::kNumSlots] = {};
+  bool has_pub = false, has_priv = false;
+  ntru::DevBuf d_h, d_f, d_fp;     // context keys, P entries each
+  ntru::KeyMatrix km_h, km_f, km_fp;
+  ntru::DevBuf d_b;                // lifted polynomial b between the two decrypt products (tensor schedule)
+  ntru::DevBuf slot_bufs[ntru::kNumSlots][10];
+  ntru::DevBuf d_partial;
+  size_t chunk_rows = 32768;
+  int opt_path = 0;
+  int last_path = 0;
+  int sm_count = 148;
+  bool tensor_ok = false;          // device is sm_100 and the tcgen05 schedule initialised
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace ntru {
+
+int fail(ntru_ctx *ctx, int code, const std::string &msg);
+int cuda_fail(ntru_ctx *ctx, cudaError_t e, const char *what);
+
+#define NTRU_CUDA(ctx, expr)                                        \
+  do {                                                              \
+    cudaError_t _e = (expr);                                        \
+    if (_e != cudaSuccess) return ntru::cuda_fail(ctx, _e, #expr);  \
+  } while (0)
+
+// ---- CUDA-core schedule (generic_kernels.cu) ----
+int launch_encrypt_generic(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r,
+                           const void *m, int m_wide, uint16_t *value, uint16_t *quo, uint16_t *rem);
+int launch_decrypt_generic(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, size_t key_stride,
+                           const uint16_t *e, uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2,
+                           uint8_t *r2);
+int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial);
+int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
+int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
+
+// ---- tcgen05 schedule (umma_kernels.cu) ----
+int umma_init(ntru_ctx *ctx);                    // probes the device, sets ctx->tensor_ok
+int umma_prepare_public(ntru_ctx *ctx);          // builds km_h from d_h
+int umma_prepare_private(ntru_ctx *ctx);         // builds km_f, km_fp from d_f, d_fp
+int umma_encrypt(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m, uint16_t *value, uint16_t *quo,
+                 uint16_t *rem);
+int umma_decrypt(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uint16_t *q1, uint16_t *r1,
+                 uint8_t *q2, uint8_t *r2);
+
+}  // namespace ntru

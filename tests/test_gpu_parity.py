@@ -1,0 +1,290 @@
+"""Parity of the CUDA engine (through the C ABI) against the oracle.  Bit-exact: integer work."""
+import random
+
+import numpy as np
+import pytest
+
+import ntru_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+CFGS = ["tiny17", "default167", "hps509", "hps677", "hps821", "hrss701"]
+ENC_KEYS = ("value", "quotientE", "remainderE")
+DEC_KEYS = ("value", "quotient1", "remainder1", "quotient2", "remainder2")
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import ntru_circom_b200 as nb
+    return nb
+
+
+@pytest.fixture(scope="module")
+def engines(nb, golden):
+    cache = {}
+
+    def get(cfg):
+        if cfg not in cache:
+            g = golden(cfg)
+            eng = nb.Engine(int(g["N"]), int(g["p"]), int(g["q"]), 0)
+            eng.set_public_key(g["h"])
+            eng.set_private_key(g["f"], g["fp"])
+            cache[cfg] = eng
+        return cache[cfg]
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+def _paths(nb, eng):
+    """Schedules to test: the CUDA-core one always, the tcgen05 one when the library built it."""
+    out = [nb.PATH_CUDA_CORE]
+    try:
+        eng.set_path(nb.PATH_TENSOR)
+        g = np.zeros((1, eng.N), dtype=np.uint8)
+        eng.encrypt_batch(g, g, witness=False)
+        out.append(nb.PATH_TENSOR)
+    except nb.NtruError:
+        pass
+    eng.set_path(nb.PATH_AUTO)
+    return out
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_golden_vectors_both_schedules(cfg, nb, engines, golden):
+    g, eng = golden(cfg), engines(cfg)
+    for path in _paths(nb, eng):
+        eng.set_path(path)
+        enc = eng.encrypt_batch(g["r"], g["m"])
+        assert eng.last_path == path
+        for k in ENC_KEYS:
+            assert np.array_equal(enc[k], g[k]), (cfg, path, k)
+        dec = eng.decrypt_batch(g["value"])
+        for k, gk in zip(DEC_KEYS, ("dec_value",) + DEC_KEYS[1:]):
+            assert np.array_equal(dec[k], g[gk]), (cfg, path, k)
+        assert np.array_equal(eng.sum(g["value"]), g["sum"])
+    eng.set_path(nb.PATH_AUTO)
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_random_batch_vs_oracle(cfg, nb, engines, golden):
+    """Seeded random batch with a ragged size (not a multiple of any tile), all schedules."""
+    g, eng = golden(cfg), engines(cfg)
+    N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
+    B = 301 if N > 200 else 1000
+    rng = np.random.default_rng(123)
+    r = o.sample_ternary_rows(B, N, dr, dr, rng).astype(np.uint8)
+    m = rng.integers(0, 3, size=(B, N)).astype(np.uint8)
+    m[0] = 0
+    r[1] = 0                                    # degenerate randomness: e == m
+    m[2] = 255                                  # largest byte message coefficients
+    m[3, N // 3:] = 0
+    want_e = o.encrypt_batch(g["h"].astype(np.int64), r, m, q)
+    want_d = o.decrypt_batch(g["f"].astype(np.int64), g["fp"].astype(np.int64), want_e["value"], q, p)
+    for path in _paths(nb, eng):
+        eng.set_path(path)
+        enc = eng.encrypt_batch(r, m)
+        for k in ENC_KEYS:
+            assert np.array_equal(enc[k], want_e[k]), (cfg, path, k)
+        dec = eng.decrypt_batch(enc["value"])
+        for k in DEC_KEYS:
+            assert np.array_equal(dec[k], want_d[k]), (cfg, path, k)
+        # value-only mode produces the same ciphertext / plaintext
+        assert np.array_equal(eng.encrypt_batch(r, m, witness=False)["value"], want_e["value"])
+        assert np.array_equal(eng.decrypt_batch(enc["value"], witness=False)["value"], want_d["value"])
+    eng.set_path(nb.PATH_AUTO)
+    if q % 3 == 2:                              # the reference's lift is the true centred lift only then
+        ok = (m[4:] < 3).all(axis=1)
+        assert np.array_equal(want_d["value"][4:][ok], m[4:][ok])
+
+
+@pytest.mark.parametrize("cfg", ["default167", "hps677"])
+def test_distinct_keys(cfg, nb, engines, golden):
+    """Config 3: a different key per row (CUDA-core schedule), full witness; 8 valid keys + random ones."""
+    g, eng = golden(cfg), engines(cfg)
+    N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
+    keys = [o.make_key(cfg, 100 + i) for i in range(8)]
+    rng = np.random.default_rng(5)
+    B = 8 + 40
+    h = np.zeros((B, N), dtype=np.int64)
+    f = np.zeros((B, N), dtype=np.int64)
+    fp = np.zeros((B, N), dtype=np.int64)
+    for i, k in enumerate(keys):
+        h[i], f[i], fp[i] = o.expand_array(k.h, N), k.f, o.expand_array(k.fp, N)
+    h[8:] = rng.integers(0, q, size=(B - 8, N))
+    f[8:] = o.sample_ternary_rows(B - 8, N, dr, dr - 1, rng, neg_value=-1)
+    fp[8:] = rng.integers(0, p, size=(B - 8, N))
+    r = o.sample_ternary_rows(B, N, dr, dr, rng)
+    m = rng.integers(0, 2, size=(B, N))
+    want_e = o.encrypt_batch(h, r, m, q)
+    enc = eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8), h=h.astype(np.uint16))
+    assert eng.last_path == nb.PATH_CUDA_CORE
+    for k in ENC_KEYS:
+        assert np.array_equal(enc[k], want_e[k]), k
+    want_d = o.decrypt_batch(f, fp, want_e["value"], q, p)
+    dec = eng.decrypt_batch(enc["value"], f=f.astype(np.int8), fp=fp.astype(np.uint8))
+    for k in DEC_KEYS:
+        assert np.array_equal(dec[k], want_d[k]), k
+    assert np.array_equal(dec["value"][:8], m[:8])           # valid keys round-trip (q % 3 == 2 here)
+
+
+def test_empty_batch_and_errors(nb, engines):
+    eng = engines("default167")
+    z8 = np.zeros((0, 167), dtype=np.uint8)
+    out = eng.encrypt_batch(z8, z8)
+    assert out["value"].shape == (0, 167)
+    assert eng.decrypt_batch(np.zeros((0, 167), dtype=np.uint16))["value"].shape == (0, 167)
+    assert np.array_equal(eng.sum(np.zeros((0, 167), dtype=np.uint16)), np.zeros(167, dtype=np.uint16))
+    with pytest.raises(IndexError):
+        eng.encrypt_batch(np.zeros((2, 168), dtype=np.uint8), np.zeros((2, 168), dtype=np.uint8))
+    fresh = nb.Engine(167, 3, 128, 0)
+    with pytest.raises(nb.NtruError, match="public key"):
+        fresh.encrypt_batch(np.zeros((1, 167), dtype=np.uint8), np.zeros((1, 167), dtype=np.uint8))
+    with pytest.raises(nb.NtruError, match="private key"):
+        fresh.decrypt_batch(np.zeros((1, 167), dtype=np.uint16))
+    with pytest.raises(nb.NtruError):
+        fresh.set_public_key(np.full(167, 128, dtype=np.uint16))      # coefficient outside [0,q)
+    fresh.close()
+
+
+def test_wide_messages(nb, engines, golden):
+    """m coefficients >= 256 (the reference reduces any integer mod q, index.js:91)."""
+    g, eng = golden("hps509"), engines("hps509")
+    N, q = 509, 2048
+    rng = np.random.default_rng(8)
+    r = o.sample_ternary_rows(5, N, 169, 169, rng).astype(np.uint8)
+    m = rng.integers(0, q, size=(5, N))
+    want = o.encrypt_batch(g["h"].astype(np.int64), r, m, q)
+    enc = eng.encrypt_batch(r, m.astype(np.uint16))
+    for k in ENC_KEYS:
+        assert np.array_equal(enc[k], want[k]), k
+
+
+@pytest.mark.parametrize("cfg", ["tiny17", "default167", "hrss701"])
+def test_class_api_matches_reference_objects(cfg, nb, golden):
+    """encryptBits/decryptBits return the same {value, inputs, params} as the oracle's class NTRU."""
+    g = golden(cfg)
+    opts = dict(o.CONFIGS[cfg], f=g["f"].tolist(), fp=o.trim_polynomial(g["fp"].tolist()),
+                fq=o.trim_polynomial(g["fq"].tolist()), g=g["g"].tolist(), h=o.trim_polynomial(g["h"].tolist()))
+    ref = o.NTRU(dict(opts), literal=cfg == "tiny17")
+    mine = nb.NTRU(dict(opts))
+    m = [1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1]           # test/circuits.test.js:258
+    r = ref.sample_r()
+    a, b = ref.encryptBits(m, r), mine.encryptBits(m, r)
+    assert dict(b) == a
+    assert b["input"] is b["inputs"]
+    assert o.verify_encrypt(b["inputs"], b["params"])
+    da, db = ref.decryptBits(a["value"]), mine.decryptBits(b["value"])
+    assert dict(db) == da
+    assert o.verify_decrypt(db["inputs"], db["params"])
+    assert db["value"] == m
+    # tamper (test/circuits.test.js:296-301)
+    db["inputs"]["remainder2"][0] += 1
+    assert not o.verify_decrypt(db["inputs"], db["params"])
+    with pytest.raises(IndexError):
+        mine.encryptBits([1] * (mine.N + 1))
+    with pytest.raises(IndexError):
+        mine.decryptBits([1] * (mine.N + 1))
+
+
+def test_string_roundtrip_and_wrong_key(nb):
+    # test/reference.test.js:6-25
+    k = nb.NTRU()
+    k.generatePrivateKeyF()
+    k.generateNewPublicKeyGH()
+    e = k.encryptStr("Hello World")
+    assert k.decryptStr(e) == "Hello World"
+    other = nb.NTRU()
+    other.generatePrivateKeyF()
+    assert other.decryptStr(e) != "Hello World"
+
+
+def test_large_key_string_roundtrip(nb):
+    # test/reference.test.js:27-44
+    d = 701 // 3
+    k = nb.NTRU({"N": 701, "q": 8192, "df": d, "dg": d, "dr": d})
+    k.generatePrivateKeyF()
+    k.generateNewPublicKeyGH()
+    assert k.decryptStr(k.encryptStr("Big polys")) == "Big polys"
+
+
+def test_additive_homomorphism(nb, golden):
+    # test/reference.test.js:48-61 ("this test may fail" upstream: use a fixed valid key)
+    g = golden("default167")
+    k = nb.NTRU(dict(o.CONFIGS["default167"], f=g["f"].tolist(), fp=o.trim_polynomial(g["fp"].tolist()),
+                     h=o.trim_polynomial(g["h"].tolist())))
+    e1 = k.encryptBits([1, 2, 1, 0, 1])["value"]
+    e2 = k.encryptBits([0, 1, 1, 1, 0, 1, 0, 1])["value"]
+    s = nb.addPolynomials(e1, e2, k.q)
+    es = np.zeros((2, k.N), dtype=np.uint16)
+    es[0, : len(e1)] = e1
+    es[1, : len(e2)] = e2
+    assert k.sumCiphertexts(es) == s == o.sum_ciphertexts([e1, e2], k.q)
+    assert k.decryptBits(s)["value"] == [1, 0, 2, 1, 1, 1, 0, 1]
+
+
+def test_sum_many_rows(nb, engines):
+    """Config 5 shape at reduced count: column sums of uniform rows mod q, plus linearity."""
+    eng = engines("hrss701")
+    rng = np.random.default_rng(3)
+    e = rng.integers(0, 8192, size=(20011, 701), dtype=np.uint16)
+    want = o.sum_batch(e, 8192)
+    assert np.array_equal(eng.sum(e), want)
+    a, b = eng.sum(e[:9000]), eng.sum(e[9000:])
+    assert np.array_equal((a.astype(np.int64) + b) % 8192, want)
+
+
+def test_device_sampler_matches_host_fisher_yates(nb, engines):
+    torch = pytest.importorskip("torch")
+    eng = engines("hps509")
+    N, dr, B, seed, row0 = 509, 169, 70, 99, 5
+    r = torch.zeros((B, eng.pitch), dtype=torch.uint8, device="cuda")
+    eng.sample_r_dev(B, dr, seed, row0, r)
+    eng.sync()
+    got = r.cpu().numpy()
+    assert not got[:, N:].any()
+    for b in (0, 1, 63, 64, 69):
+        it = iter(range(N - 1, 0, -1))
+        draws = iter([nb.sampler_rand32(seed, row0 + b, i) for i in range(N - 1, 0, -1)])
+        arr = nb.generateCustomArray(N, dr, dr, rand32=lambda: next(draws))
+        assert got[b, :N].tolist() == [2 if x == -1 else x for x in arr]
+    assert (np.count_nonzero(got == 1, axis=1) == dr).all() and (np.count_nonzero(got == 2, axis=1) == dr).all()
+
+
+def test_device_resident_api_and_properties_at_scale(nb, engines, golden):
+    """Device-pointer entry points at a large batch: decrypt(encrypt(m)) == m and witness identities."""
+    torch = pytest.importorskip("torch")
+    g, eng = golden("hps509"), engines("hps509")
+    N, q, P, B = 509, 2048, eng.pitch, 1 << 16
+    dev = "cuda"
+    gen = torch.Generator(device=dev).manual_seed(1)
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    eng.sample_r_dev(B, 169, 7, 0, r)
+    m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    m[:, :N] = torch.randint(0, 2, (B, N), generator=gen, device=dev, dtype=torch.uint8)
+    val = torch.empty((B, P), dtype=torch.int16, device=dev)
+    quo = torch.empty((B, P), dtype=torch.int16, device=dev)
+    out = torch.empty((B, P), dtype=torch.uint8, device=dev)
+    q1 = torch.empty((B, P), dtype=torch.int16, device=dev)
+    r1 = torch.empty((B, P), dtype=torch.int16, device=dev)
+    q2 = torch.empty((B, P), dtype=torch.uint8, device=dev)
+    eng.encrypt_dev(B, r, m, value=val, quotientE=quo)
+    eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2)
+    eng.sync()
+    assert torch.equal(out[:, :N], m[:, :N])
+    # spot-check rows against the oracle
+    idx = [0, 1, 12345, B - 1]
+    want = o.encrypt_batch(g["h"].astype(np.int64), r[idx, :N].cpu().numpy(), m[idx, :N].cpu().numpy(), q)
+    got = val[idx].cpu().numpy().view(np.uint16)
+    assert np.array_equal(got[:, :N], want["value"])
+    assert np.array_equal(quo[idx].cpu().numpy().view(np.uint16)[:, : N + 1], want["quotientE"])
+    # pad / entry N are zero so that the arrays are valid witness rows
+    assert not quo[:, N - 1:].any() and not val[:, N:].any()
+    # checksum of checksums: sum of ciphertexts decrypts to the sum of messages' columns mod q relation
+    part = torch.zeros(P, dtype=torch.int32, device=dev)
+    eng.sum_partial_dev(B, val, part)
+    s16 = torch.empty(P, dtype=torch.int16, device=dev)
+    eng.sum_finalize_dev(part, s16)
+    eng.sync()
+    want_sum = (val[:, :N].to(torch.int64) & 0xFFFF).sum(dim=0) % q
+    assert torch.equal(s16[:N].to(torch.int64) & 0xFFFF, want_sum)

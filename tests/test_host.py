@@ -1,0 +1,123 @@
+"""CPU-side checks of the product's host code and of the C ABI surface (no compute calls)."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import ntru_circom_b200 as nb
+import ntru_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ntru_circom_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "ntru_b200.h")).read()
+    declared = set(re.findall(r"\b(ntru_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("ntru_ctx")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"libntru_b200.so does not export {name}"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_abi_rejects_bad_parameters_without_a_gpu():
+    from ntru_circom_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.ntru_create(ctypes.byref(h), 167, 5, 128, 0) == _lib.NTRU_E_PARAM      # p != 3
+    assert lib.ntru_create(ctypes.byref(h), 167, 3, 100, 0) == _lib.NTRU_E_PARAM      # q not a power of two
+    assert lib.ntru_create(ctypes.byref(h), 4, 3, 128, 0) == _lib.NTRU_E_PARAM        # N too small
+    assert lib.ntru_create(ctypes.byref(h), 1024, 3, 16384, 0) == _lib.NTRU_E_PARAM   # fp32 exactness bound
+    assert lib.ntru_strerror(_lib.NTRU_E_NOKEY) == b"key not set"
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ntru-circom_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "ntru_oracle" not in txt and "c_oracle" not in txt and "libntru_oracle" not in txt, fn
+
+
+def test_poly_matches_oracle_kats():
+    assert nb.multiplyPolynomials([1, 2, 3, 4], [6, 5, 4, 3], 2 ** 20) == [6, 17, 32, 50, 38, 25, 12]
+    assert nb.multiplyPolynomials([], [1], 5) == [0]
+    assert nb.dividePolynomials([1, 2], [2, 3], 8) == {"quotient": [6], "remainder": [5]}
+    assert nb.dividePolynomials([81, 2, 96], [48, 2, 31], 128) == {"quotient": [32], "remainder": [81, 66]}
+    assert nb.dividePolynomials([81, 2, 96], [48, 2, 31], 16) == {"quotient": [0], "remainder": [1, 2]}
+    with pytest.raises(ValueError, match="No inverse"):
+        nb.dividePolynomials([1, 2], [2, 3], 3)
+    assert nb.extendedEuclideanAlgorithm([4, 2, 0, 3], [3, 2, 1], 11)["inverse"] == [5, 8]
+    assert nb.modInverse(-1, 2048) == 2047 and nb.modInverse(2, 4) is None
+    rng = random.Random(3)
+    for _ in range(20):
+        p = rng.choice([3, 7, 32, 2048])
+        a = [rng.randrange(-3, p) for _ in range(rng.randrange(1, 12))]
+        b = [rng.randrange(-3, p) for _ in range(rng.randrange(1, 12))]
+        assert nb.multiplyPolynomials(a, b, p) == o.multiply_polynomials_fft(a, b, p)
+        assert nb.addPolynomials(a, b, p) == o.add_polynomials(a, b, p)
+        assert nb.subtractPolynomials(a, b, p) == o.subtract_polynomials(a, b, p)
+        if p in (3, 7):
+            b2 = b if o.degree([x % p for x in b]) >= 0 else [1]
+            aa, bb = [x % p for x in a], [x % p for x in b2]
+            assert nb.dividePolynomials(aa, bb, p) == o.divide_polynomials(aa, bb, p)
+
+
+def test_format_helpers():
+    assert nb.stringToBits("Hi") == o.string_to_bits("Hi")
+    assert nb.bitsToString(nb.stringToBits("Hello World")) == "Hello World"
+    assert nb.expandArrayToMultiple([1, 1, 1], 8) == [1, 1, 1, 0, 0, 0, 0, 0]
+    with pytest.raises(IndexError):
+        nb.expandArray([1, 2, 3], 2)
+    assert nb.trimPolynomial([0, 0]) == [0] and nb.trimPolynomial([1, 0, 2, 0]) == [1, 0, 2]
+    # packOutput / unpackInput round trip (index.js:572-620; test/circuits.test.js:20-58)
+    data = [random.Random(1).randrange(8192) for _ in range(701)]
+    packed = nb.packOutput(8191, 701, data)
+    assert packed["maxInputBits"] == 13 and packed["outputSize"] == 37
+    un = nb.unpackInput(8191, packed["maxOutputBits"], packed["expected"])
+    assert un["unpacked"] == nb.trimPolynomial(data)
+    assert nb.bitsToBigInt(list(reversed(nb.bigintToBits(1234567)))) == 1234567
+
+
+@pytest.mark.parametrize("cfg", ["tiny17", "default167", "hps509"])
+def test_host_keygen_matches_oracle(cfg):
+    """Same seeded draws -> same f, fq, fp, g, h as the oracle's restatement of index.js:30-79."""
+    ref = o.NTRU(dict(o.CONFIGS[cfg]), rng=random.Random(42))
+    ref.generatePrivateKeyF()
+    ref.generateNewPublicKeyGH()
+    rng = random.Random(42)
+    mine = nb.NTRU(dict(o.CONFIGS[cfg]), rand32=lambda: rng.getrandbits(32))
+    mine.generatePrivateKeyF()
+    mine.generateNewPublicKeyGH()
+    assert (mine.f, mine.fq, mine.fp, mine.g, mine.h) == (ref.f, ref.fq, ref.fp, ref.g, ref.h)
+    assert mine.calculateNq() == ref.calculateNq() and mine.calculateNp() == ref.calculateNp()
+    w = mine.verifyKeysInputs()
+    assert w["fq"]["inputs"]["remainderI"] == [1] + [0] * mine.N
+    assert w["fp"]["inputs"]["remainderI"] == [1] + [0] * mine.N
+    assert w["h"]["inputs"]["remainderI"][: len(mine.h)] == mine.h
+
+
+def test_constructor_defaults_and_errors():
+    k = nb.NTRU()
+    assert (k.N, k.p, k.q, k.df, k.dg, k.dr) == (167, 3, 128, 61, 20, 18)
+    assert k.I == [1] + [0] * 166 + [-1]
+    with pytest.raises(TypeError):
+        k.encryptBits([1, 0, 1])          # h === null -> TypeError in the reference (index.js:90)
+    with pytest.raises(TypeError):
+        k.decryptBits([1, 2, 3])
+    with pytest.raises(ValueError, match="missing private key F"):
+        k.generatePublicKeyH()
+    with pytest.raises(ValueError):
+        nb.generateCustomArray(5, 3, 3)
+
+
+def test_sampler_generator_is_reproducible():
+    a = [nb.sampler_rand32(1, 2, i) for i in range(4)]
+    assert a == [nb.sampler_rand32(1, 2, i) for i in range(4)]
+    assert len(set(a)) == 4 and all(0 <= x < 2 ** 32 for x in a)
