@@ -1,13 +1,596 @@
-// placeholder: tcgen05 schedule not built yet
+// tcgen05 schedule: many ciphertexts under ONE key = a dense int8 contraction against the key's
+// Toeplitz matrices, int32 accumulators in TMEM, reduction / fold / witness fused in the epilogue.
+//
+// One launch computes, for a batch of rows x (the per-ciphertext polynomial: r, e or b) and a fixed
+// key polynomial y (h, f or fp), the two halves of the linear product c = lin(x, y):
+//     cyc[k] = sum_i x[i] * y[(k-i) mod N]          (= c[k] + c[k+N], the remainder of c / (1 - x^N))
+//     hi [k] = sum_{i>k} x[i] * y[k+N-i]            (= c[k+N];  the quotient is -hi)
+// which is everything multiplyPolynomials + dividePolynomials(., I, .) (index.js:319-401) produce on
+// the hot path (closed form: SURVEY.md section 8a).  Three modes share the kernel:
+//     ENC  : x = r (bytes 0..2),   y = h (mod q)   -> value/remainderE = (cyc + m) mod q, quotientE = -hi mod q
+//     DEC1 : x = e (uint16 mod q), y = f (ternary) -> remainder1 = cyc mod q, quotient1 = -hi mod q,
+//                                                     b = (remainder1 + [remainder1 > q/2]) mod 3   (index.js:117)
+//     DEC2 : x = b (bytes 0..2),   y = fp (0..2)   -> value/remainder2 = cyc mod 3, quotient2 = -hi mod 3
+//
+// GEMM view per 128-row tile: D[128 x NC] += A[128 x K] * B[NC x K]^T with
+//   A = the batch operand, built in shared memory by "builder" warps straight from global memory into
+//       the UMMA K-major SWIZZLE_128B layout (r and b are byte copies, e is split into byte limbs);
+//   B = rows of the key matrix Mat (one row per output column, K-major), precomputed once per key by
+//       k_build_keymat and streamed by TMA (it is at most 3 MB and lives in L2).
+// Operands wider than 8 bits use two byte limbs laid side by side along K with the 2^8 weight split
+// between the operands so that ONE int32 accumulator receives the exact product:
+//   ENC : A = [r | r<<5],            B = [h & 255 | (h>>8)<<3]      (u8 x u8)
+//   DEC1: A = [e & 255 | (e>>8)<<2], B = [f | f<<6]                 (u8 x s8)
+// All-zero K ranges of the triangular hi matrix are skipped at 128-byte granularity.
+//
+// Warp roles (576 threads, 1 CTA per SM, persistent over row tiles):
+//   warp 0      TMA producer of B slices           warp 1      tcgen05.mma issuer, owns TMEM
+//   warps 2-9   two builder groups for A slices    warps 10-17 epilogue (TMEM -> registers -> global)
+// Pipelines: a 4-stage shared-memory ring (full/empty mbarriers) and two 256-column TMEM accumulators
+// (tmem_full/tmem_empty mbarriers) so that the epilogue of chunk j overlaps the MMAs of chunk j+1.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
 #include "ntru_internal.cuh"
+
 namespace ntru {
-int umma_init(ntru_ctx *ctx) { ctx->tensor_ok = false; return NTRU_OK; }
-int umma_prepare_public(ntru_ctx *) { return NTRU_OK; }
-int umma_prepare_private(ntru_ctx *) { return NTRU_OK; }
-int umma_encrypt(ntru_ctx *ctx, size_t, const uint8_t *, const uint8_t *, uint16_t *, uint16_t *, uint16_t *) {
-  return fail(ctx, NTRU_E_UNSUPPORTED, "tensor schedule not built");
+
+namespace {
+
+enum Mode { ENC = 0, DEC1 = 1, DEC2 = 2 };
+
+constexpr int kStages = 4;
+constexpr int kTileRows = 128;
+constexpr int kAtomK = 128;                      // bytes of K per pipeline slice (one 128B swizzle atom)
+constexpr int kABytes = kTileRows * kAtomK;      // 16 KB
+constexpr int kBBytesMax = 256 * kAtomK;         // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kThreads = 576;
+constexpr int kBuilderWarp0 = 2, kEpilogueWarp0 = 10;
+constexpr int kAccCols = 256;                    // TMEM columns per accumulator buffer
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct UmmaArgs {
+  int N, P, Kp, atoms, limbs, NC, nchunks, with_hi, q;
+  uint32_t qmask;
+  size_t B;
+  int ntiles;
+  const void *a_src;      // r / e / b rows, pitch P elements
+  const uint8_t *m;       // ENC: message rows
+  uint16_t *o16_cyc;      // ENC: value, DEC1: remainder1
+  uint16_t *o16_cyc2;     // ENC: remainderE (same data, second destination)
+  uint16_t *o16_hi;       // ENC: quotientE, DEC1: quotient1
+  uint8_t *o8_cyc;        // DEC1: b, DEC2: value
+  uint8_t *o8_cyc2;       // DEC2: remainder2
+  uint8_t *o8_hi;         // DEC2: quotient2
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-int umma_decrypt(ntru_ctx *ctx, size_t, const uint16_t *, uint8_t *, uint16_t *, uint16_t *, uint8_t *, uint8_t *) {
-  return fail(ctx, NTRU_E_UNSUPPORTED, "tensor schedule not built");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4, LBO = 1 (ignored for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1, layout 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// cute::UMMA::InstrDescriptor for kind::i8: c_format=S32 (2) at [4,6), a_format at [7,10), b_format at [10,13)
+// (0 = u8, 1 = s8), K-major A and B, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int a_signed, int b_signed, int n) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kTileRows >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t mod3_small(uint32_t v) {   // v < 65536
+  return v - 3u * ((v * 0xAAABu) >> 17);
+}
+
+// first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= c*NC + 1
+__device__ __forceinline__ int first_atom(const UmmaArgs &a, int part_hi, int c) {
+  if (!part_hi) return 0;
+  const int a0 = (c * a.NC + 1) / kAtomK;
+  return a0 < a.atoms ? a0 : a.atoms - 1;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * kStageBytes);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then the TMEM base address
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1 + 4);     // TMA expect_tx arrival + 4 builder warps
+      mbar_init(empty_bar(s), 1);        // tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);        // tcgen05.commit
+      mbar_init(tempty_bar(b), 8);       // 8 epilogue warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int parts = a.with_hi ? 2 : 1;          // part 0 = hi (when present), last part = cyc
+  const int slices_cyc = a.limbs * a.atoms;
+
+  if (warp == 0) {
+    // ===================== TMA producer: B slices =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t bytes = (uint32_t)a.NC * kAtomK;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int part = 0; part < parts; ++part) {
+          const int hi = a.with_hi && part == 0;
+          for (int c = 0; c < a.nchunks; ++c) {
+            const int a0 = first_atom(a, hi, c);
+            const int row0 = (hi ? a.nchunks * a.NC : 0) + c * a.NC;
+            for (int limb = 0; limb < a.limbs; ++limb) {
+              for (int at = a0; at < a.atoms; ++at, ++it) {
+                const int s = it % kStages;
+                mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(full_bar(s), bytes);
+                tma_load_2d(smem_base + s * kStageBytes + kABytes, &tmap, limb * a.Kp + at * kAtomK, row0, full_bar(s));
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(0, MODE == DEC1 ? 1 : 0, a.NC);
+      uint32_t it = 0, cc = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int part = 0; part < parts; ++part) {
+          const int hi = a.with_hi && part == 0;
+          for (int c = 0; c < a.nchunks; ++c, ++cc) {
+            const int a0 = first_atom(a, hi, c);
+            const int buf = cc & 1;
+            mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * kAccCols;
+            uint32_t first = 1;
+            for (int limb = 0; limb < a.limbs; ++limb) {
+              for (int at = a0; at < a.atoms; ++at, ++it) {
+                const int s = it % kStages;
+                mbar_wait(full_bar(s), (it / kStages) & 1);
+                tc_fence_after();
+                const uint64_t da = make_smem_desc(smem_base + s * kStageBytes);
+                const uint64_t db = make_smem_desc(smem_base + s * kStageBytes + kABytes);
+#pragma unroll
+                for (int k = 0; k < kAtomK / 32; ++k) {
+                  umma_i8(d_tmem, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);   // +32 bytes of K per step
+                  first = 0;
+                }
+                umma_commit(empty_bar(s));
+              }
+            }
+            umma_commit(tfull_bar(buf));
+          }
+        }
+      }
+    }
+  } else if (warp < kEpilogueWarp0) {
+    // ===================== builders: A slices, global -> swizzled smem =====================
+    const int group = (warp - kBuilderWarp0) >> 2;                  // 0 or 1: even / odd slices
+    const int t = threadIdx.x - (kBuilderWarp0 + 4 * group) * 32;   // 0..127 within the group
+    const int chunk = t & 7;                                        // 16-byte chunk within the 128-byte row
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const size_t row_base = (size_t)tile * kTileRows;
+      for (int part = 0; part < parts; ++part) {
+        const int hi = a.with_hi && part == 0;
+        for (int c = 0; c < a.nchunks; ++c) {
+          const int a0 = first_atom(a, hi, c);
+          for (int limb = 0; limb < a.limbs; ++limb) {
+            for (int at = a0; at < a.atoms; ++at, ++it) {
+              if ((int)(it & 1) != group) continue;
+              const int s = it % kStages;
+              const int col = at * kAtomK + chunk * 16;             // first coefficient of this thread's chunk
+              uint4 val[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r_in = j * 16 + (t >> 3);
+                const size_t row = row_base + r_in;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (row < a.B && col < a.P) {
+                  if (MODE == DEC1) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(a.a_src) +
+                                                                        row * (size_t)a.P + col);
+                    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
+                    if (limb == 0) {
+                      v.x = __byte_perm(w0.x, w0.y, 0x6420);
+                      v.y = __byte_perm(w0.z, w0.w, 0x6420);
+                      v.z = __byte_perm(w1.x, w1.y, 0x6420);
+                      v.w = __byte_perm(w1.z, w1.w, 0x6420);
+                    } else {   // (e >> 8) << 2 in the low byte of each 16-bit field
+                      v.x = __byte_perm((w0.x >> 6) & 0x00FC00FCu, (w0.y >> 6) & 0x00FC00FCu, 0x6420);
+                      v.y = __byte_perm((w0.z >> 6) & 0x00FC00FCu, (w0.w >> 6) & 0x00FC00FCu, 0x6420);
+                      v.z = __byte_perm((w1.x >> 6) & 0x00FC00FCu, (w1.y >> 6) & 0x00FC00FCu, 0x6420);
+                      v.w = __byte_perm((w1.z >> 6) & 0x00FC00FCu, (w1.w >> 6) & 0x00FC00FCu, 0x6420);
+                    }
+                  } else {
+                    v = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(a.a_src) +
+                                                              row * (size_t)a.P + col));
+                    if (limb == 1) {   // r << 5 per byte
+                      v.x = (v.x << 5) & 0xE0E0E0E0u;
+                      v.y = (v.y << 5) & 0xE0E0E0E0u;
+                      v.z = (v.z << 5) & 0xE0E0E0E0u;
+                      v.w = (v.w << 5) & 0xE0E0E0E0u;
+                    }
+                  }
+                }
+                val[j] = v;
+              }
+              mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+              uint8_t *dstA = smem + (size_t)s * kStageBytes;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int r_in = j * 16 + (t >> 3);
+                const int off = (r_in >> 3) * 1024 + (r_in & 7) * 128 + ((chunk ^ (r_in & 7)) << 4);
+                *reinterpret_cast<uint4 *>(dstA + off) = val[j];
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(full_bar(s));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int ew = warp - kEpilogueWarp0;          // 0..7
+    const int quad = warp & 3;                     // TMEM lanes [32*quad, 32*quad+32) are this warp's
+    const int half = ew >> 2;                      // which column groups
+    const int ngroups32 = a.NC >> 5;
+    const int tail16 = (a.NC & 31) ? 1 : 0;
+    const uint32_t halfq = (uint32_t)a.q >> 1;
+    uint32_t cc = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const size_t row = (size_t)tile * kTileRows + quad * 32 + lane;
+      const bool row_ok = row < a.B;
+      const size_t rbase = row * (size_t)a.P;
+      for (int part = 0; part < parts; ++part) {
+        const int hi = a.with_hi && part == 0;
+        for (int c = 0; c < a.nchunks; ++c, ++cc) {
+          const int buf = cc & 1;
+          mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
+          for (int g = half; g < ngroups32 + tail16; g += 2) {
+            uint32_t v[32];
+            const int ncols = g < ngroups32 ? 32 : 16;
+            if (ncols == 32)
+              tmem_ld32(t_addr + g * 32, v);
+            else
+              tmem_ld16(t_addr + g * 32, v);
+            tmem_ld_wait();
+            const int k0 = c * a.NC + g * 32;
+#pragma unroll
+            for (int h16 = 0; h16 < 2; ++h16) {
+              if (h16 * 16 >= ncols) break;
+              const int kk = k0 + h16 * 16;
+              if (!row_ok || kk >= a.P) continue;
+              uint32_t w[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) w[j] = v[h16 * 16 + j];
+              if (MODE == ENC || MODE == DEC1) {
+                if (hi) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) w[j] = (0u - w[j]) & a.qmask;
+                } else if (MODE == ENC) {
+                  const uint4 mm = __ldg(reinterpret_cast<const uint4 *>(a.m + rbase + kk));
+                  const uint32_t mw[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const uint32_t mj = (mw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    w[j] = (kk + j < a.N) ? ((w[j] + mj) & a.qmask) : 0u;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) w[j] &= a.qmask;
+                }
+                uint4 p0 = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
+                uint4 p1 = make_uint4(w[8] | (w[9] << 16), w[10] | (w[11] << 16), w[12] | (w[13] << 16),
+                                      w[14] | (w[15] << 16));
+                uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
+                if (d0) {
+                  reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
+                  reinterpret_cast<uint4 *>(d0 + rbase + kk)[1] = p1;
+                }
+                if (!hi && a.o16_cyc2) {
+                  reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[0] = p0;
+                  reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[1] = p1;
+                }
+                if (MODE == DEC1 && !hi && a.o8_cyc) {
+                  uint32_t bq[4] = {0, 0, 0, 0};
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const uint32_t bj = mod3_small(w[j] + (w[j] > halfq ? 1u : 0u));   // index.js:117
+                    bq[j >> 2] |= bj << (8 * (j & 3));
+                  }
+                  *reinterpret_cast<uint4 *>(a.o8_cyc + rbase + kk) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
+                }
+              } else {   // DEC2: mod 3
+                uint32_t bq[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  uint32_t x = mod3_small(w[j]);
+                  if (hi) x = mod3_small(3u - x);
+                  bq[j >> 2] |= x << (8 * (j & 3));
+                }
+                const uint4 pk = make_uint4(bq[0], bq[1], bq[2], bq[3]);
+                uint8_t *d0 = hi ? a.o8_hi : a.o8_cyc;
+                if (d0) *reinterpret_cast<uint4 *>(d0 + rbase + kk) = pk;
+                if (!hi && a.o8_cyc2) *reinterpret_cast<uint4 *>(a.o8_cyc2 + rbase + kk) = pk;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// ---- key matrix: Mat[row][kb], row = part * cols + k (part 0 = cyc, 1 = hi), kb = limb * Kp + i -------------
+__global__ void k_build_keymat(int mode, int N, int Kp, int limbs, int cols, const void *poly, uint8_t *mat) {
+  const int klen = limbs * Kp;
+  const size_t total = (size_t)2 * cols * klen;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int kb = (int)(idx % klen);
+    const int row = (int)(idx / klen);
+    const int part = row / cols, k = row % cols;
+    const int limb = kb / Kp, i = kb % Kp;
+    int coef = 0;
+    bool nz = k < N && i < N;
+    int src = 0;
+    if (nz) {
+      if (part == 0) {
+        src = k - i;
+        if (src < 0) src += N;
+      } else {
+        nz = i > k;
+        src = k + N - i;
+      }
+    }
+    if (nz) {
+      if (mode == ENC) coef = reinterpret_cast<const uint16_t *>(poly)[src];
+      else if (mode == DEC1) coef = reinterpret_cast<const int8_t *>(poly)[src];
+      else coef = reinterpret_cast<const uint8_t *>(poly)[src];
+    }
+    uint8_t out;
+    if (mode == ENC) out = limb == 0 ? (uint8_t)(coef & 0xff) : (uint8_t)((coef >> 8) << 3);
+    else if (mode == DEC1) out = (uint8_t)(int8_t)(limb == 0 ? coef : coef * 64);
+    else out = (uint8_t)coef;
+    mat[idx] = out;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+void geometry(const ntru_ctx *ctx, int limbs, KeyMatrix &km) {
+  const int N = ctx->N;
+  km.limbs = limbs;
+  km.nchunks = (N + 255) / 256;
+  const int per = (N + km.nchunks - 1) / km.nchunks;
+  km.chunk_cols = ((per + 15) / 16) * 16;
+  const int Kp = ((N + kAtomK - 1) / kAtomK) * kAtomK;
+  km.klen = limbs * Kp;
+}
+
+int build_keymat(ntru_ctx *ctx, int mode, int limbs, const void *poly, KeyMatrix &km) {
+  geometry(ctx, limbs, km);
+  const int cols = km.nchunks * km.chunk_cols;
+  const int Kp = km.klen / limbs;
+  const size_t bytes = (size_t)2 * cols * km.klen;
+  NTRU_CUDA(ctx, km.mat.reserve(bytes));
+  k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, limbs, cols, poly, (uint8_t *)km.mat.ptr);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)km.klen, (cuuint64_t)(2 * cols)};
+  cuuint64_t gstride[1] = {(cuuint64_t)km.klen};
+  cuuint32_t box[2] = {(cuuint32_t)kAtomK, (cuuint32_t)km.chunk_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap *>(km.tmap), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, km.mat.ptr, gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  km.ready = true;
+  return NTRU_OK;
+}
+
+template <int MODE>
+int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_product<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_set = true;
+  }
+  a.N = ctx->N; a.P = ctx->P; a.limbs = km.limbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
+  a.NC = km.chunk_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
+  a.ntiles = (int)((a.B + kTileRows - 1) / kTileRows);
+  const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
+  CUtensorMap tm;
+  memcpy(&tm, km.tmap, sizeof tm);
+  k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tm);
+  ctx->launches++;
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+}  // namespace
+
+int umma_init(ntru_ctx *ctx) {
+  ctx->tensor_ok = false;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return NTRU_OK;
+  if (prop.major != 10) return NTRU_OK;                       // tcgen05 needs sm_100a
+  if ((size_t)prop.sharedMemPerBlockOptin < kSmemBytes) return NTRU_OK;
+  if (!get_encode_fn()) return NTRU_OK;
+  ctx->tensor_ok = true;
+  return NTRU_OK;
+}
+
+int umma_prepare_public(ntru_ctx *ctx) {
+  return build_keymat(ctx, ENC, ctx->q > 256 ? 2 : 1, ctx->d_h.ptr, ctx->km_h);
+}
+
+int umma_prepare_private(ntru_ctx *ctx) {
+  int rc = build_keymat(ctx, DEC1, ctx->q > 256 ? 2 : 1, ctx->d_f.ptr, ctx->km_f);
+  if (rc) return rc;
+  return build_keymat(ctx, DEC2, 1, ctx->d_fp.ptr, ctx->km_fp);
+}
+
+int umma_encrypt(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m, uint16_t *value, uint16_t *quo,
+                 uint16_t *rem) {
+  if (B == 0) return NTRU_OK;
+  UmmaArgs a = {};
+  a.B = B; a.a_src = r; a.m = m;
+  a.with_hi = quo != nullptr;
+  a.o16_cyc = value ? value : rem;
+  a.o16_cyc2 = value ? rem : nullptr;
+  a.o16_hi = quo;
+  return launch_product<ENC>(ctx, ctx->km_h, a);
+}
+
+int umma_decrypt(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2,
+                 uint8_t *r2) {
+  if (B == 0) return NTRU_OK;
+  NTRU_CUDA(ctx, ctx->d_b.reserve(B * (size_t)ctx->P));
+  UmmaArgs a = {};
+  a.B = B; a.a_src = e;
+  a.with_hi = q1 != nullptr;
+  a.o16_cyc = r1; a.o16_hi = q1; a.o8_cyc = (uint8_t *)ctx->d_b.ptr;
+  int rc = launch_product<DEC1>(ctx, ctx->km_f, a);
+  if (rc) return rc;
+  UmmaArgs b = {};
+  b.B = B; b.a_src = ctx->d_b.ptr;
+  b.with_hi = q2 != nullptr;
+  b.o8_cyc = value ? value : r2;
+  b.o8_cyc2 = value ? r2 : nullptr;
+  b.o8_hi = q2;
+  return launch_product<DEC2>(ctx, ctx->km_fp, b);
+}
+
 }  // namespace ntru
