@@ -51,7 +51,20 @@ enum {
 /* ntru_set_option keys */
 enum {
   NTRU_OPT_PATH = 1,        /* 0 auto, 1 force CUDA-core schedule, 2 force tcgen05 tensor schedule (same-key only) */
-  NTRU_OPT_CHUNK_ROWS = 2   /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
+  NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
+  NTRU_OPT_TIMING = 3       /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
+};
+
+/* kernel kinds reported by ntru_timing_read */
+enum {
+  NTRU_K_ENC_TENSOR = 0,    /* tcgen05: lin(r,h) + m, fold, quotientE */
+  NTRU_K_DEC1_TENSOR = 1,   /* tcgen05: lin(f,e), fold, quotient1, lift to b */
+  NTRU_K_DEC2_TENSOR = 2,   /* tcgen05: lin(fp,b) mod 3, fold, quotient2 */
+  NTRU_K_ENC_CORE = 3,      /* CUDA-core encrypt */
+  NTRU_K_DEC_CORE = 4,      /* CUDA-core decrypt (both products) */
+  NTRU_K_SUM = 5,           /* ciphertext column sum */
+  NTRU_K_OTHER = 6,         /* sampler, finalize, key-matrix build */
+  NTRU_K_COUNT = 7
 };
 
 /* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 32768], 8 <= N <= 1024. */
@@ -66,6 +79,10 @@ int ntru_pitch(const ntru_ctx *ctx);
 uint64_t ntru_launch_count(const ntru_ctx *ctx);
 /* which schedule the last batch call used: 1 CUDA-core, 2 tcgen05 */
 int ntru_last_path(const ntru_ctx *ctx);
+/* with NTRU_OPT_TIMING on: synchronises, then returns the summed device time (ms) and launch count of one
+ * kernel kind since the last ntru_timing_reset */
+int ntru_timing_read(ntru_ctx *ctx, int kind, double *total_ms, uint64_t *launches);
+int ntru_timing_reset(ntru_ctx *ctx);
 
 /* this.h = ... (index.js:72-79 result, expanded to N entries in [0,q)) */
 int ntru_set_public_key(ntru_ctx *ctx, const uint16_t *h);

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libntru_b200.so")
 NTRU_OK = 0
 NTRU_E_PARAM, NTRU_E_LENGTH, NTRU_E_NOKEY, NTRU_E_CUDA = -1, -2, -3, -4
 NTRU_E_NCCL, NTRU_E_NOMEM, NTRU_E_UNSUPPORTED = -5, -6, -7
-NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS = 1, 2
+NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING = 1, 2, 3
+KERNEL_KINDS = ["enc_tensor", "dec1_tensor", "dec2_tensor", "enc_core", "dec_core", "sum", "other"]
 PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR = 0, 1, 2
 
 #: every symbol include/ntru_b200.h declares: name -> (restype, argtypes)
@@ -29,6 +30,8 @@ SYMBOLS = {
     "ntru_pitch": (c_int, [_P]),
     "ntru_launch_count": (c_uint64, [_P]),
     "ntru_last_path": (c_int, [_P]),
+    "ntru_timing_read": (c_int, [_P, c_int, POINTER(ctypes.c_double), POINTER(c_uint64)]),
+    "ntru_timing_reset": (c_int, [_P]),
     "ntru_set_public_key": (c_int, [_P, _P]),
     "ntru_set_private_key": (c_int, [_P, _P, _P]),
     "ntru_encrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P]),

@@ -23,6 +23,31 @@ int cuda_fail(ntru_ctx *ctx, cudaError_t e, const char *what) {
   return NTRU_E_CUDA;
 }
 
+static cudaEvent_t pool_get(ntru_ctx *ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+LaunchTimer::LaunchTimer(ntru_ctx *c, int k) : ctx(c), kind(k) {
+  ctx->launches++;
+  if (!ctx->timing) return;
+  a = pool_get(ctx);
+  b = pool_get(ctx);
+  cudaEventRecord(a, ctx->stream);
+}
+
+LaunchTimer::~LaunchTimer() {
+  if (!a) return;
+  cudaEventRecord(b, ctx->stream);
+  ctx->timed.push_back({kind, a, b});
+}
+
 namespace {
 
 // One array of a host-buffer call: packed on the host (row = width elements), pitched on the device.
@@ -212,6 +237,11 @@ void ntru_destroy(ntru_ctx *ctx) {
   }
   ctx->d_h.release(); ctx->d_f.release(); ctx->d_fp.release(); ctx->d_b.release(); ctx->d_partial.release();
   ctx->km_h.mat.release(); ctx->km_f.mat.release(); ctx->km_fp.mat.release();
+  for (auto &t : ctx->timed) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -229,6 +259,9 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
       if (value < 128) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_CHUNK_ROWS must be >= 128");
       ctx->chunk_rows = (size_t)value;
       return NTRU_OK;
+    case NTRU_OPT_TIMING:
+      ctx->timing = value != 0;
+      return NTRU_OK;
     default:
       return fail(ctx, NTRU_E_PARAM, "unknown option");
   }
@@ -237,6 +270,37 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
 int ntru_pitch(const ntru_ctx *ctx) { return ctx ? ctx->P : 0; }
 uint64_t ntru_launch_count(const ntru_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int ntru_last_path(const ntru_ctx *ctx) { return ctx ? ctx->last_path : 0; }
+
+int ntru_timing_reset(ntru_ctx *ctx) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto &t : ctx->timed) {
+    ctx->event_pool.push_back(t.a);
+    ctx->event_pool.push_back(t.b);
+  }
+  ctx->timed.clear();
+  return NTRU_OK;
+}
+
+int ntru_timing_read(ntru_ctx *ctx, int kind, double *total_ms, uint64_t *launches) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (kind < 0 || kind >= NTRU_K_COUNT || !total_ms || !launches) return fail(ctx, NTRU_E_PARAM, "bad timing query");
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double sum = 0;
+  uint64_t n = 0;
+  for (auto &t : ctx->timed) {
+    if (t.kind != kind) continue;
+    float ms = 0;
+    NTRU_CUDA(ctx, cudaEventElapsedTime(&ms, t.a, t.b));
+    sum += ms;
+    ++n;
+  }
+  *total_ms = sum;
+  *launches = n;
+  return NTRU_OK;
+}
 
 int ntru_set_public_key(ntru_ctx *ctx, const uint16_t *h) {
   int rc = check(ctx);

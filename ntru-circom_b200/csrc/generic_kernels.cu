@@ -364,11 +364,13 @@ int launch_encrypt_generic(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_
   const size_t smem = (size_t)24 * a.NB * sizeof(float);
   const size_t cap = (size_t)ctx->sm_count * 16;
   const unsigned grid = (unsigned)(B < cap ? B : cap);
-  if (m_wide)
-    k_encrypt_generic<true><<<grid, threads, smem, ctx->stream>>>(a);
-  else
-    k_encrypt_generic<false><<<grid, threads, smem, ctx->stream>>>(a);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, NTRU_K_ENC_CORE);
+    if (m_wide)
+      k_encrypt_generic<true><<<grid, threads, smem, ctx->stream>>>(a);
+    else
+      k_encrypt_generic<false><<<grid, threads, smem, ctx->stream>>>(a);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }
@@ -385,8 +387,10 @@ int launch_decrypt_generic(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8
   const size_t smem = (size_t)24 * a.NB * sizeof(float);
   const size_t cap = (size_t)ctx->sm_count * 16;
   const unsigned grid = (unsigned)(B < cap ? B : cap);
-  k_decrypt_generic<<<grid, threads, smem, ctx->stream>>>(a);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, NTRU_K_DEC_CORE);
+    k_decrypt_generic<<<grid, threads, smem, ctx->stream>>>(a);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }
@@ -400,15 +404,19 @@ int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *par
   size_t blocks = (B + RY - 1) / RY;
   const size_t cap = (size_t)ctx->sm_count * 4;
   if (blocks > cap) blocks = cap;
-  k_sum_partial<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, partial);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, NTRU_K_SUM);
+    k_sum_partial<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, partial);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }
 
 int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out) {
-  k_sum_finalize<<<(ctx->P + 255) / 256, 256, 0, ctx->stream>>>(partial, ctx->N, ctx->P, (uint32_t)ctx->q - 1, out);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, NTRU_K_OTHER);
+    k_sum_finalize<<<(ctx->P + 255) / 256, 256, 0, ctx->stream>>>(partial, ctx->N, ctx->P, (uint32_t)ctx->q - 1, out);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }
@@ -422,8 +430,10 @@ int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row
     attr_set = true;
   }
   const size_t blocks = (B + kSampleRows - 1) / kSampleRows;
-  k_sample_r<<<(unsigned)blocks, kSampleRows, smem, ctx->stream>>>(ctx->N, ctx->P, dr, seed, row0, B, r);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, NTRU_K_OTHER);
+    k_sample_r<<<(unsigned)blocks, kSampleRows, smem, ctx->stream>>>(ctx->N, ctx->P, dr, seed, row0, B, r);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }

@@ -64,12 +64,26 @@ struct ntru_ctx {
   bool tensor_ok = false;          // device is sm_100 and the tcgen05 schedule initialised
   uint64_t launches = 0;
   std::string err;
+  // optional per-launch timing (NTRU_OPT_TIMING)
+  bool timing = false;
+  struct TimedLaunch { int kind; cudaEvent_t a, b; };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace ntru {
 
 int fail(ntru_ctx *ctx, int code, const std::string &msg);
 int cuda_fail(ntru_ctx *ctx, cudaError_t e, const char *what);
+
+// Brackets one kernel launch with events on ctx->stream when timing is enabled.
+struct LaunchTimer {
+  ntru_ctx *ctx;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  LaunchTimer(ntru_ctx *c, int k);
+  ~LaunchTimer();
+};
 
 #define NTRU_CUDA(ctx, expr)                                        \
   do {                                                              \

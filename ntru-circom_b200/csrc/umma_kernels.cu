@@ -203,7 +203,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
   const uint32_t tmem_base = *tmem_slot;
 
   const int parts = a.with_hi ? 2 : 1;          // part 0 = hi (when present), last part = cyc
-  const int slices_cyc = a.limbs * a.atoms;
 
   if (warp == 0) {
     // ===================== TMA producer: B slices =====================
@@ -502,8 +501,10 @@ int build_keymat(ntru_ctx *ctx, int mode, int limbs, const void *poly, KeyMatrix
   const int Kp = km.klen / limbs;
   const size_t bytes = (size_t)2 * cols * km.klen;
   NTRU_CUDA(ctx, km.mat.reserve(bytes));
-  k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, limbs, cols, poly, (uint8_t *)km.mat.ptr);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, NTRU_K_OTHER);
+    k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, limbs, cols, poly, (uint8_t *)km.mat.ptr);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -533,8 +534,10 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a) {
   const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
   CUtensorMap tm;
   memcpy(&tm, km.tmap, sizeof tm);
-  k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tm);
-  ctx->launches++;
+  {
+    LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
+    k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tm);
+  }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }

@@ -82,6 +82,22 @@ class Engine:
     def last_path(self) -> int:
         return int(self.lib.ntru_last_path(self._h))
 
+    def set_timing(self, on: bool):
+        self.set_option(_lib.NTRU_OPT_TIMING, 1 if on else 0)
+
+    def timing_reset(self):
+        self._check(self.lib.ntru_timing_reset(self._h))
+
+    def timing_read(self) -> dict:
+        """{kind: (total_ms, launches)} of the kernels launched since timing_reset (synchronises)."""
+        out = {}
+        for i, name in enumerate(_lib.KERNEL_KINDS):
+            ms, n = ctypes.c_double(0), ctypes.c_uint64(0)
+            self._check(self.lib.ntru_timing_read(self._h, i, ctypes.byref(ms), ctypes.byref(n)))
+            if n.value:
+                out[name] = (ms.value, int(n.value))
+        return out
+
     def stream(self) -> int:
         return int(self.lib.ntru_stream(self._h) or 0)
 
