@@ -39,7 +39,7 @@ struct KeyMatrix {
   DevBuf mat;            // [2*ncols_pad][klen] bytes, K-major
   alignas(64) unsigned char tmap[128];   // CUtensorMap
   bool ready = false;
-  int limbs = 0, klen = 0, nchunks = 0, chunk_cols = 0;
+  int limbs = 0, nlimbs = 0, klen = 0, nchunks = 0, chunk_cols = 0, out_cols = 0;
 };
 
 }  // namespace ntru

@@ -13,19 +13,21 @@
 //     DEC2 : x = b (bytes 0..2),   y = fp (0..2)   -> value/remainder2 = cyc mod 3, quotient2 = -hi mod 3
 //
 // GEMM view per 128-row tile: D[128 x NC] += A[128 x K] * B[NC x K]^T with
-//   A = the batch operand, built in shared memory by "builder" warps straight from global memory into
-//       the UMMA K-major SWIZZLE_128B layout (r and b are byte copies, e is split into byte limbs);
-//   B = rows of the key matrix Mat (one row per output column, K-major), precomputed once per key by
-//       k_build_keymat and streamed by TMA (it is at most 3 MB and lives in L2).
-// Operands wider than 8 bits use two byte limbs laid side by side along K with the 2^8 weight split
-// between the operands so that ONE int32 accumulator receives the exact product:
-//   ENC : A = [r | r<<5],            B = [h & 255 | (h>>8)<<3]      (u8 x u8)
-//   DEC1: A = [e & 255 | (e>>8)<<2], B = [f | f<<6]                 (u8 x s8)
+//   A = the batch operand in the UMMA K-major SWIZZLE_128B layout.  r and b are bytes already: TMA
+//       loads them straight from the pitched global rows (out-of-range rows / columns read as zero).
+//       e is uint16: "transform" warps split it into byte limbs on the way from global to shared.
+//   B = rows of the key matrix Mat (one row per accumulator column, K-major), precomputed once per
+//       key by k_build_keymat and streamed by TMA (at most 3 MB, L2 resident).
+// Operands wider than 8 bits:
+//   ENC : h = h0 + 256*h1 -> two accumulator column groups per chunk ("N limbs": B rows [h0 | h1]),
+//         recombined in the epilogue as acc0 + (acc1 << 8); A is the same r slice for both.
+//   DEC1: e = e0 + 256*e1 -> two K ranges ("K limbs") A = [e0 | e1<<2], B = [f | f<<6], so that ONE
+//         int32 accumulator receives the exact product (u8 x s8).
 // All-zero K ranges of the triangular hi matrix are skipped at 128-byte granularity.
 //
 // Warp roles (576 threads, 1 CTA per SM, persistent over row tiles):
-//   warp 0      TMA producer of B slices           warp 1      tcgen05.mma issuer, owns TMEM
-//   warps 2-9   two builder groups for A slices    warps 10-17 epilogue (TMEM -> registers -> global)
+//   warp 0      TMA producer (A and B slices)      warp 1      tcgen05.mma issuer, owns TMEM
+//   warps 2-9   DEC1 only: e -> byte-limb A slices warps 10-17 epilogue (TMEM -> registers -> global)
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers) and two 256-column TMEM accumulators
 // (tmem_full/tmem_empty mbarriers) so that the epilogue of chunk j overlaps the MMAs of chunk j+1.
 
@@ -53,11 +55,16 @@ constexpr int kAccCols = 256;                    // TMEM columns per accumulator
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct UmmaArgs {
-  int N, P, Kp, atoms, limbs, NC, nchunks, with_hi, q;
+  int N, P, Kp, atoms;
+  int kl;                 // K limbs (DEC1 with q > 256: 2)
+  int nl;                 // N limbs (ENC with q > 256: 2)
+  int NC;                 // accumulator columns per chunk = MMA N = nl * NCo
+  int NCo;                // output coefficients per chunk
+  int nchunks, with_hi, q;
   uint32_t qmask;
   size_t B;
   int ntiles;
-  const void *a_src;      // r / e / b rows, pitch P elements
+  const void *a_src;      // DEC1: e rows (uint16), pitch P elements
   const uint8_t *m;       // ENC: message rows
   uint16_t *o16_cyc;      // ENC: value, DEC1: remainder1
   uint16_t *o16_cyc2;     // ENC: remainderE (same data, second destination)
@@ -157,16 +164,43 @@ __device__ __forceinline__ uint32_t mod3_small(uint32_t v) {   // v < 65536
   return v - 3u * ((v * 0xAAABu) >> 17);
 }
 
-// first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= c*NC + 1
+// first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= c*NCo + 1
 __device__ __forceinline__ int first_atom(const UmmaArgs &a, int part_hi, int c) {
   if (!part_hi) return 0;
-  const int a0 = (c * a.NC + 1) / kAtomK;
+  const int a0 = (c * a.NCo + 1) / kAtomK;
   return a0 < a.atoms ? a0 : a.atoms - 1;
 }
 
+// Enumerates the (tile, part, chunk, atom) work items of one CTA in pipeline order.
+struct AtomIter {
+  int tile, part, c, at, parts;
+  bool valid;
+  __device__ __forceinline__ void start(const UmmaArgs &a) {
+    parts = a.with_hi ? 2 : 1;
+    tile = blockIdx.x; part = 0; c = 0;
+    valid = tile < a.ntiles;
+    at = valid ? first_atom(a, a.with_hi, 0) : 0;
+  }
+  __device__ __forceinline__ void next(const UmmaArgs &a) {
+    if (++at < a.atoms) return;
+    if (++c == a.nchunks) {
+      c = 0;
+      if (++part == parts) {
+        part = 0;
+        tile += gridDim.x;
+        if (tile >= a.ntiles) { valid = false; return; }
+      }
+    }
+    at = first_atom(a, a.with_hi && part == 0, c);
+  }
+};
+
+constexpr int kMaxUnits = 8;   // 16-coefficient units one epilogue warp handles per chunk (256 / 16 / 2)
+
 // ---- the kernel --------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kThreads, 1)
+k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * kStageBytes);
@@ -183,8 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1 + 4);     // TMA expect_tx arrival + 4 builder warps
-      mbar_init(empty_bar(s), 1);        // tcgen05.commit
+      mbar_init(full_bar(s), MODE == DEC1 ? 1 + 8 : 1);   // TMA expect_tx arrival (+ 8 transform warps)
+      mbar_init(empty_bar(s), 1);                         // tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);        // tcgen05.commit
@@ -205,22 +239,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
   const int parts = a.with_hi ? 2 : 1;          // part 0 = hi (when present), last part = cyc
 
   if (warp == 0) {
-    // ===================== TMA producer: B slices =====================
+    // ===================== TMA producer: B slices (and A slices unless DEC1) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t bytes = (uint32_t)a.NC * kAtomK;
+      const uint32_t bytes = (uint32_t)a.NC * kAtomK + (MODE == DEC1 ? 0u : (uint32_t)kABytes);
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         for (int part = 0; part < parts; ++part) {
           const int hi = a.with_hi && part == 0;
           for (int c = 0; c < a.nchunks; ++c) {
             const int a0 = first_atom(a, hi, c);
-            const int row0 = (hi ? a.nchunks * a.NC : 0) + c * a.NC;
-            for (int limb = 0; limb < a.limbs; ++limb) {
-              for (int at = a0; at < a.atoms; ++at, ++it) {
+            const int row0 = (hi * a.nchunks + c) * a.NC;
+            for (int at = a0; at < a.atoms; ++at) {
+              for (int lk = 0; lk < a.kl; ++lk, ++it) {
                 const int s = it % kStages;
                 mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
                 mbar_arrive_expect_tx(full_bar(s), bytes);
-                tma_load_2d(smem_base + s * kStageBytes + kABytes, &tmap, limb * a.Kp + at * kAtomK, row0, full_bar(s));
+                if (MODE != DEC1)
+                  tma_load_2d(smem_base + s * kStageBytes, &tmapA, at * kAtomK, tile * kTileRows, full_bar(s));
+                tma_load_2d(smem_base + s * kStageBytes + kABytes, &tmapB, lk * a.Kp + at * kAtomK, row0, full_bar(s));
               }
             }
           }
@@ -242,8 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * kAccCols;
             uint32_t first = 1;
-            for (int limb = 0; limb < a.limbs; ++limb) {
-              for (int at = a0; at < a.atoms; ++at, ++it) {
+            for (int at = a0; at < a.atoms; ++at) {
+              for (int lk = 0; lk < a.kl; ++lk, ++it) {
                 const int s = it % kStages;
                 mbar_wait(full_bar(s), (it / kStages) & 1);
                 tc_fence_after();
@@ -263,80 +299,77 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
       }
     }
   } else if (warp < kEpilogueWarp0) {
-    // ===================== builders: A slices, global -> swizzled smem =====================
-    const int group = (warp - kBuilderWarp0) >> 2;                  // 0 or 1: even / odd slices
-    const int t = threadIdx.x - (kBuilderWarp0 + 4 * group) * 32;   // 0..127 within the group
-    const int chunk = t & 7;                                        // 16-byte chunk within the 128-byte row
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const size_t row_base = (size_t)tile * kTileRows;
-      for (int part = 0; part < parts; ++part) {
-        const int hi = a.with_hi && part == 0;
-        for (int c = 0; c < a.nchunks; ++c) {
-          const int a0 = first_atom(a, hi, c);
-          for (int limb = 0; limb < a.limbs; ++limb) {
-            for (int at = a0; at < a.atoms; ++at, ++it) {
-              if ((int)(it & 1) != group) continue;
-              const int s = it % kStages;
-              const int col = at * kAtomK + chunk * 16;             // first coefficient of this thread's chunk
-              uint4 val[8];
+    // ===================== DEC1 transform: e (uint16, global) -> byte-limb A slices (swizzled smem) =====
+    if (MODE == DEC1) {
+      const int t = threadIdx.x - kBuilderWarp0 * 32;      // 0..255
+      const int chunk = t & 7;                             // 16-byte chunk of the 128-byte A row
+      const int r0 = t >> 3;                               // rows r0, r0+32, r0+64, r0+96
+      const uint16_t *src = reinterpret_cast<const uint16_t *>(a.a_src);
+      auto load_atom = [&](const AtomIter &w, uint4 (&raw)[8]) {
+        const int col = w.at * kAtomK + chunk * 16;        // first coefficient of this thread's chunk
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int r_in = j * 16 + (t >> 3);
-                const size_t row = row_base + r_in;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (row < a.B && col < a.P) {
-                  if (MODE == DEC1) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(a.a_src) +
-                                                                        row * (size_t)a.P + col);
-                    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
-                    if (limb == 0) {
-                      v.x = __byte_perm(w0.x, w0.y, 0x6420);
-                      v.y = __byte_perm(w0.z, w0.w, 0x6420);
-                      v.z = __byte_perm(w1.x, w1.y, 0x6420);
-                      v.w = __byte_perm(w1.z, w1.w, 0x6420);
-                    } else {   // (e >> 8) << 2 in the low byte of each 16-bit field
-                      v.x = __byte_perm((w0.x >> 6) & 0x00FC00FCu, (w0.y >> 6) & 0x00FC00FCu, 0x6420);
-                      v.y = __byte_perm((w0.z >> 6) & 0x00FC00FCu, (w0.w >> 6) & 0x00FC00FCu, 0x6420);
-                      v.z = __byte_perm((w1.x >> 6) & 0x00FC00FCu, (w1.y >> 6) & 0x00FC00FCu, 0x6420);
-                      v.w = __byte_perm((w1.z >> 6) & 0x00FC00FCu, (w1.w >> 6) & 0x00FC00FCu, 0x6420);
-                    }
-                  } else {
-                    v = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(a.a_src) +
-                                                              row * (size_t)a.P + col));
-                    if (limb == 1) {   // r << 5 per byte
-                      v.x = (v.x << 5) & 0xE0E0E0E0u;
-                      v.y = (v.y << 5) & 0xE0E0E0E0u;
-                      v.z = (v.z << 5) & 0xE0E0E0E0u;
-                      v.w = (v.w << 5) & 0xE0E0E0E0u;
-                    }
-                  }
-                }
-                val[j] = v;
-              }
-              mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-              uint8_t *dstA = smem + (size_t)s * kStageBytes;
+        for (int j = 0; j < 4; ++j) {
+          const size_t row = (size_t)w.tile * kTileRows + r0 + 32 * j;
+          const bool ok = w.valid && row < a.B && col < a.P;
+          const uint4 *ptr = reinterpret_cast<const uint4 *>(src + (ok ? row * (size_t)a.P + col : 0));
+          uint4 x0 = __ldg(ptr), x1 = __ldg(ptr + 1);
+          if (!ok) x0 = x1 = make_uint4(0, 0, 0, 0);
+          raw[2 * j] = x0;
+          raw[2 * j + 1] = x1;
+        }
+      };
+      AtomIter cur, nxt;
+      cur.start(a);
+      uint4 raw[8], raw_next[8];
+      if (cur.valid) load_atom(cur, raw);
+      uint32_t it = 0;
+      while (cur.valid) {
+        nxt = cur;
+        nxt.next(a);
+        load_atom(nxt, raw_next);                           // prefetch one atom ahead (zeros when !valid)
+        const int s0 = it % kStages, s1 = (it + 1) % kStages;
+        mbar_wait(empty_bar(s0), ((it / kStages) & 1) ^ 1);
+        if (a.kl == 2) mbar_wait(empty_bar(s1), (((it + 1) / kStages) & 1) ^ 1);
+        uint8_t *dst0 = smem + (size_t)s0 * kStageBytes;
+        uint8_t *dst1 = smem + (size_t)s1 * kStageBytes;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int r_in = j * 16 + (t >> 3);
-                const int off = (r_in >> 3) * 1024 + (r_in & 7) * 128 + ((chunk ^ (r_in & 7)) << 4);
-                *reinterpret_cast<uint4 *>(dstA + off) = val[j];
-              }
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(full_bar(s));
-            }
+        for (int j = 0; j < 4; ++j) {
+          const int r_in = r0 + 32 * j;
+          const int off = (r_in >> 3) * 1024 + (r_in & 7) * 128 + ((chunk ^ (r_in & 7)) << 4);
+          const uint4 w0 = raw[2 * j], w1 = raw[2 * j + 1];
+          uint4 lo;
+          lo.x = __byte_perm(w0.x, w0.y, 0x6420);
+          lo.y = __byte_perm(w0.z, w0.w, 0x6420);
+          lo.z = __byte_perm(w1.x, w1.y, 0x6420);
+          lo.w = __byte_perm(w1.z, w1.w, 0x6420);
+          *reinterpret_cast<uint4 *>(dst0 + off) = lo;
+          if (a.kl == 2) {                                  // (e >> 8) << 2 in the low byte of each 16-bit field
+            uint4 hi4;
+            hi4.x = __byte_perm((w0.x >> 6) & 0x00FC00FCu, (w0.y >> 6) & 0x00FC00FCu, 0x6420);
+            hi4.y = __byte_perm((w0.z >> 6) & 0x00FC00FCu, (w0.w >> 6) & 0x00FC00FCu, 0x6420);
+            hi4.z = __byte_perm((w1.x >> 6) & 0x00FC00FCu, (w1.y >> 6) & 0x00FC00FCu, 0x6420);
+            hi4.w = __byte_perm((w1.z >> 6) & 0x00FC00FCu, (w1.w >> 6) & 0x00FC00FCu, 0x6420);
+            *reinterpret_cast<uint4 *>(dst1 + off) = hi4;
           }
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(full_bar(s0));
+          if (a.kl == 2) mbar_arrive(full_bar(s1));
+        }
+        it += a.kl;
+        cur = nxt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) raw[j] = raw_next[j];
       }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int ew = warp - kEpilogueWarp0;          // 0..7
     const int quad = warp & 3;                     // TMEM lanes [32*quad, 32*quad+32) are this warp's
-    const int half = ew >> 2;                      // which column groups
-    const int ngroups32 = a.NC >> 5;
-    const int tail16 = (a.NC & 31) ? 1 : 0;
+    const int half = ew >> 2;                      // units half, half+2, ...
+    const int units = a.NCo >> 4;
     const uint32_t halfq = (uint32_t)a.q >> 1;
     uint32_t cc = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -347,76 +380,84 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
         const int hi = a.with_hi && part == 0;
         for (int c = 0; c < a.nchunks; ++c, ++cc) {
           const int buf = cc & 1;
+          // ENC: fetch this thread's message bytes for the whole chunk before waiting on the accumulator
+          uint4 mm[kMaxUnits];
+          if (MODE == ENC && !hi) {
+#pragma unroll
+            for (int ui = 0; ui < kMaxUnits; ++ui) {
+              const int kk = c * a.NCo + (half + 2 * ui) * 16;
+              const bool ok = row_ok && (half + 2 * ui) < units && kk < a.P;
+              mm[ui] = ok ? __ldg(reinterpret_cast<const uint4 *>(a.m + rbase + kk)) : make_uint4(0, 0, 0, 0);
+            }
+          }
           mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
           tc_fence_after();
           const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
-          for (int g = half; g < ngroups32 + tail16; g += 2) {
-            uint32_t v[32];
-            const int ncols = g < ngroups32 ? 32 : 16;
-            if (ncols == 32)
-              tmem_ld32(t_addr + g * 32, v);
-            else
-              tmem_ld16(t_addr + g * 32, v);
-            tmem_ld_wait();
-            const int k0 = c * a.NC + g * 32;
 #pragma unroll
-            for (int h16 = 0; h16 < 2; ++h16) {
-              if (h16 * 16 >= ncols) break;
-              const int kk = k0 + h16 * 16;
-              if (!row_ok || kk >= a.P) continue;
-              uint32_t w[16];
+          for (int ui = 0; ui < kMaxUnits; ++ui) {
+            const int u = half + 2 * ui;
+            if (u >= units) break;
+            uint32_t w[32];
+            tmem_ld16(t_addr + u * 16, w);
+            if (MODE == ENC && a.nl == 2) {
+              uint32_t w1[32];
+              tmem_ld16(t_addr + a.NCo + u * 16, w1);
+              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] = v[h16 * 16 + j];
-              if (MODE == ENC || MODE == DEC1) {
-                if (hi) {
+              for (int j = 0; j < 16; ++j) w[j] += w1[j] << 8;
+            } else {
+              tmem_ld_wait();
+            }
+            const int kk = c * a.NCo + u * 16;
+            if (!row_ok || kk >= a.P) continue;
+            if (MODE == ENC || MODE == DEC1) {
+              if (hi) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) w[j] = (0u - w[j]) & a.qmask;
-                } else if (MODE == ENC) {
-                  const uint4 mm = __ldg(reinterpret_cast<const uint4 *>(a.m + rbase + kk));
-                  const uint32_t mw[4] = {mm.x, mm.y, mm.z, mm.w};
+                for (int j = 0; j < 16; ++j) w[j] = (0u - w[j]) & a.qmask;
+              } else if (MODE == ENC) {
+                const uint32_t mw[4] = {mm[ui].x, mm[ui].y, mm[ui].z, mm[ui].w};
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const uint32_t mj = (mw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    w[j] = (kk + j < a.N) ? ((w[j] + mj) & a.qmask) : 0u;
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) w[j] &= a.qmask;
+                for (int j = 0; j < 16; ++j) {
+                  const uint32_t mj = (mw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                  w[j] = (kk + j < a.N) ? ((w[j] + mj) & a.qmask) : 0u;
                 }
-                uint4 p0 = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
-                uint4 p1 = make_uint4(w[8] | (w[9] << 16), w[10] | (w[11] << 16), w[12] | (w[13] << 16),
-                                      w[14] | (w[15] << 16));
-                uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
-                if (d0) {
-                  reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
-                  reinterpret_cast<uint4 *>(d0 + rbase + kk)[1] = p1;
-                }
-                if (!hi && a.o16_cyc2) {
-                  reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[0] = p0;
-                  reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[1] = p1;
-                }
-                if (MODE == DEC1 && !hi && a.o8_cyc) {
-                  uint32_t bq[4] = {0, 0, 0, 0};
+              } else {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const uint32_t bj = mod3_small(w[j] + (w[j] > halfq ? 1u : 0u));   // index.js:117
-                    bq[j >> 2] |= bj << (8 * (j & 3));
-                  }
-                  *reinterpret_cast<uint4 *>(a.o8_cyc + rbase + kk) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
-                }
-              } else {   // DEC2: mod 3
+                for (int j = 0; j < 16; ++j) w[j] &= a.qmask;
+              }
+              const uint4 p0 = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
+              const uint4 p1 = make_uint4(w[8] | (w[9] << 16), w[10] | (w[11] << 16), w[12] | (w[13] << 16),
+                                          w[14] | (w[15] << 16));
+              uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
+              if (d0) {
+                reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
+                reinterpret_cast<uint4 *>(d0 + rbase + kk)[1] = p1;
+              }
+              if (!hi && a.o16_cyc2) {
+                reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[0] = p0;
+                reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[1] = p1;
+              }
+              if (MODE == DEC1 && !hi && a.o8_cyc) {
                 uint32_t bq[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  uint32_t x = mod3_small(w[j]);
-                  if (hi) x = mod3_small(3u - x);
-                  bq[j >> 2] |= x << (8 * (j & 3));
+                  const uint32_t bj = mod3_small(w[j] + (w[j] > halfq ? 1u : 0u));   // index.js:117
+                  bq[j >> 2] |= bj << (8 * (j & 3));
                 }
-                const uint4 pk = make_uint4(bq[0], bq[1], bq[2], bq[3]);
-                uint8_t *d0 = hi ? a.o8_hi : a.o8_cyc;
-                if (d0) *reinterpret_cast<uint4 *>(d0 + rbase + kk) = pk;
-                if (!hi && a.o8_cyc2) *reinterpret_cast<uint4 *>(a.o8_cyc2 + rbase + kk) = pk;
+                *reinterpret_cast<uint4 *>(a.o8_cyc + rbase + kk) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
               }
+            } else {   // DEC2: mod 3
+              uint32_t bq[4] = {0, 0, 0, 0};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                uint32_t x = mod3_small(w[j]);
+                if (hi) x = mod3_small(3u - x);
+                bq[j >> 2] |= x << (8 * (j & 3));
+              }
+              const uint4 pk = make_uint4(bq[0], bq[1], bq[2], bq[3]);
+              uint8_t *d0 = hi ? a.o8_hi : a.o8_cyc;
+              if (d0) *reinterpret_cast<uint4 *>(d0 + rbase + kk) = pk;
+              if (!hi && a.o8_cyc2) *reinterpret_cast<uint4 *>(a.o8_cyc2 + rbase + kk) = pk;
             }
           }
           tc_fence_before();
@@ -435,15 +476,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_product(const UmmaArgs a, 
   }
 }
 
-// ---- key matrix: Mat[row][kb], row = part * cols + k (part 0 = cyc, 1 = hi), kb = limb * Kp + i -------------
-__global__ void k_build_keymat(int mode, int N, int Kp, int limbs, int cols, const void *poly, uint8_t *mat) {
-  const int klen = limbs * Kp;
-  const size_t total = (size_t)2 * cols * klen;
+// ---- key matrix ---------------------------------------------------------------------------------
+// Mat[row][kb]: row = ((part * nchunks + c) * nl + ln) * NCo + j  (part 0 = cyc, 1 = hi; output k = c*NCo + j),
+//               kb  = lk * Kp + i.
+__global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, int NCo, int nchunks, const void *poly,
+                               uint8_t *mat) {
+  const int klen = kl * Kp;
+  const size_t total = (size_t)2 * nchunks * nl * NCo * klen;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int kb = (int)(idx % klen);
-    const int row = (int)(idx / klen);
-    const int part = row / cols, k = row % cols;
-    const int limb = kb / Kp, i = kb % Kp;
+    int row = (int)(idx / klen);
+    const int j = row % NCo; row /= NCo;
+    const int ln = row % nl; row /= nl;
+    const int c = row % nchunks;
+    const int part = row / nchunks;
+    const int k = c * NCo + j;
+    const int lk = kb / Kp, i = kb % Kp;
     int coef = 0;
     bool nz = k < N && i < N;
     int src = 0;
@@ -462,8 +510,8 @@ __global__ void k_build_keymat(int mode, int N, int Kp, int limbs, int cols, con
       else coef = reinterpret_cast<const uint8_t *>(poly)[src];
     }
     uint8_t out;
-    if (mode == ENC) out = limb == 0 ? (uint8_t)(coef & 0xff) : (uint8_t)((coef >> 8) << 3);
-    else if (mode == DEC1) out = (uint8_t)(int8_t)(limb == 0 ? coef : coef * 64);
+    if (mode == ENC) out = ln == 0 ? (uint8_t)(coef & 0xff) : (uint8_t)(coef >> 8);
+    else if (mode == DEC1) out = (uint8_t)(int8_t)(lk == 0 ? coef : coef * 64);
     else out = (uint8_t)coef;
     mat[idx] = out;
   }
@@ -485,58 +533,78 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-void geometry(const ntru_ctx *ctx, int limbs, KeyMatrix &km) {
+void geometry(const ntru_ctx *ctx, int kl, int nl, KeyMatrix &km) {
   const int N = ctx->N;
-  km.limbs = limbs;
-  km.nchunks = (N + 255) / 256;
+  km.limbs = kl;
+  km.nlimbs = nl;
+  const int max_out = 256 / nl;                       // output coefficients one 256-column accumulator holds
+  km.nchunks = (N + max_out - 1) / max_out;
   const int per = (N + km.nchunks - 1) / km.nchunks;
-  km.chunk_cols = ((per + 15) / 16) * 16;
+  km.out_cols = ((per + 15) / 16) * 16;
+  km.chunk_cols = km.out_cols * nl;
   const int Kp = ((N + kAtomK - 1) / kAtomK) * kAtomK;
-  km.klen = limbs * Kp;
+  km.klen = kl * Kp;
 }
 
-int build_keymat(ntru_ctx *ctx, int mode, int limbs, const void *poly, KeyMatrix &km) {
-  geometry(ctx, limbs, km);
-  const int cols = km.nchunks * km.chunk_cols;
-  const int Kp = km.klen / limbs;
-  const size_t bytes = (size_t)2 * cols * km.klen;
+int encode_2d(ntru_ctx *ctx, void *out, void *base, uint64_t inner, uint64_t rows, uint64_t stride_bytes, uint32_t box_inner,
+              uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return NTRU_OK;
+}
+
+int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyMatrix &km) {
+  geometry(ctx, kl, nl, km);
+  const int rows = 2 * km.nchunks * km.chunk_cols;
+  const int Kp = km.klen / kl;
+  const size_t bytes = (size_t)rows * km.klen;
   NTRU_CUDA(ctx, km.mat.reserve(bytes));
   {
     LaunchTimer timer(ctx, NTRU_K_OTHER);
-    k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, limbs, cols, poly, (uint8_t *)km.mat.ptr);
+    k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, kl, nl, km.out_cols, km.nchunks, poly,
+                                                               (uint8_t *)km.mat.ptr);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {(cuuint64_t)km.klen, (cuuint64_t)(2 * cols)};
-  cuuint64_t gstride[1] = {(cuuint64_t)km.klen};
-  cuuint32_t box[2] = {(cuuint32_t)kAtomK, (cuuint32_t)km.chunk_cols};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(reinterpret_cast<CUtensorMap *>(km.tmap), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, km.mat.ptr, gdim, gstride,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  int rc = encode_2d(ctx, km.tmap, km.mat.ptr, (uint64_t)km.klen, (uint64_t)rows, (uint64_t)km.klen, kAtomK,
+                     (uint32_t)km.chunk_cols);
+  if (rc) return rc;
   NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   km.ready = true;
   return NTRU_OK;
 }
 
 template <int MODE>
-int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a) {
+int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *a_bytes) {
   static bool attr_set = false;
   if (!attr_set) {
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_product<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
-  a.N = ctx->N; a.P = ctx->P; a.limbs = km.limbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
-  a.NC = km.chunk_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
+  a.N = ctx->N; a.P = ctx->P; a.kl = km.limbs; a.nl = km.nlimbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
+  a.NC = km.chunk_cols; a.NCo = km.out_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
   a.ntiles = (int)((a.B + kTileRows - 1) / kTileRows);
   const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
-  CUtensorMap tm;
-  memcpy(&tm, km.tmap, sizeof tm);
+  CUtensorMap tmB, tmA;
+  memcpy(&tmB, km.tmap, sizeof tmB);
+  memset(&tmA, 0, sizeof tmA);
+  if (MODE != DEC1) {
+    // byte rows straight into the UMMA layout: inner extent N (columns beyond read as zero), row pitch P
+    if (((uintptr_t)a_bytes & 15) != 0) return fail(ctx, NTRU_E_PARAM, "device rows must be 16-byte aligned");
+    int rc = encode_2d(ctx, &tmA, const_cast<void *>(a_bytes), (uint64_t)ctx->N, (uint64_t)a.B, (uint64_t)ctx->P, kAtomK,
+                       kTileRows);
+    if (rc) return rc;
+  }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
-    k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tm);
+    k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
@@ -556,25 +624,25 @@ int umma_init(ntru_ctx *ctx) {
 }
 
 int umma_prepare_public(ntru_ctx *ctx) {
-  return build_keymat(ctx, ENC, ctx->q > 256 ? 2 : 1, ctx->d_h.ptr, ctx->km_h);
+  return build_keymat(ctx, ENC, 1, ctx->q > 256 ? 2 : 1, ctx->d_h.ptr, ctx->km_h);
 }
 
 int umma_prepare_private(ntru_ctx *ctx) {
-  int rc = build_keymat(ctx, DEC1, ctx->q > 256 ? 2 : 1, ctx->d_f.ptr, ctx->km_f);
+  int rc = build_keymat(ctx, DEC1, ctx->q > 256 ? 2 : 1, 1, ctx->d_f.ptr, ctx->km_f);
   if (rc) return rc;
-  return build_keymat(ctx, DEC2, 1, ctx->d_fp.ptr, ctx->km_fp);
+  return build_keymat(ctx, DEC2, 1, 1, ctx->d_fp.ptr, ctx->km_fp);
 }
 
 int umma_encrypt(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m, uint16_t *value, uint16_t *quo,
                  uint16_t *rem) {
   if (B == 0) return NTRU_OK;
   UmmaArgs a = {};
-  a.B = B; a.a_src = r; a.m = m;
+  a.B = B; a.m = m;
   a.with_hi = quo != nullptr;
   a.o16_cyc = value ? value : rem;
   a.o16_cyc2 = value ? rem : nullptr;
   a.o16_hi = quo;
-  return launch_product<ENC>(ctx, ctx->km_h, a);
+  return launch_product<ENC>(ctx, ctx->km_h, a, r);
 }
 
 int umma_decrypt(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2,
@@ -585,15 +653,15 @@ int umma_decrypt(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uin
   a.B = B; a.a_src = e;
   a.with_hi = q1 != nullptr;
   a.o16_cyc = r1; a.o16_hi = q1; a.o8_cyc = (uint8_t *)ctx->d_b.ptr;
-  int rc = launch_product<DEC1>(ctx, ctx->km_f, a);
+  int rc = launch_product<DEC1>(ctx, ctx->km_f, a, nullptr);
   if (rc) return rc;
   UmmaArgs b = {};
-  b.B = B; b.a_src = ctx->d_b.ptr;
+  b.B = B;
   b.with_hi = q2 != nullptr;
   b.o8_cyc = value ? value : r2;
   b.o8_cyc2 = value ? r2 : nullptr;
   b.o8_hi = q2;
-  return launch_product<DEC2>(ctx, ctx->km_fp, b);
+  return launch_product<DEC2>(ctx, ctx->km_fp, b, ctx->d_b.ptr);
 }
 
 }  // namespace ntru
