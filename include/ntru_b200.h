@@ -52,7 +52,8 @@ enum {
 enum {
   NTRU_OPT_PATH = 1,        /* 0 auto, 1 force CUDA-core schedule, 2 force tcgen05 tensor schedule (same-key only) */
   NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
-  NTRU_OPT_TIMING = 3       /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
+  NTRU_OPT_TIMING = 3,      /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
+  NTRU_OPT_TENSOR_VARIANT = 4 /* tcgen05 schedule: 0 = CTA-pair kernel (cta_group::2, default), 1 = single-CTA kernel */
 };
 
 /* kernel kinds reported by ntru_timing_read */

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libntru_b200.so")
 SOURCES = ["api.cu", "generic_kernels.cu", "umma_kernels.cu"]
-HEADERS = ["ntru_internal.cuh", os.path.join("..", "..", "include", "ntru_b200.h")]
+HEADERS = ["ntru_internal.cuh", "umma_pair.cuh", os.path.join("..", "..", "include", "ntru_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -262,6 +262,10 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
     case NTRU_OPT_TIMING:
       ctx->timing = value != 0;
       return NTRU_OK;
+    case NTRU_OPT_TENSOR_VARIANT:
+      if (value < 0 || value > 1) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_TENSOR_VARIANT must be 0 or 1");
+      ctx->tensor_variant = (int)value;
+      return NTRU_OK;
     default:
       return fail(ctx, NTRU_E_PARAM, "unknown option");
   }

@@ -37,7 +37,8 @@ struct DevBuf {
 // Operand matrices of the tcgen05 schedule for one fixed key polynomial (see umma_kernels.cu).
 struct KeyMatrix {
   DevBuf mat;            // [2*ncols_pad][klen] bytes, K-major
-  alignas(64) unsigned char tmap[128];   // CUtensorMap
+  alignas(64) unsigned char tmap[128];        // CUtensorMap, box = NC rows (single-CTA kernel)
+  alignas(64) unsigned char tmap_half[128];   // CUtensorMap, box = NC/2 rows (CTA-pair kernel)
   bool ready = false;
   int limbs = 0, nlimbs = 0, klen = 0, nchunks = 0, chunk_cols = 0, out_cols = 0;
 };
@@ -59,6 +60,7 @@ struct ntru_ctx {
   ntru::DevBuf d_partial;
   size_t chunk_rows = 32768;
   int opt_path = 0;
+  int tensor_variant = 0;          // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
   int last_path = 0;
   int sm_count = 148;
   bool tensor_ok = false;          // device is sm_100 and the tcgen05 schedule initialised

@@ -27,7 +27,7 @@
 //
 // Warp roles (576 threads, 1 CTA per SM, persistent over row tiles):
 //   warp 0      TMA producer (A and B slices)      warp 1      tcgen05.mma issuer, owns TMEM
-//   warps 2-9   DEC1 only: e -> byte-limb A slices warps 10-17 epilogue (TMEM -> registers -> global)
+//   warps 2-9   DEC1: e -> byte-limb A slices; ENC / DEC2: epilogue   warps 10-17 epilogue (TMEM -> regs -> global)
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers) and two 256-column TMEM accumulators
 // (tmem_full/tmem_empty mbarriers) so that the epilogue of chunk j overlaps the MMAs of chunk j+1.
 
@@ -64,6 +64,10 @@ struct UmmaArgs {
   uint32_t qmask;
   size_t B;
   int ntiles;
+  // 2-CTA variant (umma_pair.cuh)
+  int npairs;             // 256-row pair tiles
+  int nA, nB;             // shared-memory slots for A and stages for B
+  int a_resident;         // A slots hold the whole tile (loaded once per tile)
   const void *a_src;      // DEC1: e rows (uint16), pitch P elements
   const uint8_t *m;       // ENC: message rows
   uint16_t *o16_cyc;      // ENC: value, DEC1: remainder1
@@ -195,7 +199,123 @@ struct AtomIter {
   }
 };
 
-constexpr int kMaxUnits = 8;   // 16-coefficient units one epilogue warp handles per chunk (256 / 16 / 2)
+// One accumulator chunk of one epilogue warp: prefetch what the chunk needs from global memory, wait for the
+// MMAs, then TMEM -> registers -> reduction / fold / witness -> global.  `sub` = this warp's index among the kSub
+// warps of its TMEM lane quadrant; it owns the 16-coefficient units sub, sub + kSub, ...
+template <int MODE, int kSub, class WaitFn>
+__device__ __forceinline__ void epilogue_chunk(const UmmaArgs &a, int hi, int c, int sub, bool row_ok, size_t rbase,
+                                               uint32_t t_addr, WaitFn wait_acc) {
+  constexpr int kUnitsPerWarp = 16 / kSub;
+  const int units = a.NCo >> 4;
+  const uint32_t Q2 = a.qmask | (a.qmask << 16);             // the modulus mask in both 16-bit lanes
+  const uint32_t lift_add = ((uint32_t)a.q >> 1) - 1;        // x > q/2  <=>  (x + q/2 - 1) >> log2(q)
+  const int logq = 31 - __clz(a.q);
+  // ENC: fetch this thread's message bytes for the whole chunk before waiting on the accumulator;
+  // bytes of coefficients >= N are cleared so that the pad of every output row is written as zero
+  uint4 mm[kUnitsPerWarp];
+  if (MODE == ENC && !hi) {
+#pragma unroll
+    for (int ui = 0; ui < kUnitsPerWarp; ++ui) {
+      const int u = sub + kSub * ui;
+      const int kk = c * a.NCo + u * 16;
+      const bool ok = row_ok && u < units && kk < a.N;
+      uint4 x = ok ? __ldg(reinterpret_cast<const uint4 *>(a.m + rbase + kk)) : make_uint4(0, 0, 0, 0);
+      const int nvalid = a.N - kk;
+      if (ok && nvalid < 16) {
+        uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+          const int nb = nvalid - 4 * wd;               // valid bytes in this word
+          xs[wd] = nb >= 4 ? xs[wd] : (nb <= 0 ? 0u : (xs[wd] & (0xffffffffu >> (8 * (4 - nb)))));
+        }
+        x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+      }
+      mm[ui] = x;
+    }
+  }
+  wait_acc();
+  tc_fence_after();
+#pragma unroll
+  for (int ui = 0; ui < kUnitsPerWarp; ++ui) {
+    const int u = sub + kSub * ui;
+    if (u >= units) break;
+    uint32_t w[32];
+    tmem_ld16(t_addr + u * 16, w);
+    if (MODE == ENC && a.nl == 2) {
+      uint32_t w1[32];
+      tmem_ld16(t_addr + a.NCo + u * 16, w1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] += w1[j] << 8;
+    } else {
+      tmem_ld_wait();
+    }
+    const int kk = c * a.NCo + u * 16;
+    if (!row_ok || kk >= a.P) continue;
+    if (MODE == ENC || MODE == DEC1) {
+      // two coefficients per 32-bit word, reduced mod q in both lanes at once
+      uint32_t pk[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) pk[jj] = __byte_perm(w[2 * jj], w[2 * jj + 1], 0x5410);
+      if (hi) {             // -hi mod q = ((q-1-x) + 1) mod q, no carry between lanes
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) pk[jj] = ((~pk[jj] & Q2) + 0x00010001u) & Q2;
+      } else if (MODE == ENC) {
+        const uint32_t mw[4] = {mm[ui].x, mm[ui].y, mm[ui].z, mm[ui].w};
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint32_t mp = __byte_perm(mw[jj >> 1], 0u, (jj & 1) ? 0x4342 : 0x4140);   // bytes -> lanes
+          pk[jj] = ((pk[jj] & Q2) + mp) & Q2;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) pk[jj] &= Q2;
+      }
+      const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      const uint4 p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
+      if (d0) {
+        reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
+        reinterpret_cast<uint4 *>(d0 + rbase + kk)[1] = p1;
+      }
+      if (!hi && a.o16_cyc2) {
+        reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[0] = p0;
+        reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[1] = p1;
+      }
+      if (MODE == DEC1 && !hi && a.o8_cyc) {
+        uint32_t bq[4];
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+          uint32_t bb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t x = w[4 * wd + j] & a.qmask;
+            const uint32_t y = x + ((x + lift_add) >> logq);          // index.js:117
+            bb[j] = y - 3u * __umulhi(y, 0x55555556u);
+          }
+          bq[wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
+        }
+        *reinterpret_cast<uint4 *>(a.o8_cyc + rbase + kk) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
+      }
+    } else {   // DEC2: mod 3 (hi: -x mod 3 = 2x mod 3)
+      uint32_t bq[4];
+#pragma unroll
+      for (int wd = 0; wd < 4; ++wd) {
+        uint32_t bb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t y = hi ? 2u * w[4 * wd + j] : w[4 * wd + j];
+          bb[j] = y - 3u * __umulhi(y, 0x55555556u);
+        }
+        bq[wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
+      }
+      const uint4 pk4 = make_uint4(bq[0], bq[1], bq[2], bq[3]);
+      uint8_t *d0 = hi ? a.o8_hi : a.o8_cyc;
+      if (d0) *reinterpret_cast<uint4 *>(d0 + rbase + kk) = pk4;
+      if (!hi && a.o8_cyc2) *reinterpret_cast<uint4 *>(a.o8_cyc2 + rbase + kk) = pk4;
+    }
+  }
+}
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <int MODE>
@@ -222,7 +342,7 @@ k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);        // tcgen05.commit
-      mbar_init(tempty_bar(b), 8);       // 8 epilogue warps
+      mbar_init(tempty_bar(b), MODE == DEC1 ? 8 : 16);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -298,9 +418,9 @@ k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, cons
         }
       }
     }
-  } else if (warp < kEpilogueWarp0) {
+  } else if (MODE == DEC1 && warp < kEpilogueWarp0) {
     // ===================== DEC1 transform: e (uint16, global) -> byte-limb A slices (swizzled smem) =====
-    if (MODE == DEC1) {
+    {
       const int t = threadIdx.x - kBuilderWarp0 * 32;      // 0..255
       const int chunk = t & 7;                             // 16-byte chunk of the 128-byte A row
       const int r0 = t >> 3;                               // rows r0, r0+32, r0+64, r0+96
@@ -366,11 +486,11 @@ k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, cons
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int ew = warp - kEpilogueWarp0;          // 0..7
+    // DEC1: warps 10-17 (2 per TMEM lane quadrant); ENC / DEC2: warps 2-17 (4 per quadrant).
+    constexpr int kSub = MODE == DEC1 ? 2 : 4;                 // epilogue warps per quadrant
+    const int ew = warp - (MODE == DEC1 ? kEpilogueWarp0 : kBuilderWarp0);
     const int quad = warp & 3;                     // TMEM lanes [32*quad, 32*quad+32) are this warp's
-    const int half = ew >> 2;                      // units half, half+2, ...
-    const int units = a.NCo >> 4;
-    const uint32_t halfq = (uint32_t)a.q >> 1;
+    const int sub = ew >> 2;                       // this warp's units: sub, sub + kSub, ...
     uint32_t cc = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const size_t row = (size_t)tile * kTileRows + quad * 32 + lane;
@@ -380,86 +500,9 @@ k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, cons
         const int hi = a.with_hi && part == 0;
         for (int c = 0; c < a.nchunks; ++c, ++cc) {
           const int buf = cc & 1;
-          // ENC: fetch this thread's message bytes for the whole chunk before waiting on the accumulator
-          uint4 mm[kMaxUnits];
-          if (MODE == ENC && !hi) {
-#pragma unroll
-            for (int ui = 0; ui < kMaxUnits; ++ui) {
-              const int kk = c * a.NCo + (half + 2 * ui) * 16;
-              const bool ok = row_ok && (half + 2 * ui) < units && kk < a.P;
-              mm[ui] = ok ? __ldg(reinterpret_cast<const uint4 *>(a.m + rbase + kk)) : make_uint4(0, 0, 0, 0);
-            }
-          }
-          mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
-          tc_fence_after();
           const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
-#pragma unroll
-          for (int ui = 0; ui < kMaxUnits; ++ui) {
-            const int u = half + 2 * ui;
-            if (u >= units) break;
-            uint32_t w[32];
-            tmem_ld16(t_addr + u * 16, w);
-            if (MODE == ENC && a.nl == 2) {
-              uint32_t w1[32];
-              tmem_ld16(t_addr + a.NCo + u * 16, w1);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w[j] += w1[j] << 8;
-            } else {
-              tmem_ld_wait();
-            }
-            const int kk = c * a.NCo + u * 16;
-            if (!row_ok || kk >= a.P) continue;
-            if (MODE == ENC || MODE == DEC1) {
-              if (hi) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] = (0u - w[j]) & a.qmask;
-              } else if (MODE == ENC) {
-                const uint32_t mw[4] = {mm[ui].x, mm[ui].y, mm[ui].z, mm[ui].w};
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const uint32_t mj = (mw[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                  w[j] = (kk + j < a.N) ? ((w[j] + mj) & a.qmask) : 0u;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] &= a.qmask;
-              }
-              const uint4 p0 = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
-              const uint4 p1 = make_uint4(w[8] | (w[9] << 16), w[10] | (w[11] << 16), w[12] | (w[13] << 16),
-                                          w[14] | (w[15] << 16));
-              uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
-              if (d0) {
-                reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
-                reinterpret_cast<uint4 *>(d0 + rbase + kk)[1] = p1;
-              }
-              if (!hi && a.o16_cyc2) {
-                reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[0] = p0;
-                reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[1] = p1;
-              }
-              if (MODE == DEC1 && !hi && a.o8_cyc) {
-                uint32_t bq[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const uint32_t bj = mod3_small(w[j] + (w[j] > halfq ? 1u : 0u));   // index.js:117
-                  bq[j >> 2] |= bj << (8 * (j & 3));
-                }
-                *reinterpret_cast<uint4 *>(a.o8_cyc + rbase + kk) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
-              }
-            } else {   // DEC2: mod 3
-              uint32_t bq[4] = {0, 0, 0, 0};
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                uint32_t x = mod3_small(w[j]);
-                if (hi) x = mod3_small(3u - x);
-                bq[j >> 2] |= x << (8 * (j & 3));
-              }
-              const uint4 pk = make_uint4(bq[0], bq[1], bq[2], bq[3]);
-              uint8_t *d0 = hi ? a.o8_hi : a.o8_cyc;
-              if (d0) *reinterpret_cast<uint4 *>(d0 + rbase + kk) = pk;
-              if (!hi && a.o8_cyc2) *reinterpret_cast<uint4 *>(a.o8_cyc2 + rbase + kk) = pk;
-            }
-          }
+          epilogue_chunk<MODE, kSub>(a, hi, c, sub, row_ok, rbase, t_addr,
+                                     [&] { mbar_wait(tfull_bar(buf), (cc >> 1) & 1); });
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -475,6 +518,8 @@ k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, cons
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
+
+#include "umma_pair.cuh"
 
 // ---- key matrix ---------------------------------------------------------------------------------
 // Mat[row][kb]: row = ((part * nchunks + c) * nl + ln) * NCo + j  (part 0 = cyc, 1 = hi; output k = c*NCo + j),
@@ -576,6 +621,9 @@ int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyM
   int rc = encode_2d(ctx, km.tmap, km.mat.ptr, (uint64_t)km.klen, (uint64_t)rows, (uint64_t)km.klen, kAtomK,
                      (uint32_t)km.chunk_cols);
   if (rc) return rc;
+  rc = encode_2d(ctx, km.tmap_half, km.mat.ptr, (uint64_t)km.klen, (uint64_t)rows, (uint64_t)km.klen, kAtomK,
+                 (uint32_t)km.chunk_cols / 2);
+  if (rc) return rc;
   NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   km.ready = true;
   return NTRU_OK;
@@ -586,14 +634,22 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   static bool attr_set = false;
   if (!attr_set) {
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_product<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
     attr_set = true;
   }
   a.N = ctx->N; a.P = ctx->P; a.kl = km.limbs; a.nl = km.nlimbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
   a.NC = km.chunk_cols; a.NCo = km.out_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
   a.ntiles = (int)((a.B + kTileRows - 1) / kTileRows);
-  const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
+  a.npairs = (int)((a.B + 2 * kTileRows - 1) / (2 * kTileRows));
+  const int a_slots = a.atoms * a.kl;
+  if (a_slots + 4 <= kPairSlots) {
+    a.a_resident = 1; a.nA = a_slots; a.nB = kPairSlots - a_slots;
+  } else {
+    a.a_resident = 0; a.nA = 6; a.nB = kPairSlots - 6;
+  }
   CUtensorMap tmB, tmA;
-  memcpy(&tmB, km.tmap, sizeof tmB);
+  const bool pair = ctx->tensor_variant == 0;
+  memcpy(&tmB, pair ? km.tmap_half : km.tmap, sizeof tmB);
   memset(&tmA, 0, sizeof tmA);
   if (MODE != DEC1) {
     // byte rows straight into the UMMA layout: inner extent N (columns beyond read as zero), row pitch P
@@ -604,7 +660,13 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
-    k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);
+    if (pair) {
+      const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
+      k_umma_pair<MODE><<<2 * clusters, kThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA);
+    } else {
+      const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
+      k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);
+    }
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
@@ -617,7 +679,7 @@ int umma_init(ntru_ctx *ctx) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return NTRU_OK;
   if (prop.major != 10) return NTRU_OK;                       // tcgen05 needs sm_100a
-  if ((size_t)prop.sharedMemPerBlockOptin < kSmemBytes) return NTRU_OK;
+  if ((size_t)prop.sharedMemPerBlockOptin < kSmemBytes || (size_t)prop.sharedMemPerBlockOptin < kPairSmemBytes) return NTRU_OK;
   if (!get_encode_fn()) return NTRU_OK;
   ctx->tensor_ok = true;
   return NTRU_OK;

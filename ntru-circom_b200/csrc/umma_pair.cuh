@@ -1,0 +1,344 @@
+// 2-CTA variant of the tcgen05 schedule (included by umma_kernels.cu, inside its anonymous namespace).
+//
+// Two CTAs of a cluster (one SM pair) share every B slice: tcgen05.mma.cta_group::2 multiplies a 256-row
+// batch tile (128 rows per CTA, each in its own shared memory and TMEM) against NC accumulator columns whose
+// B rows are split between the two CTAs (NC/2 rows each).  Per ciphertext this halves both the L2 -> SM
+// traffic and the shared-memory reads of the key matrix -- the v2 single-CTA kernel was bound by exactly that
+// (ncu: lts throughput 65-75 % of peak, tensor pipe 34 %).
+//
+// The A operand (128 rows x K bytes per CTA) is kept RESIDENT in shared memory for the whole tile when it
+// fits (every byte-operand mode, DEC1 up to N = 640): it is loaded (TMA) or built (DEC1 transform warps)
+// once per tile instead of once per accumulator chunk.  When it does not fit, A slices stream through a
+// small ring exactly like B slices.
+//
+// Shared memory: 14 slots of 16 KB = nA A-slots + nB B-stages.  Barriers (same offsets in both CTAs):
+//   a_full[i], b_full[j]   : used in the LEADER CTA only; both CTAs' TMA loads / transform warps signal them
+//   a_empty[i], b_empty[j] : in both CTAs, signalled by tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full[b]           : in both CTAs (commit multicast);  tmem_empty[b]: leader only, all epilogue warps
+// Only the leader's warp 1 issues MMAs; producer, transform and epilogue warps run in both CTAs.
+
+constexpr int kSlotBytes = 16384;
+constexpr int kPairSlots = 14;
+constexpr int kPairBars = 4 * kPairSlots + 4;
+constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 8 * kPairBars + 64;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier given by its shared::cluster address (own or peer CTA).  Default semantics (release at CTA
+// scope) on purpose: a cluster-scope release makes ptxas emit MEMBAR.ALL.GPU + ERRBAR, which stalls the epilogue
+// warps until their global stores drain (ncu, profiles/r1_ncu_pair_v1: 40 % of all stall samples); the data these
+// barriers guard is ordered by fence.proxy.async / tcgen05.fence, not by the arrive itself.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of the pair; completion bytes are credited to `bar_cluster` (the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signed, int n) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+// One pipeline slice = one 128-byte K atom of one K limb of one accumulator chunk.
+struct Slice {
+  int T, hi, c, at, lk;
+  uint32_t cc;            // running chunk index (TMEM buffer = cc & 1)
+  uint32_t sb, b_par;     // B ring stage and its phase parity
+  uint32_t sa, a_par;     // A slot and its phase parity
+  uint32_t ia;            // running A-load index (streaming mode)
+  bool a_load;            // this slice (re)loads its A slot
+  bool a_release;         // the MMA frees the A slot after this slice
+  bool chunk_first, chunk_last;
+};
+
+// Calls f(slice) for every slice of this CTA pair in pipeline order; every role walks the same sequence.
+template <class F>
+__device__ __forceinline__ void pair_walk(const UmmaArgs &a, F &&f) {
+  const int parts = a.with_hi ? 2 : 1;
+  uint32_t ib = 0, ia = 0, cc = 0;
+  int titer = 0;
+  for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, ++titer) {
+    for (int part = 0; part < parts; ++part) {
+      const int hi = a.with_hi && part == 0;
+      for (int c = 0; c < a.nchunks; ++c, ++cc) {
+        const int a0 = first_atom(a, hi, c);
+        const bool first_chunk = part == 0 && c == 0, last_chunk = part == parts - 1 && c == a.nchunks - 1;
+        for (int at = a0; at < a.atoms; ++at) {
+          for (int lk = 0; lk < a.kl; ++lk, ++ib) {
+            Slice s;
+            s.T = T; s.hi = hi; s.c = c; s.at = at; s.lk = lk; s.cc = cc;
+            s.sb = ib % a.nB; s.b_par = (ib / a.nB) & 1;
+            s.ia = ia;
+            if (a.a_resident) {
+              s.sa = at * a.kl + lk; s.a_par = titer & 1; s.a_load = first_chunk; s.a_release = last_chunk;
+            } else {
+              s.sa = ia % a.nA; s.a_par = (ia / a.nA) & 1; s.a_load = true; s.a_release = true;
+              ++ia;
+            }
+            s.chunk_first = at == a0 && lk == 0;
+            s.chunk_last = at == a.atoms - 1 && lk == a.kl - 1;
+            f(s);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kPairSlots * kSlotBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kPairBars);
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](uint32_t i) { return bar0 + 8u * i; };
+  auto a_empty = [&](uint32_t i) { return bar0 + 8u * (kPairSlots + i); };
+  auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * kPairSlots + i); };
+  auto b_empty = [&](uint32_t i) { return bar0 + 8u * (3 * kPairSlots + i); };
+  auto tfull_bar = [&](uint32_t b) { return bar0 + 8u * (4 * kPairSlots + b); };
+  auto tempty_bar = [&](uint32_t b) { return bar0 + 8u * (4 * kPairSlots + 2 + b); };
+  const uint32_t smem_base = smem_u32(smem);
+  auto a_slot = [&](uint32_t i) { return smem_base + i * kSlotBytes; };
+  auto b_slot = [&](uint32_t j) { return smem_base + (a.nA + j) * kSlotBytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr int kEpiWarps = MODE == DEC1 ? 8 : 16;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.nA; ++i) {
+      mbar_init(a_full(i), MODE == DEC1 ? 16 : 2);   // DEC1: 8 transform warps per CTA; else one producer per CTA
+      mbar_init(a_empty(i), 1);                      // tcgen05.commit (multicast)
+    }
+    for (int j = 0; j < a.nB; ++j) {
+      mbar_init(b_full(j), 2);                       // one producer arrival per CTA (+ transaction bytes)
+      mbar_init(b_empty(j), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 2 * kEpiWarps);       // every epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // barrier addresses in the LEADER CTA, usable from either CTA
+  auto lead = [&](uint32_t local_bar) { return mapa_u32(local_bar, 0); };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const int half_rows = a.NC >> 1;
+      const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK, a_bytes = 2u * kABytes;
+      pair_walk(a, [&](const Slice &s) {
+        if (MODE != DEC1 && s.a_load) {
+          mbar_wait(a_empty(s.sa), s.a_par ^ 1);
+          const uint32_t bar = lead(a_full(s.sa));
+          if (leader) mbar_arrive_expect_tx(a_full(s.sa), a_bytes);
+          else mbar_arrive_cluster(bar);
+          tma_load_2d_pair(a_slot(s.sa), &tmapA, s.at * kAtomK, s.T * 256 + (int)rank * kTileRows, bar);
+        }
+        mbar_wait(b_empty(s.sb), s.b_par ^ 1);
+        const uint32_t bar = lead(b_full(s.sb));
+        if (leader) mbar_arrive_expect_tx(b_full(s.sb), b_bytes);
+        else mbar_arrive_cluster(bar);
+        const int row0 = (s.hi * a.nchunks + s.c) * a.NC + (int)rank * half_rows;
+        tma_load_2d_pair(b_slot(s.sb), &tmapB, s.lk * a.Kp + s.at * kAtomK, row0, bar);
+      });
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.NC);
+      uint32_t first = 1;
+      pair_walk(a, [&](const Slice &s) {
+        const uint32_t buf = s.cc & 1;
+        if (s.chunk_first) {
+          mbar_wait(tempty_bar(buf), ((s.cc >> 1) & 1) ^ 1);
+          first = 1;
+        }
+        mbar_wait(b_full(s.sb), s.b_par);
+        if (s.a_load) mbar_wait(a_full(s.sa), s.a_par);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kAccCols;
+        const uint64_t da = make_smem_desc(a_slot(s.sa));
+        const uint64_t db = make_smem_desc(b_slot(s.sb));
+#pragma unroll
+        for (int k = 0; k < kAtomK / 32; ++k) {
+          umma_i8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        umma_commit_pair(b_empty(s.sb));
+        if (s.a_release) umma_commit_pair(a_empty(s.sa));
+        if (s.chunk_last) umma_commit_pair(tfull_bar(buf));
+      });
+    }
+  } else if (MODE == DEC1 && warp < kEpilogueWarp0) {
+    // ===================== DEC1 transform (both CTAs): e (uint16, global) -> byte-limb A slots =====
+    const int t = threadIdx.x - kBuilderWarp0 * 32;      // 0..255
+    const int chunk = t & 7;                             // 16-byte chunk of the 128-byte A row
+    const int r0 = t >> 3;                               // rows r0, r0+32, r0+64, r0+96
+    const uint16_t *src = reinterpret_cast<const uint16_t *>(a.a_src);
+    // work list: the atoms whose A slots must be (re)built, in pipeline order
+    struct Item { int T, part, c, at; uint32_t ia; int titer; bool valid; };
+    const int parts = a.with_hi ? 2 : 1;
+    auto advance = [&](Item &w) {
+      if (a.a_resident) {
+        if (++w.at < a.atoms) return;
+        w.at = 0;
+      } else {
+        w.ia += a.kl;
+        if (++w.at < a.atoms) return;
+        if (++w.c == a.nchunks) {
+          w.c = 0;
+          if (++w.part == parts) w.part = 0; else { w.at = first_atom(a, a.with_hi && w.part == 0, w.c); return; }
+        } else {
+          w.at = first_atom(a, a.with_hi && w.part == 0, w.c);
+          return;
+        }
+      }
+      w.T += gridDim.x >> 1;
+      ++w.titer;
+      w.valid = w.T < a.npairs;
+      w.at = first_atom(a, a.with_hi, 0);
+    };
+    auto load_atom = [&](const Item &w, uint4 (&raw)[8]) {
+      const int col = w.at * kAtomK + chunk * 16;        // first coefficient of this thread's chunk
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t row = (size_t)w.T * 256 + rank * kTileRows + r0 + 32 * j;
+        const bool ok = w.valid && row < a.B && col < a.P;
+        const uint4 *ptr = reinterpret_cast<const uint4 *>(src + (ok ? row * (size_t)a.P + col : 0));
+        uint4 x0 = __ldg(ptr), x1 = __ldg(ptr + 1);
+        if (!ok) x0 = x1 = make_uint4(0, 0, 0, 0);
+        raw[2 * j] = x0;
+        raw[2 * j + 1] = x1;
+      }
+    };
+    Item cur;
+    cur.T = blockIdx.x >> 1; cur.part = 0; cur.c = 0; cur.ia = 0; cur.titer = 0;
+    cur.valid = cur.T < a.npairs;
+    cur.at = first_atom(a, a.with_hi, 0);
+    uint4 raw[8], raw_next[8];
+    if (cur.valid) load_atom(cur, raw);
+    while (cur.valid) {
+      Item nxt = cur;
+      advance(nxt);
+      load_atom(nxt, raw_next);                           // prefetch one atom ahead (zeros when !valid)
+      uint32_t sa0, sa1, par0, par1;
+      if (a.a_resident) {
+        sa0 = cur.at * a.kl; sa1 = sa0 + 1; par0 = par1 = cur.titer & 1;
+      } else {
+        sa0 = cur.ia % a.nA; par0 = (cur.ia / a.nA) & 1;
+        sa1 = (cur.ia + 1) % a.nA; par1 = ((cur.ia + 1) / a.nA) & 1;
+      }
+      mbar_wait(a_empty(sa0), par0 ^ 1);
+      if (a.kl == 2) mbar_wait(a_empty(sa1), par1 ^ 1);
+      uint8_t *dst0 = smem + (size_t)sa0 * kSlotBytes;
+      uint8_t *dst1 = smem + (size_t)sa1 * kSlotBytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r_in = r0 + 32 * j;
+        const int off = (r_in >> 3) * 1024 + (r_in & 7) * 128 + ((chunk ^ (r_in & 7)) << 4);
+        const uint4 w0 = raw[2 * j], w1 = raw[2 * j + 1];
+        uint4 lo;
+        lo.x = __byte_perm(w0.x, w0.y, 0x6420);
+        lo.y = __byte_perm(w0.z, w0.w, 0x6420);
+        lo.z = __byte_perm(w1.x, w1.y, 0x6420);
+        lo.w = __byte_perm(w1.z, w1.w, 0x6420);
+        *reinterpret_cast<uint4 *>(dst0 + off) = lo;
+        if (a.kl == 2) {                                  // (e >> 8) << 2 in the low byte of each 16-bit field
+          uint4 hi4;
+          hi4.x = __byte_perm((w0.x >> 6) & 0x00FC00FCu, (w0.y >> 6) & 0x00FC00FCu, 0x6420);
+          hi4.y = __byte_perm((w0.z >> 6) & 0x00FC00FCu, (w0.w >> 6) & 0x00FC00FCu, 0x6420);
+          hi4.z = __byte_perm((w1.x >> 6) & 0x00FC00FCu, (w1.y >> 6) & 0x00FC00FCu, 0x6420);
+          hi4.w = __byte_perm((w1.z >> 6) & 0x00FC00FCu, (w1.w >> 6) & 0x00FC00FCu, 0x6420);
+          *reinterpret_cast<uint4 *>(dst1 + off) = hi4;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(lead(a_full(sa0)));
+        if (a.kl == 2) mbar_arrive_cluster(lead(a_full(sa1)));
+      }
+      cur = nxt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) raw[j] = raw_next[j];
+    }
+  } else {
+    // ===================== epilogue (both CTAs): TMEM -> registers -> global =====================
+    constexpr int kSub = MODE == DEC1 ? 2 : 4;
+    const int ew = warp - (MODE == DEC1 ? kEpilogueWarp0 : kBuilderWarp0);
+    const int quad = warp & 3;
+    const int sub = ew >> 2;
+    const int parts = a.with_hi ? 2 : 1;
+    uint32_t cc = 0;
+    for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
+      const size_t row = (size_t)T * 256 + rank * kTileRows + quad * 32 + lane;
+      const bool row_ok = row < a.B;
+      const size_t rbase = row * (size_t)a.P;
+      for (int part = 0; part < parts; ++part) {
+        const int hi = a.with_hi && part == 0;
+        for (int c = 0; c < a.nchunks; ++c, ++cc) {
+          const uint32_t buf = cc & 1;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
+          epilogue_chunk<MODE, kSub>(a, hi, c, sub, row_ok, rbase, t_addr,
+                                     [&] { mbar_wait(tfull_bar(buf), (cc >> 1) & 1); });
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead(tempty_bar(buf)));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}

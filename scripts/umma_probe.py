@@ -36,6 +36,7 @@ def main():
         eng.set_public_key(g["h"])
         eng.set_private_key(g["f"], g["fp"])
         eng.set_path(nb.PATH_TENSOR)
+        eng.set_option(4, int(os.environ.get('NTRU_VARIANT', '0')))
         rng = np.random.default_rng(1)
         B = 300
         r = o.sample_ternary_rows(B, N, dr, dr, rng).astype(np.uint8)
