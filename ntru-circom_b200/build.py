@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-    "--use_fast_math",          # only affects float division/transcendentals; none on the hot path
+    "--use_fast_math",         # only affects float division/transcendentals; none on the hot path
 ]
 
 

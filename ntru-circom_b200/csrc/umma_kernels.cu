@@ -202,9 +202,13 @@ struct AtomIter {
 // One accumulator chunk of one epilogue warp: prefetch what the chunk needs from global memory, wait for the
 // MMAs, then TMEM -> registers -> reduction / fold / witness -> global.  `sub` = this warp's index among the kSub
 // warps of its TMEM lane quadrant; it owns the 16-coefficient units sub, sub + kSub, ...
-template <int MODE, int kSub, class WaitFn>
+struct NoMark {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+
+template <int MODE, int kSub, class WaitFn, class MarkFn = NoMark>
 __device__ __forceinline__ void epilogue_chunk(const UmmaArgs &a, int hi, int c, int sub, bool row_ok, size_t rbase,
-                                               uint32_t t_addr, WaitFn wait_acc) {
+                                               uint32_t t_addr, WaitFn wait_acc, MarkFn mark = MarkFn()) {
   constexpr int kUnitsPerWarp = 16 / kSub;
   const int units = a.NCo >> 4;
   const uint32_t Q2 = a.qmask | (a.qmask << 16);             // the modulus mask in both 16-bit lanes
@@ -250,6 +254,7 @@ __device__ __forceinline__ void epilogue_chunk(const UmmaArgs &a, int hi, int c,
     } else {
       tmem_ld_wait();
     }
+    mark(3 + 3 * ui);   // accumulators of this unit are in registers
     const int kk = c * a.NCo + u * 16;
     if (!row_ok || kk >= a.P) continue;
     if (MODE == ENC || MODE == DEC1) {
@@ -273,6 +278,7 @@ __device__ __forceinline__ void epilogue_chunk(const UmmaArgs &a, int hi, int c,
       }
       const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       const uint4 p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      mark(4 + 3 * ui);   // math done
       uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
       if (d0) {
         reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
@@ -673,6 +679,16 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
 }
 
 }  // namespace
+
+#ifdef NTRU_TRACE
+extern "C" int ntru_debug_trace_dump(unsigned long long *out, unsigned int cap) {
+  cudaDeviceSynchronize();
+  const unsigned int n = kTraceLanes * kTraceCap;
+  if (cap < n) return -1;
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * n);
+  return (int)n;
+}
+#endif
 
 int umma_init(ntru_ctx *ctx) {
   ctx->tensor_ok = false;

@@ -17,10 +17,38 @@
 //   tmem_full[b]           : in both CTAs (commit multicast);  tmem_empty[b]: leader only, all epilogue warps
 // Only the leader's warp 1 issues MMAs; producer, transform and epilogue warps run in both CTAs.
 
+#ifdef NTRU_TRACE
+// debug timeline of cluster 0 / CTA 0: each traced thread appends (tag << 40 | clock) words to its own
+// shared-memory lane buffer (cheap: one STS), dumped to global memory at kernel end.
+constexpr int kTraceLanes = 3, kTraceCap = 1024;
+__device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
+#define TRACE(role, ev, idx)                                                                      \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && trace_n[role - 1] < kTraceCap) {                                       \
+      trace_buf[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                   \
+          ((unsigned long long)(((ev) << 12) | ((idx) & 0xfff)) << 40) | (clock64() & 0xffffffffffull); \
+    }                                                                                             \
+  } while (0)
+#else
+#define TRACE(role, ev, idx) do {} while (0)
+#endif
+
 constexpr int kSlotBytes = 16384;
+#ifdef NTRU_TRACE
+constexpr int kPairSlots = 12;   // 32 KB of shared memory go to the trace buffers
+#else
 constexpr int kPairSlots = 14;
+#endif
 constexpr int kPairBars = 4 * kPairSlots + 4;
+// Warp roles: the warp scheduler favours the highest warp id of an SM sub-partition, so the two single-thread
+// roles that sit on the critical path get the highest ids: 16 = TMA producer, 17 = MMA issuer.  Warps 0-15 are
+// epilogue warps (DEC1: 0-7 transform, 8-15 epilogue); an epilogue warp reads TMEM lanes 32*(warp%4)...
+constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17, kPairEpiWarp0Dec1 = 8;
+#ifdef NTRU_TRACE
+constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 1024 + 8 * 3 * 1024;
+#else
 constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 8 * kPairBars + 64;
+#endif
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -66,6 +94,17 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"((uint16_t)3)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      ".reg .b32 r;\n\t"
+      "elect.sync r|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
 }
 __host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signed, int n) {
   return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
@@ -136,6 +175,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   auto a_slot = [&](uint32_t i) { return smem_base + i * kSlotBytes; };
   auto b_slot = [&](uint32_t j) { return smem_base + (a.nA + j) * kSlotBytes; };
 
+#ifdef NTRU_TRACE
+  unsigned long long *trace_buf = reinterpret_cast<unsigned long long *>(smem + (size_t)kPairSlots * kSlotBytes + 1024);
+  int trace_n[kTraceLanes] = {0, 0, 0};
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -156,7 +199,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kPairMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
@@ -167,57 +210,117 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   // barrier addresses in the LEADER CTA, usable from either CTA
   auto lead = [&](uint32_t local_bar) { return mapa_u32(local_bar, 0); };
 
-  if (warp == 0) {
+  if (warp == kPairProducerWarp) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // Same lean structure as the MMA issuer below: uniform control flow for the whole warp, incremental ring
+    // counters, one elected lane issues.  (The generic slice iterator cost ~900 cycles per slice here, more than
+    // the 512 cycles of MMA work a slice holds, so the ring never filled and every TMA latency was exposed.)
+    {
       const int half_rows = a.NC >> 1;
       const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK, a_bytes = 2u * kABytes;
-      pair_walk(a, [&](const Slice &s) {
-        if (MODE != DEC1 && s.a_load) {
-          mbar_wait(a_empty(s.sa), s.a_par ^ 1);
-          const uint32_t bar = lead(a_full(s.sa));
-          if (leader) mbar_arrive_expect_tx(a_full(s.sa), a_bytes);
-          else mbar_arrive_cluster(bar);
-          tma_load_2d_pair(a_slot(s.sa), &tmapA, s.at * kAtomK, s.T * 256 + (int)rank * kTileRows, bar);
+      const uint32_t lead_a_full = lead(a_full(0)), lead_b_full = lead(b_full(0));
+      const int parts = a.with_hi ? 2 : 1;
+      const bool resident = a.a_resident != 0;
+      uint32_t sb = 0, b_par = 0, sas = 0, a_par_s = 0, t_par = 0;
+      for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
+        const int a_row = T * 256 + (int)rank * kTileRows;
+        for (int part = 0; part < parts; ++part) {
+          const int hi = a.with_hi && part == 0;
+          for (int c = 0; c < a.nchunks; ++c) {
+            const int a0 = first_atom(a, hi, c);
+            const bool a_load = MODE != DEC1 && (!resident || (part == 0 && c == 0));
+            const int row0 = (hi * a.nchunks + c) * a.NC + (int)rank * half_rows;
+            for (int at = a0; at < a.atoms; ++at) {
+              for (int lk = 0; lk < a.kl; ++lk) {
+                if (a_load) {
+                  const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
+                  mbar_wait(a_empty(sa), (resident ? t_par : a_par_s) ^ 1);
+                  if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(a_full(sa), a_bytes);
+                    else mbar_arrive_cluster(lead_a_full + 8u * sa);
+                    tma_load_2d_pair(a_slot(sa), &tmapA, at * kAtomK, a_row, lead_a_full + 8u * sa);
+                  }
+                  __syncwarp();
+                }
+                mbar_wait(b_empty(sb), b_par ^ 1);
+                if (elect_one()) {
+                  if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
+                  else mbar_arrive_cluster(lead_b_full + 8u * sb);
+                  tma_load_2d_pair(b_slot(sb), &tmapB, lk * a.Kp + at * kAtomK, row0, lead_b_full + 8u * sb);
+                  TRACE(3, 2, (hi ? 0 : a.nchunks) + c);
+                }
+                __syncwarp();
+                if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
+                if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
+              }
+            }
+          }
         }
-        mbar_wait(b_empty(s.sb), s.b_par ^ 1);
-        const uint32_t bar = lead(b_full(s.sb));
-        if (leader) mbar_arrive_expect_tx(b_full(s.sb), b_bytes);
-        else mbar_arrive_cluster(bar);
-        const int row0 = (s.hi * a.nchunks + s.c) * a.NC + (int)rank * half_rows;
-        tma_load_2d_pair(b_slot(s.sb), &tmapB, s.lk * a.Kp + s.at * kAtomK, row0, bar);
-      });
+      }
     }
-  } else if (warp == 1) {
+  } else if (warp == kPairMmaWarp) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.  The loop
+    // is written with incremental counters: every instruction here sits on the critical path of the tensor
+    // pipe (512 cycles of MMA work per slice), and the first version -- one divergent lane walking the generic
+    // slice iterator, ~150 SASS instructions per slice -- was issue-bound at ~1400 cycles per slice (ncu).
+    if (leader) {
       const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.NC);
-      uint32_t first = 1;
-      pair_walk(a, [&](const Slice &s) {
-        const uint32_t buf = s.cc & 1;
-        if (s.chunk_first) {
-          mbar_wait(tempty_bar(buf), ((s.cc >> 1) & 1) ^ 1);
-          first = 1;
+      const uint64_t desc_hi = make_smem_desc(0) & ~0x3FFFull;             // everything but the start address
+      const uint32_t a_addr16 = (smem_base >> 4), b_addr16 = (smem_base + a.nA * kSlotBytes) >> 4;
+      const int parts = a.with_hi ? 2 : 1;
+      const bool resident = a.a_resident != 0;
+      uint32_t sb = 0, b_par = 0;           // B ring position / phase parity
+      uint32_t sas = 0, a_par_s = 0;        // streaming A ring position / phase parity
+      uint32_t cc = 0, t_par = 0;           // chunk counter, resident-A phase parity (per tile)
+      for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
+        for (int part = 0; part < parts; ++part) {
+          const int hi = a.with_hi && part == 0;
+          for (int c = 0; c < a.nchunks; ++c, ++cc) {
+            const int a0 = first_atom(a, hi, c);
+            const bool first_chunk = part == 0 && c == 0, last_chunk = part == parts - 1 && c == a.nchunks - 1;
+            const bool a_wait = !resident || first_chunk, a_release = !resident || last_chunk;
+            const uint32_t buf = cc & 1;
+            if (lane == 0) TRACE(1, 0, cc);
+            mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
+            if (lane == 0) TRACE(1, 1, cc);
+            const uint32_t d_tmem = tmem_base + buf * kAccCols;
+            uint32_t accumulate = 0;
+            for (int at = a0; at < a.atoms; ++at) {
+              for (int lk = 0; lk < a.kl; ++lk) {
+                const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
+                if (lane == 0) TRACE(1, 4, cc);
+                mbar_wait(b_full(sb), b_par);
+                if (lane == 0) TRACE(1, 2, cc);
+                if (a_wait) mbar_wait(a_full(sa), resident ? t_par : a_par_s);
+                if (lane == 0) TRACE(1, 3, cc);
+                tc_fence_after();
+                const uint64_t da = desc_hi | (uint64_t)((a_addr16 + sa * (kSlotBytes >> 4)) & 0x3FFF);
+                const uint64_t db = desc_hi | (uint64_t)((b_addr16 + sb * (kSlotBytes >> 4)) & 0x3FFF);
+                const bool last = at == a.atoms - 1 && lk == a.kl - 1;
+                if (elect_one()) {
+                  umma_i8_pair(d_tmem, da, db, idesc, accumulate);
+                  umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+                  umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+                  umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+                  umma_commit_pair(b_empty(sb));
+                  if (a_release) umma_commit_pair(a_empty(sa));
+                  if (last) umma_commit_pair(tfull_bar(buf));
+                }
+                __syncwarp();
+                if (lane == 0) TRACE(1, 5, cc);
+                accumulate = 1;
+                if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
+                if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
+              }
+            }
+          }
         }
-        mbar_wait(b_full(s.sb), s.b_par);
-        if (s.a_load) mbar_wait(a_full(s.sa), s.a_par);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kAccCols;
-        const uint64_t da = make_smem_desc(a_slot(s.sa));
-        const uint64_t db = make_smem_desc(b_slot(s.sb));
-#pragma unroll
-        for (int k = 0; k < kAtomK / 32; ++k) {
-          umma_i8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
-          first = 0;
-        }
-        umma_commit_pair(b_empty(s.sb));
-        if (s.a_release) umma_commit_pair(a_empty(s.sa));
-        if (s.chunk_last) umma_commit_pair(tfull_bar(buf));
-      });
+      }
     }
-  } else if (MODE == DEC1 && warp < kEpilogueWarp0) {
+  } else if (MODE == DEC1 && warp < kPairEpiWarp0Dec1) {
     // ===================== DEC1 transform (both CTAs): e (uint16, global) -> byte-limb A slots =====
-    const int t = threadIdx.x - kBuilderWarp0 * 32;      // 0..255
+    const int t = threadIdx.x;                           // 0..255 (warps 0-7)
     const int chunk = t & 7;                             // 16-byte chunk of the 128-byte A row
     const int r0 = t >> 3;                               // rows r0, r0+32, r0+64, r0+96
     const uint16_t *src = reinterpret_cast<const uint16_t *>(a.a_src);
@@ -311,7 +414,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   } else {
     // ===================== epilogue (both CTAs): TMEM -> registers -> global =====================
     constexpr int kSub = MODE == DEC1 ? 2 : 4;
-    const int ew = warp - (MODE == DEC1 ? kEpilogueWarp0 : kBuilderWarp0);
+    const int ew = warp - (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0);
     const int quad = warp & 3;
     const int sub = ew >> 2;
     const int parts = a.with_hi ? 2 : 1;
@@ -325,19 +428,31 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         for (int c = 0; c < a.nchunks; ++c, ++cc) {
           const uint32_t buf = cc & 1;
           const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
+          if (lane == 0 && ew == 0) TRACE(2, 0, cc);
           epilogue_chunk<MODE, kSub>(a, hi, c, sub, row_ok, rbase, t_addr,
-                                     [&] { mbar_wait(tfull_bar(buf), (cc >> 1) & 1); });
+                                     [&] { mbar_wait(tfull_bar(buf), (cc >> 1) & 1); if (lane == 0 && ew == 0) TRACE(2, 1, cc); },
+                                     [&](int ev) { if (lane == 0 && ew == 0) TRACE(2, ev, cc); });
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(lead(tempty_bar(buf)));
+          if (lane == 0 && ew == 0) TRACE(2, 2, cc);
         }
       }
     }
   }
 
+#ifdef NTRU_TRACE
+  if (blockIdx.x == 0 && lane == 0) {
+    const int role = warp == kPairProducerWarp ? 3 : (warp == kPairMmaWarp ? 1 : (warp == (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0) ? 2 : 0));
+    if (role) {
+      for (int i = 0; i < kTraceCap; ++i)
+        g_trace[(role - 1) * kTraceCap + i] = i < trace_n[role - 1] ? trace_buf[(role - 1) * kTraceCap + i] : 0ull;
+    }
+  }
+#endif
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 1) {
+  if (warp == kPairMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
