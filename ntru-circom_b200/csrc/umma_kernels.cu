@@ -68,6 +68,8 @@ struct UmmaArgs {
   int npairs;             // 256-row pair tiles
   int nA, nB;             // shared-memory slots for A and stages for B
   int a_resident;         // A slots hold the whole tile (loaded once per tile)
+  int nM, nS;             // message slots (ENC), store-staging slots
+  int out_mask;           // which outputs exist: bit0 = cyc #1, bit1 = cyc #2, bit2 = hi
   const void *a_src;      // DEC1: e rows (uint16), pitch P elements
   const uint8_t *m;       // ENC: message rows
   uint16_t *o16_cyc;      // ENC: value, DEC1: remainder1
@@ -584,36 +586,48 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-void geometry(const ntru_ctx *ctx, int kl, int nl, KeyMatrix &km) {
+void geometry(const ntru_ctx *ctx, int mode, int kl, int nl, KeyMatrix &km) {
   const int N = ctx->N;
   km.limbs = kl;
   km.nlimbs = nl;
-  const int max_out = 256 / nl;                       // output coefficients one 256-column accumulator holds
+  // output coefficients per chunk: a 256-column accumulator holds 256 / nl; ENC is capped at 128 so that a
+  // chunk's message bytes are exactly one 128-byte TMA atom per row
+  const int max_out = mode == ENC ? 128 : 256 / nl;
   km.nchunks = (N + max_out - 1) / max_out;
   const int per = (N + km.nchunks - 1) / km.nchunks;
-  km.out_cols = ((per + 15) / 16) * 16;
+  // the CTA-pair kernel's epilogue stages whole passes of 32 (ENC, DEC1) or 64 (DEC2) coefficients per warp:
+  // every warp of a TMEM lane quadrant must own a whole number of passes of each chunk
+  const int round = mode == ENC ? 128 : (mode == DEC1 ? 64 : 256);
+  km.out_cols = ((per + round - 1) / round) * round;
+  if (km.out_cols > max_out) km.out_cols = max_out;
   km.chunk_cols = km.out_cols * nl;
   const int Kp = ((N + kAtomK - 1) / kAtomK) * kAtomK;
   km.klen = kl * Kp;
 }
 
-int encode_2d(ntru_ctx *ctx, void *out, void *base, uint64_t inner, uint64_t rows, uint64_t stride_bytes, uint32_t box_inner,
-              uint32_t box_rows) {
+int encode_2d_ex(ntru_ctx *ctx, void *out, void *base, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (((uintptr_t)base & 15) != 0) return fail(ctx, NTRU_E_PARAM, "device arrays must be 16-byte aligned");
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)stride_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                   2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(ctx, NTRU_E_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return NTRU_OK;
 }
 
+int encode_2d(ntru_ctx *ctx, void *out, void *base, uint64_t inner, uint64_t rows, uint64_t stride_bytes, uint32_t box_inner,
+              uint32_t box_rows) {
+  return encode_2d_ex(ctx, out, base, 1, inner, rows, stride_bytes, box_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyMatrix &km) {
-  geometry(ctx, kl, nl, km);
+  geometry(ctx, mode, kl, nl, km);
   const int rows = 2 * km.nchunks * km.chunk_cols;
   const int Kp = km.klen / kl;
   const size_t bytes = (size_t)rows * km.klen;
@@ -647,28 +661,59 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   a.NC = km.chunk_cols; a.NCo = km.out_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
   a.ntiles = (int)((a.B + kTileRows - 1) / kTileRows);
   a.npairs = (int)((a.B + 2 * kTileRows - 1) / (2 * kTileRows));
+  a.nS = 2;
+  a.nM = MODE == ENC ? 2 : 0;
+  const int avail = kPairSlots - a.nS - a.nM;
   const int a_slots = a.atoms * a.kl;
-  if (a_slots + 4 <= kPairSlots) {
-    a.a_resident = 1; a.nA = a_slots; a.nB = kPairSlots - a_slots;
+  if (a_slots + 4 <= avail) {
+    a.a_resident = 1; a.nA = a_slots; a.nB = avail - a_slots;
   } else {
-    a.a_resident = 0; a.nA = 6; a.nB = kPairSlots - 6;
+    a.a_resident = 0; a.nA = 6; a.nB = avail - 6;
   }
-  CUtensorMap tmB, tmA;
+  CUtensorMap tmB, tmA, tmM, tmO[3];
   const bool pair = ctx->tensor_variant == 0;
   memcpy(&tmB, pair ? km.tmap_half : km.tmap, sizeof tmB);
   memset(&tmA, 0, sizeof tmA);
+  memset(&tmM, 0, sizeof tmM);
+  memset(tmO, 0, sizeof tmO);
+  const uint64_t N = (uint64_t)ctx->N, P = (uint64_t)ctx->P;
+  int rc;
   if (MODE != DEC1) {
     // byte rows straight into the UMMA layout: inner extent N (columns beyond read as zero), row pitch P
-    if (((uintptr_t)a_bytes & 15) != 0) return fail(ctx, NTRU_E_PARAM, "device rows must be 16-byte aligned");
-    int rc = encode_2d(ctx, &tmA, const_cast<void *>(a_bytes), (uint64_t)ctx->N, (uint64_t)a.B, (uint64_t)ctx->P, kAtomK,
-                       kTileRows);
+    rc = encode_2d(ctx, &tmA, const_cast<void *>(a_bytes), N, (uint64_t)a.B, P, kAtomK, kTileRows);
     if (rc) return rc;
+  }
+  if (pair) {
+    if (MODE == ENC) {
+      rc = encode_2d(ctx, &tmM, const_cast<uint8_t *>(a.m), N, (uint64_t)a.B, P, kAtomK, kTileRows);
+      if (rc) return rc;
+    }
+    // outputs: per-warp tiles of 32 rows x 64 bytes (SWIZZLE_64B); DEC1's b is 32 rows x 32 bytes, unswizzled
+    void *optr[3];
+    int oelem[3], obox[3];
+    CUtensorMapSwizzle oswz[3];
+    if (MODE == ENC || MODE == DEC1) {
+      optr[0] = a.o16_cyc; oelem[0] = 2; obox[0] = 32; oswz[0] = CU_TENSOR_MAP_SWIZZLE_64B;
+      optr[2] = a.o16_hi; oelem[2] = 2; obox[2] = 32; oswz[2] = CU_TENSOR_MAP_SWIZZLE_64B;
+      if (MODE == ENC) { optr[1] = a.o16_cyc2; oelem[1] = 2; obox[1] = 32; oswz[1] = CU_TENSOR_MAP_SWIZZLE_64B; }
+      else { optr[1] = a.o8_cyc; oelem[1] = 1; obox[1] = 32; oswz[1] = CU_TENSOR_MAP_SWIZZLE_NONE; }
+    } else {
+      optr[0] = a.o8_cyc; optr[1] = a.o8_cyc2; optr[2] = a.o8_hi;
+      for (int i = 0; i < 3; ++i) { oelem[i] = 1; obox[i] = 64; oswz[i] = CU_TENSOR_MAP_SWIZZLE_64B; }
+    }
+    a.out_mask = 0;
+    for (int i = 0; i < 3; ++i) {
+      if (!optr[i]) continue;
+      a.out_mask |= 1 << i;
+      rc = encode_2d_ex(ctx, &tmO[i], optr[i], oelem[i], P, (uint64_t)a.B, P * oelem[i], (uint32_t)obox[i], 32, oswz[i]);
+      if (rc) return rc;
+    }
   }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
     if (pair) {
       const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
-      k_umma_pair<MODE><<<2 * clusters, kThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA);
+      k_umma_pair<MODE><<<2 * clusters, kThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
     } else {
       const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
       k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);

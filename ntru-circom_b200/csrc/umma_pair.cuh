@@ -39,7 +39,7 @@ constexpr int kPairSlots = 12;   // 32 KB of shared memory go to the trace buffe
 #else
 constexpr int kPairSlots = 14;
 #endif
-constexpr int kPairBars = 4 * kPairSlots + 4;
+constexpr int kPairBars = 4 * kPairSlots + 8;   // a_full/a_empty/b_full/b_empty[kPairSlots], tmem full/empty[2], m full/empty[2]
 // Warp roles: the warp scheduler favours the highest warp id of an SM sub-partition, so the two single-thread
 // roles that sit on the critical path get the highest ids: 16 = TMA producer, 17 = MMA issuer.  Warps 0-15 are
 // epilogue warps (DEC1: 0-7 transform, 8-15 epilogue); an epilogue warp reads TMEM lanes 32*(warp%4)...
@@ -94,6 +94,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"((uint16_t)3)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -159,7 +164,9 @@ __device__ __forceinline__ void pair_walk(const UmmaArgs &a, F &&f) {
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA) {
+k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA,
+            const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapO0,
+            const __grid_constant__ CUtensorMap tmapO1, const __grid_constant__ CUtensorMap tmapO2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kPairSlots * kSlotBytes);
@@ -171,9 +178,14 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   auto b_empty = [&](uint32_t i) { return bar0 + 8u * (3 * kPairSlots + i); };
   auto tfull_bar = [&](uint32_t b) { return bar0 + 8u * (4 * kPairSlots + b); };
   auto tempty_bar = [&](uint32_t b) { return bar0 + 8u * (4 * kPairSlots + 2 + b); };
+  auto m_full = [&](uint32_t b) { return bar0 + 8u * (4 * kPairSlots + 4 + b); };
+  auto m_empty = [&](uint32_t b) { return bar0 + 8u * (4 * kPairSlots + 6 + b); };
   const uint32_t smem_base = smem_u32(smem);
+  // slot order: [A slots nA][B stages nB][message slots nM][store staging nS]
   auto a_slot = [&](uint32_t i) { return smem_base + i * kSlotBytes; };
   auto b_slot = [&](uint32_t j) { return smem_base + (a.nA + j) * kSlotBytes; };
+  auto m_slot = [&](uint32_t j) { return smem_base + (a.nA + a.nB + j) * kSlotBytes; };
+  const uint32_t stage_base = smem_base + (a.nA + a.nB + a.nM) * kSlotBytes;
 
 #ifdef NTRU_TRACE
   unsigned long long *trace_buf = reinterpret_cast<unsigned long long *>(smem + (size_t)kPairSlots * kSlotBytes + 1024);
@@ -196,6 +208,8 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 2 * kEpiWarps);       // every epilogue warp of both CTAs
+      mbar_init(m_full(b), 1);                       // this CTA's producer (+ transaction bytes)
+      mbar_init(m_empty(b), kEpiWarps);              // this CTA's epilogue warps
     }
     fence_barrier_init();
   }
@@ -221,7 +235,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       const uint32_t lead_a_full = lead(a_full(0)), lead_b_full = lead(b_full(0));
       const int parts = a.with_hi ? 2 : 1;
       const bool resident = a.a_resident != 0;
-      uint32_t sb = 0, b_par = 0, sas = 0, a_par_s = 0, t_par = 0;
+      uint32_t sb = 0, b_par = 0, sas = 0, a_par_s = 0, t_par = 0, mc = 0;
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         const int a_row = T * 256 + (int)rank * kTileRows;
         for (int part = 0; part < parts; ++part) {
@@ -230,6 +244,16 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             const int a0 = first_atom(a, hi, c);
             const bool a_load = MODE != DEC1 && (!resident || (part == 0 && c == 0));
             const int row0 = (hi * a.nchunks + c) * a.NC + (int)rank * half_rows;
+            if (MODE == ENC && !hi) {   // the chunk's 128 message bytes per row, for this CTA's epilogue
+              const uint32_t ms = mc & 1;
+              mbar_wait(m_empty(ms), ((mc >> 1) & 1) ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(m_full(ms), kABytes);
+                tma_load_2d(m_slot(ms), &tmapM, c * a.NCo, a_row, m_full(ms));
+              }
+              __syncwarp();
+              ++mc;
+            }
             for (int at = a0; at < a.atoms; ++at) {
               for (int lk = 0; lk < a.kl; ++lk) {
                 if (a_load) {
@@ -412,33 +436,161 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       for (int j = 0; j < 8; ++j) raw[j] = raw_next[j];
     }
   } else {
-    // ===================== epilogue (both CTAs): TMEM -> registers -> global =====================
+    // ===================== epilogue (both CTAs): TMEM -> registers -> shared staging -> TMA store ==========
+    // Each warp owns 32 rows (its TMEM lane quadrant) and a contiguous run of 16-coefficient units per chunk.
+    // Results are staged in a small per-warp shared-memory tile and written with cp.async.bulk.tensor stores:
+    // the first version stored straight from registers (each lane its own row), 32 cache lines per warp
+    // instruction, and the epilogue warps spent their time in LSU back-pressure (ncu: lg_throttle; trace:
+    // ~3000 cycles per chunk against ~2000 cycles of MMA work).  ENC reads the message bytes from a TMA-loaded
+    // shared tile for the same reason.
     constexpr int kSub = MODE == DEC1 ? 2 : 4;
+    constexpr int kPassUnits = MODE == DEC2 ? 4 : 2;               // units staged per TMA store (64-byte rows)
     const int ew = warp - (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0);
     const int quad = warp & 3;
     const int sub = ew >> 2;
     const int parts = a.with_hi ? 2 : 1;
-    uint32_t cc = 0;
+    const int upw = (a.NCo >> 4) / kSub;                           // units per warp per chunk
+    const uint32_t Q2 = a.qmask | (a.qmask << 16);
+    const uint32_t lift_add = ((uint32_t)a.q >> 1) - 1;
+    const int logq = 31 - __clz(a.q);
+    const uint32_t stage = stage_base + (uint32_t)ew * (MODE == DEC1 ? 4096u : 2048u);   // this warp's staging tile
+    uint8_t *stage_ptr = smem + (stage - smem_base);
+    // swizzled position of 16-byte chunk `ch` of this lane's 64-byte staging row (SWIZZLE_64B)
+    auto st64 = [&](int ch) { return (uint32_t)(lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4)); };
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t cc = 0, mc = 0;
+    bool store_pending = false;
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
-      const size_t row = (size_t)T * 256 + rank * kTileRows + quad * 32 + lane;
-      const bool row_ok = row < a.B;
-      const size_t rbase = row * (size_t)a.P;
+      const int out_row = T * 256 + (int)rank * kTileRows + quad * 32;
       for (int part = 0; part < parts; ++part) {
         const int hi = a.with_hi && part == 0;
         for (int c = 0; c < a.nchunks; ++c, ++cc) {
           const uint32_t buf = cc & 1;
           const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
           if (lane == 0 && ew == 0) TRACE(2, 0, cc);
-          epilogue_chunk<MODE, kSub>(a, hi, c, sub, row_ok, rbase, t_addr,
-                                     [&] { mbar_wait(tfull_bar(buf), (cc >> 1) & 1); if (lane == 0 && ew == 0) TRACE(2, 1, cc); },
-                                     [&](int ev) { if (lane == 0 && ew == 0) TRACE(2, ev, cc); });
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead(tempty_bar(buf)));
+          mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0 && ew == 0) TRACE(2, 1, cc);
+          const uint32_t ms = mc & 1;
+          if (MODE == ENC && !hi) mbar_wait(m_full(ms), (mc >> 1) & 1);
+          for (int u0 = sub * upw; u0 < (sub + 1) * upw; u0 += kPassUnits) {
+            uint32_t res[kPassUnits * (MODE == DEC2 ? 4 : 8)];      // packed results of this pass
+            uint32_t bres[kPassUnits * 4];                          // DEC1: lifted polynomial b (bytes)
+#pragma unroll
+            for (int j = 0; j < kPassUnits; ++j) {
+              const int u = u0 + j;
+              uint32_t w[32];
+              tmem_ld16(t_addr + u * 16, w);
+              if (MODE == ENC && a.nl == 2) {
+                uint32_t w1[32];
+                tmem_ld16(t_addr + a.NCo + u * 16, w1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] += w1[i] << 8;
+              } else {
+                tmem_ld_wait();
+              }
+              if (MODE == ENC || MODE == DEC1) {
+                uint32_t *pk = res + 8 * j;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) pk[jj] = __byte_perm(w[2 * jj], w[2 * jj + 1], 0x5410);
+                if (hi) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) pk[jj] = ((~pk[jj] & Q2) + 0x00010001u) & Q2;
+                } else if (MODE == ENC) {
+                  const int off = (row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128 + ((u ^ (row_in_tile & 7)) << 4);
+                  const uint4 mm = *reinterpret_cast<const uint4 *>(smem + (m_slot(ms) - smem_base) + off);
+                  const uint32_t mw[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const uint32_t mp = __byte_perm(mw[jj >> 1], 0u, (jj & 1) ? 0x4342 : 0x4140);
+                    pk[jj] = ((pk[jj] & Q2) + mp) & Q2;
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) pk[jj] &= Q2;
+                  if (a.o8_cyc) {
+#pragma unroll
+                    for (int wd = 0; wd < 4; ++wd) {
+                      uint32_t bb[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                        const uint32_t x = w[4 * wd + i] & a.qmask;
+                        const uint32_t y = x + ((x + lift_add) >> logq);          // index.js:117
+                        bb[i] = y - 3u * __umulhi(y, 0x55555556u);
+                      }
+                      bres[4 * j + wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
+                    }
+                  }
+                }
+              } else {   // DEC2: mod 3 (hi: -x mod 3 = 2x mod 3)
+#pragma unroll
+                for (int wd = 0; wd < 4; ++wd) {
+                  uint32_t bb[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const uint32_t y = hi ? 2u * w[4 * wd + i] : w[4 * wd + i];
+                    bb[i] = y - 3u * __umulhi(y, 0x55555556u);
+                  }
+                  res[4 * j + wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
+                }
+              }
+            }
+            const bool last_pass = u0 + kPassUnits >= (sub + 1) * upw;
+            if (last_pass) {   // all TMEM reads (and message reads) of this chunk are done: release them early
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive_cluster(lead(tempty_bar(buf)));
+                if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));
+              }
+            }
+            // the previous store must have finished reading the staging tile before it is overwritten
+            if (store_pending) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+            if (MODE == DEC2) {
+#pragma unroll
+              for (int j = 0; j < kPassUnits; ++j)
+                *reinterpret_cast<uint4 *>(stage_ptr + st64(j)) = make_uint4(res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kPassUnits; ++j) {
+                *reinterpret_cast<uint4 *>(stage_ptr + st64(2 * j)) = make_uint4(res[8 * j], res[8 * j + 1], res[8 * j + 2], res[8 * j + 3]);
+                *reinterpret_cast<uint4 *>(stage_ptr + st64(2 * j + 1)) = make_uint4(res[8 * j + 4], res[8 * j + 5], res[8 * j + 6], res[8 * j + 7]);
+              }
+              if (MODE == DEC1 && !hi && a.o8_cyc) {   // b: 32-byte rows, no swizzle needed
+#pragma unroll
+                for (int j = 0; j < kPassUnits; ++j)
+                  *reinterpret_cast<uint4 *>(stage_ptr + 2048 + lane * 32 + j * 16) =
+                      make_uint4(bres[4 * j], bres[4 * j + 1], bres[4 * j + 2], bres[4 * j + 3]);
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int col = c * a.NCo + u0 * 16;
+              if (hi) {
+                if (a.out_mask & 4) tma_store_2d(&tmapO2, stage, col, out_row);
+              } else {
+                if (a.out_mask & 1) tma_store_2d(&tmapO0, stage, col, out_row);
+                if (MODE == DEC1) {
+                  if (a.out_mask & 2) tma_store_2d(&tmapO1, stage + 2048, col, out_row);
+                } else {
+                  if (a.out_mask & 2) tma_store_2d(&tmapO1, stage, col, out_row);
+                }
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            store_pending = true;
+          }
+          if (MODE == ENC && !hi) ++mc;
           if (lane == 0 && ew == 0) TRACE(2, 2, cc);
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
 
 #ifdef NTRU_TRACE
