@@ -281,6 +281,10 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (CUDA events on the launch stream, inside the timed region) ----
     hbm_gbs, bf16_tf, peak_src = peaks()
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
+    except OSError:
+        prof = {"bytes_per_ciphertext": {}, "int8_peak_tops": None}
     alg_bytes = {"enc_tensor": 6 * N, "dec1_tensor": 6 * N, "dec2_tensor": 2 * N, "enc_core": 6 * N, "dec_core": 8 * N}
     limbs = 2 if q > 256 else 1
     alg_ops = {"enc_tensor": 2 * N * N * limbs, "dec1_tensor": 2 * N * N * limbs, "dec2_tensor": 2 * N * N,
@@ -295,10 +299,15 @@ def run_ours(args, rank, world, local_rank):
                          "TOP/s": alg_ops[name] * B / (avg * 1e-3) / 1e12}
     dom = max(kernels, key=lambda k: kernels[k]["avg_ms"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GB/s"], "peak": hbm_gbs, "unit": "GB/s",
-                "frac": kernels[dom]["GB/s"] / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["GB/s"] / hbm_gbs,
+                "traffic": (prof["bytes_per_ciphertext"].get(dom) or 0) * B or None,
+                "traffic_source": "ncu dram__bytes_read+write per ciphertext (profiles/r1_dram_traffic.json) x rows per launch",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_ciphertext": alg_bytes[dom],
-                "int8_tensor": {"achieved_TOPs": kernels[dom]["TOP/s"], "peak_TOPs": 2 * bf16_tf,
-                                "frac": kernels[dom]["TOP/s"] / (2 * bf16_tf), "peak_source": "2 x measured bf16"},
+                "int8_tensor": {"achieved_TOPs": kernels[dom]["TOP/s"], "peak_TOPs": prof.get("int8_peak_tops") or 2 * bf16_tf,
+                                "frac": kernels[dom]["TOP/s"] / (prof.get("int8_peak_tops") or 2 * bf16_tf),
+                                "peak_source": "measured MMA-loop-only probe (scripts/mma_peak.cu)" if prof.get("int8_peak_tops") else "2 x measured bf16",
+                                "frac_of_2x_measured_bf16": kernels[dom]["TOP/s"] / (2 * bf16_tf)},
                 "whole_step": {"GB/s": 14 * N * B * args.steps / (ms * 1e-3) / 1e9,
                                "frac": 14 * N * B * args.steps / (ms * 1e-3) / 1e9 / hbm_gbs},
                 "kernels": kernels}

@@ -1,0 +1,69 @@
+// Drop-in for the hot path of numtel/ntru-circom's index.js over the N-API shim (ntru_napi.c).
+// NOT RUN IN THIS REPOSITORY'S IMAGE (no node).  Usage in the reference repository:
+//     import NTRUReference, * as ref from './index.js';          // the reference, unchanged
+//     import { accelerate } from 'ntru-b200/bindings/node/index.mjs';
+//     const NTRU = accelerate(NTRUReference, ref);                // same class, GPU encryptBits/decryptBits
+// Key generation, inversion and every helper stay the reference's own JavaScript (north_star).
+import { createRequire } from 'node:module';
+const native = createRequire(import.meta.url)('./ntru_b200.node');
+
+export function accelerate(NTRUReference, ref) {
+  const { trimPolynomial, expandArray, generateCustomArray } = ref;
+  return class NTRU extends NTRUReference {
+    #ctx = null; #pub = null; #priv = null;
+    #engine() {
+      if (!this.#ctx) this.#ctx = native.create(this.N, this.p, this.q, this.device ?? 0);
+      return this.#ctx;
+    }
+    #loadPublic() {
+      const ctx = this.#engine();
+      if (this.#pub !== this.h) {                      // TypeError on h === null, like index.js:90
+        native.setPublicKey(ctx, Uint16Array.from(expandArray(this.h, this.N, 0)));
+        this.#pub = this.h;
+      }
+      return ctx;
+    }
+    #loadPrivate() {
+      const ctx = this.#engine();
+      if (this.#priv !== this.f) {
+        native.setPrivateKey(ctx, Int8Array.from(expandArray(this.f, this.N, 0)), Uint8Array.from(expandArray(this.fp, this.N, 0)));
+        this.#priv = this.f;
+      }
+      return ctx;
+    }
+    // index.js:87-110; `r` is the injection seam the reference lacks
+    encryptBits(m, r = generateCustomArray(this.N, this.dr, this.dr).map(x => x === -1 ? this.p - 1 : x)) {
+      const ctx = this.#loadPublic();
+      const mExp = expandArray(m, this.N, 0);          // RangeError when m.length > N (index.js:98)
+      const q = this.q;
+      const out = native.encryptBatch(ctx, 1, this.N, Uint8Array.from(r), Uint8Array.from(mExp, x => ((x % q) + q) % q));
+      const remainderE = Array.from(out.remainderE);
+      return {
+        value: trimPolynomial(remainderE),
+        inputs: { r, m: mExp, h: expandArray(this.h, this.N, 0), quotientE: Array.from(out.quotientE), remainderE },
+        params: [this.q, this.calculateNq(), this.N],
+      };
+    }
+    // index.js:111-140
+    decryptBits(e) {
+      const ctx = this.#loadPrivate();
+      const eExp = expandArray(e, this.N, 0);          // RangeError when e.length > N (index.js:126)
+      const q = this.q;
+      const out = native.decryptBatch(ctx, 1, this.N, Uint16Array.from(eExp, x => ((x % q) + q) % q));
+      const remainder2 = Array.from(out.remainder2);
+      return {
+        value: trimPolynomial(remainder2),
+        inputs: {
+          f: expandArray(this.f.map(x => x === -1 ? q - 1 : x), this.N, 0), fp: expandArray(this.fp, this.N, 0), e: eExp,
+          quotient1: Array.from(out.quotient1), remainder1: Array.from(out.remainder1),
+          quotient2: Array.from(out.quotient2), remainder2,
+        },
+        params: [this.q, this.calculateNq(), this.p, this.calculateNp(), this.N],
+      };
+    }
+    // engine-native unit of work: B rows per call, typed arrays in and out (fixed length, un-trimmed)
+    encryptBitsBatch(B, r, m) { return native.encryptBatch(this.#loadPublic(), B, this.N, r, m); }
+    decryptBitsBatch(B, e) { return native.decryptBatch(this.#loadPrivate(), B, this.N, e); }
+    sumCiphertexts(B, e) { return trimPolynomial(Array.from(native.sum(this.#engine(), B, this.N, e))); }
+  };
+}

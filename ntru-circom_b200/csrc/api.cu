@@ -62,6 +62,7 @@ struct HostArr {
 constexpr int kMaxArr = 10;
 
 // Runs `launch(rows, dev[])` over B rows in chunks, overlapping H2D, kernels and D2H on three streams.
+// Every array moves over PCIe as a packed 1-D copy; k_repitch converts to / from the pitched device layout.
 template <class Launch>
 int run_pipeline(ntru_ctx *ctx, size_t B, HostArr (&arr)[kMaxArr], Launch launch) {
   const size_t chunk = ctx->chunk_rows;
@@ -69,32 +70,46 @@ int run_pipeline(ntru_ctx *ctx, size_t B, HostArr (&arr)[kMaxArr], Launch launch
   const size_t rows_alloc = B < chunk ? B : chunk;
   for (int s = 0; s < kNumSlots; ++s)
     for (int a = 0; a < kMaxArr; ++a)
-      if (arr[a].used) NTRU_CUDA(ctx, ctx->slot_bufs[s][a].reserve(rows_alloc * P * arr[a].elem));
+      if (arr[a].used) {
+        NTRU_CUDA(ctx, ctx->slot_bufs[s][a].reserve(rows_alloc * P * arr[a].elem));
+        NTRU_CUDA(ctx, ctx->slot_packed[s][a].reserve(rows_alloc * arr[a].width * arr[a].elem));
+      }
   size_t ci = 0;
   for (size_t row0 = 0; row0 < B; row0 += chunk, ++ci) {
     const size_t rows = (B - row0) < chunk ? (B - row0) : chunk;
     const int s = (int)(ci % kNumSlots);
     void *dev[kMaxArr];
     for (int a = 0; a < kMaxArr; ++a) dev[a] = arr[a].used ? ctx->slot_bufs[s][a].ptr : nullptr;
+    // inputs: packed 1-D H2D on s_in (the slot's packed staging is free once the previous unpack ran)
     if (ci >= (size_t)kNumSlots) NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[s], 0));
     for (int a = 0; a < kMaxArr; ++a) {
       if (!arr[a].used || !arr[a].in) continue;
       const size_t wb = arr[a].width * arr[a].elem;
-      NTRU_CUDA(ctx, cudaMemcpy2DAsync(dev[a], P * arr[a].elem, (const char *)arr[a].in + row0 * wb, wb, wb, rows,
-                                       cudaMemcpyHostToDevice, ctx->s_in));
+      NTRU_CUDA(ctx, cudaMemcpyAsync(ctx->slot_packed[s][a].ptr, (const char *)arr[a].in + row0 * wb, rows * wb,
+                                     cudaMemcpyHostToDevice, ctx->s_in));
     }
     NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_in[s], ctx->s_in));
     NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[s], 0));
     if (ci >= (size_t)kNumSlots) NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));
+    for (int a = 0; a < kMaxArr; ++a) {
+      if (!arr[a].used || !arr[a].in) continue;
+      int rc = launch_repitch(ctx, ctx->slot_packed[s][a].ptr, dev[a], rows, (int)arr[a].width, (int)arr[a].elem, true);
+      if (rc != NTRU_OK) return rc;
+    }
     int rc = launch(rows, dev);
     if (rc != NTRU_OK) return rc;
+    for (int a = 0; a < kMaxArr; ++a) {
+      if (!arr[a].used || !arr[a].out) continue;
+      rc = launch_repitch(ctx, dev[a], ctx->slot_packed[s][a].ptr, rows, (int)arr[a].width, (int)arr[a].elem, false);
+      if (rc != NTRU_OK) return rc;
+    }
     NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_comp[s], ctx->stream));
     NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[s], 0));
     for (int a = 0; a < kMaxArr; ++a) {
       if (!arr[a].used || !arr[a].out) continue;
       const size_t wb = arr[a].width * arr[a].elem;
-      NTRU_CUDA(ctx, cudaMemcpy2DAsync((char *)arr[a].out + row0 * wb, wb, dev[a], P * arr[a].elem, wb, rows,
-                                       cudaMemcpyDeviceToHost, ctx->s_out));
+      NTRU_CUDA(ctx, cudaMemcpyAsync((char *)arr[a].out + row0 * wb, ctx->slot_packed[s][a].ptr, rows * wb,
+                                     cudaMemcpyDeviceToHost, ctx->s_out));
     }
     NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_out[s], ctx->s_out));
   }
@@ -234,6 +249,7 @@ void ntru_destroy(ntru_ctx *ctx) {
     if (ctx->ev_comp[s]) cudaEventDestroy(ctx->ev_comp[s]);
     if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
     for (auto &b : ctx->slot_bufs[s]) b.release();
+    for (auto &b : ctx->slot_packed[s]) b.release();
   }
   ctx->d_h.release(); ctx->d_f.release(); ctx->d_fp.release(); ctx->d_b.release(); ctx->d_partial.release();
   ctx->km_h.mat.release(); ctx->km_f.mat.release(); ctx->km_fp.mat.release();

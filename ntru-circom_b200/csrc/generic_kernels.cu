@@ -351,6 +351,46 @@ __global__ void __launch_bounds__(kSampleRows) k_sample_r(int N, int P, int dr, 
 
 }  // namespace
 
+// ---- pitch conversion for the host-buffer entry points --------------------------------------------
+// Host rows are packed (N or N+1 elements), device rows are pitched (P elements).  A 2-D DMA copy with ~1 KB
+// rows runs at a fraction of PCIe speed (measured 12 GB/s D2H), so the pipeline moves packed buffers with
+// plain 1-D copies and converts on the device.  kToPitched: packed -> pitched (pad columns zeroed).
+template <typename T, bool kToPitched>
+__global__ void k_repitch(const T *__restrict__ src, T *__restrict__ dst, size_t rows, int width, int P) {
+  const size_t total = rows * (size_t)(kToPitched ? P : width);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    if (kToPitched) {
+      const size_t r = idx / P;
+      const int c = (int)(idx % P);
+      dst[idx] = c < width ? src[r * width + c] : (T)0;
+    } else {
+      const size_t r = idx / width;
+      const int c = (int)(idx % width);
+      dst[idx] = src[r * (size_t)P + c];
+    }
+  }
+}
+
+int launch_repitch(ntru_ctx *ctx, const void *src, void *dst, size_t rows, int width, int elem, bool to_pitched) {
+  if (rows == 0) return NTRU_OK;
+  const size_t total = rows * (size_t)(to_pitched ? ctx->P : width);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  {
+    LaunchTimer timer(ctx, NTRU_K_OTHER);
+    if (elem == 2) {
+      if (to_pitched) k_repitch<uint16_t, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint16_t *)src, (uint16_t *)dst, rows, width, ctx->P);
+      else k_repitch<uint16_t, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint16_t *)src, (uint16_t *)dst, rows, width, ctx->P);
+    } else {
+      if (to_pitched) k_repitch<uint8_t, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint8_t *)src, (uint8_t *)dst, rows, width, ctx->P);
+      else k_repitch<uint8_t, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint8_t *)src, (uint8_t *)dst, rows, width, ctx->P);
+    }
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
 static int block_threads(int NB) { return ((NB + 31) / 32) * 32; }
 
 int launch_encrypt_generic(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r,

@@ -56,7 +56,8 @@ struct ntru_ctx {
   ntru::DevBuf d_h, d_f, d_fp;     // context keys, P entries each
   ntru::KeyMatrix km_h, km_f, km_fp;
   ntru::DevBuf d_b;                // lifted polynomial b between the two decrypt products (tensor schedule)
-  ntru::DevBuf slot_bufs[ntru::kNumSlots][10];
+  ntru::DevBuf slot_bufs[ntru::kNumSlots][10];     // pitched device arrays of the host pipeline
+  ntru::DevBuf slot_packed[ntru::kNumSlots][10];   // packed staging (what the 1-D H2D / D2H copies move)
   ntru::DevBuf d_partial;
   size_t chunk_rows = 32768;
   int opt_path = 0;
@@ -102,6 +103,7 @@ int launch_decrypt_generic(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8
 int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial);
 int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
+int launch_repitch(ntru_ctx *ctx, const void *src, void *dst, size_t rows, int width, int elem, bool to_pitched);
 
 // ---- tcgen05 schedule (umma_kernels.cu) ----
 int umma_init(ntru_ctx *ctx);                    // probes the device, sets ctx->tensor_ok
