@@ -136,7 +136,7 @@ __device__ __forceinline__ void pair_walk(const UmmaArgs &a, F &&f) {
   int titer = 0;
   for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, ++titer) {
     for (int part = 0; part < parts; ++part) {
-      const int hi = a.with_hi && part == 0;
+      const int hi = part == 1;
       for (int c = 0; c < a.nchunks; ++c, ++cc) {
         const int a0 = first_atom(a, hi, c);
         const bool first_chunk = part == 0 && c == 0, last_chunk = part == parts - 1 && c == a.nchunks - 1;
@@ -239,7 +239,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         const int a_row = T * 256 + (int)rank * kTileRows;
         for (int part = 0; part < parts; ++part) {
-          const int hi = a.with_hi && part == 0;
+          const int hi = part == 1;
           for (int c = 0; c < a.nchunks; ++c) {
             const int a0 = first_atom(a, hi, c);
             const bool a_load = MODE != DEC1 && (!resident || (part == 0 && c == 0));
@@ -299,11 +299,15 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       uint32_t cc = 0, t_par = 0;           // chunk counter, resident-A phase parity (per tile)
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         for (int part = 0; part < parts; ++part) {
-          const int hi = a.with_hi && part == 0;
+          const int hi = part == 1;
           for (int c = 0; c < a.nchunks; ++c, ++cc) {
             const int a0 = first_atom(a, hi, c);
             const bool first_chunk = part == 0 && c == 0, last_chunk = part == parts - 1 && c == a.nchunks - 1;
-            const bool a_wait = !resident || first_chunk, a_release = !resident || last_chunk;
+            const bool a_wait = !resident || first_chunk;
+            // resident A slots are freed at their last use in the tile: with the hi chunks last, chunk c is the
+            // last reader of atoms [a0(c), a0(c+1)), so the next tile's loads start several chunks ahead
+            const int rel_end = (!resident || !a.with_hi) ? a.atoms : (c + 1 < a.nchunks ? first_atom(a, 1, c + 1) : a.atoms);
+            const bool rel_chunk = !resident || (a.with_hi ? hi != 0 : last_chunk);
             const uint32_t buf = cc & 1;
             if (lane == 0) TRACE(1, 0, cc);
             mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
@@ -328,7 +332,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                   umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
                   umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
                   umma_commit_pair(b_empty(sb));
-                  if (a_release) umma_commit_pair(a_empty(sa));
+                  if (rel_chunk && at < rel_end) umma_commit_pair(a_empty(sa));
                   if (last) umma_commit_pair(tfull_bar(buf));
                 }
                 __syncwarp();
@@ -360,16 +364,16 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         if (++w.at < a.atoms) return;
         if (++w.c == a.nchunks) {
           w.c = 0;
-          if (++w.part == parts) w.part = 0; else { w.at = first_atom(a, a.with_hi && w.part == 0, w.c); return; }
+          if (++w.part == parts) w.part = 0; else { w.at = first_atom(a, w.part == 1, w.c); return; }
         } else {
-          w.at = first_atom(a, a.with_hi && w.part == 0, w.c);
+          w.at = first_atom(a, w.part == 1, w.c);
           return;
         }
       }
       w.T += gridDim.x >> 1;
       ++w.titer;
       w.valid = w.T < a.npairs;
-      w.at = first_atom(a, a.with_hi, 0);
+      w.at = 0;
     };
     auto load_atom = [&](const Item &w, uint4 (&raw)[8]) {
       const int col = w.at * kAtomK + chunk * 16;        // first coefficient of this thread's chunk
@@ -387,7 +391,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     Item cur;
     cur.T = blockIdx.x >> 1; cur.part = 0; cur.c = 0; cur.ia = 0; cur.titer = 0;
     cur.valid = cur.T < a.npairs;
-    cur.at = first_atom(a, a.with_hi, 0);
+    cur.at = 0;
     uint4 raw[8], raw_next[8];
     if (cur.valid) load_atom(cur, raw);
     while (cur.valid) {
@@ -463,7 +467,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
       const int out_row = T * 256 + (int)rank * kTileRows + quad * 32;
       for (int part = 0; part < parts; ++part) {
-        const int hi = a.with_hi && part == 0;
+        const int hi = part == 1;
         for (int c = 0; c < a.nchunks; ++c, ++cc) {
           const uint32_t buf = cc & 1;
           const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;

@@ -1,0 +1,95 @@
+"""Throughput of the other BASELINE configs (device-resident, CUDA events): python scripts/bench_configs.py [names...]"""
+import json, os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ntru_circom_b200 as nb
+
+HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+dev = "cuda"
+
+
+def timed(fn, iters=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def setup(cfg):
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{cfg}.npz")))
+    N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    return g, eng, N, q, dr
+
+
+def same_key(cfg, B):
+    g, eng, N, q, dr = setup(cfg)
+    P = eng.pitch
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, dr, 1, 0, r)
+    m = torch.zeros((B, P), dtype=torch.uint8, device=dev); m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
+    val = torch.empty((B, P), dtype=torch.int16, device=dev); quo = torch.empty_like(val)
+    out = torch.empty((B, P), dtype=torch.uint8, device=dev); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)
+    t_enc = timed(lambda: eng.encrypt_dev(B, r, m, value=val, quotientE=quo))
+    t_dec = timed(lambda: eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2))
+    ok = bool(torch.equal(out[:, :N], m[:, :N]))
+    tot = t_enc + t_dec
+    print(json.dumps({"config": cfg, "mode": "same-key tcgen05", "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
+                      "ct_per_s": B / (tot * 1e-3), "GBps_14N": 14 * N * B / (tot * 1e-3) / 1e9, "frac_hbm": 14 * N * B / (tot * 1e-3) / 1e9 / HBM,
+                      "roundtrip_equals_message": ok}))
+    eng.close()
+
+
+def distinct_key(cfg, B):
+    g, eng, N, q, dr = setup(cfg)
+    P = eng.pitch
+    h = torch.zeros((B, P), dtype=torch.int16, device=dev); h[:, :N] = torch.randint(0, q, (B, N), device=dev, dtype=torch.int16)
+    f = torch.zeros((B, P), dtype=torch.int8, device=dev); f[:, :N] = torch.randint(-1, 2, (B, N), device=dev, dtype=torch.int8)
+    fp = torch.zeros((B, P), dtype=torch.uint8, device=dev); fp[:, :N] = torch.randint(0, 3, (B, N), device=dev, dtype=torch.uint8)
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, dr, 1, 0, r)
+    m = torch.zeros((B, P), dtype=torch.uint8, device=dev); m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
+    val = torch.empty((B, P), dtype=torch.int16, device=dev); quo = torch.empty_like(val)
+    out = torch.empty((B, P), dtype=torch.uint8, device=dev); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)
+    t_enc = timed(lambda: eng.encrypt_dev(B, r, m, value=val, quotientE=quo, h_rows=h), iters=3, warm=1)
+    t_dec = timed(lambda: eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2, f_rows=f, fp_rows=fp), iters=3, warm=1)
+    tot = t_enc + t_dec
+    print(json.dumps({"config": cfg, "mode": "distinct-key CUDA-core", "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
+                      "ct_per_s": B / (tot * 1e-3), "GBps_18N": 18 * N * B / (tot * 1e-3) / 1e9, "frac_hbm": 18 * N * B / (tot * 1e-3) / 1e9 / HBM,
+                      "GFMA_per_s": 3 * N * N * B / (tot * 1e-3) / 1e9}))
+    eng.close()
+
+
+def sum_rows(cfg, B):
+    g, eng, N, q, dr = setup(cfg)
+    P = eng.pitch
+    e = torch.randint(0, q, (B, P), device=dev, dtype=torch.int16)
+    part = torch.zeros(P, dtype=torch.int32, device=dev); out = torch.empty(P, dtype=torch.int16, device=dev)
+    def run():
+        part.zero_()
+        eng.sum_partial_dev(B, e, part)
+        eng.sum_finalize_dev(part, out)
+    t = timed(run, iters=5, warm=2)
+    want = (e[:, :N].to(torch.int64).sum(dim=0)) % q
+    ok = bool(torch.equal(out[:N].to(torch.int64) & 0xFFFF, want))
+    print(json.dumps({"config": cfg, "mode": "ciphertext sum", "rows": B, "ms": t, "ct_per_s": B / (t * 1e-3),
+                      "GBps_2N": 2 * N * B / (t * 1e-3) / 1e9, "frac_hbm_2N": 2 * N * B / (t * 1e-3) / 1e9 / HBM,
+                      "GBps_pitched": 2 * P * B / (t * 1e-3) / 1e9, "matches_torch_sum": ok}))
+    eng.close()
+
+
+which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
+if "c1" in which: same_key("default167", 1 << 20)
+if "c2" in which: same_key("hps509", 1 << 20)
+if "c3" in which: distinct_key("hps677", 1 << 18)
+if "c3s" in which: same_key("hps677", 1 << 20)
+if "c4" in which: same_key("hps821", 1 << 20)
+if "c5" in which: sum_rows("hrss701", 10_000_000)
+if "c5s" in which: same_key("hrss701", 1 << 20)
