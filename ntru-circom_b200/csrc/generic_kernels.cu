@@ -464,10 +464,9 @@ int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out) {
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r) {
   if (B == 0) return NTRU_OK;
   const size_t smem = (size_t)kSampleRows * (ctx->P + 4);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->sampler_attr_set) {
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_sample_r, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+    ctx->sampler_attr_set = true;
   }
   const size_t blocks = (B + kSampleRows - 1) / kSampleRows;
   {

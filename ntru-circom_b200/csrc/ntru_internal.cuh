@@ -61,6 +61,8 @@ struct ntru_ctx {
   ntru::DevBuf d_partial;
   size_t chunk_rows = 32768;
   int opt_path = 0;
+  int umma_attr_set = 0;           // bit per kernel mode: dynamic shared memory attribute applied on this device
+  bool sampler_attr_set = false;
   int tensor_variant = 0;          // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
   int last_path = 0;
   int sm_count = 148;

@@ -34,6 +34,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ntru_internal.cuh"
 
@@ -69,6 +70,9 @@ struct UmmaArgs {
   int nA, nB;             // shared-memory slots for A and stages for B
   int a_resident;         // A slots hold the whole tile (loaded once per tile)
   int nM, nS;             // message slots (ENC), store-staging slots
+  int a_rel;              // commits that free an A slot: 2 (both MMA issuers) for resident A, else 1
+  int two_issuers;        // second MMA issuer warp enabled (needs slices per chunk < B ring stages)
+  int mat_rows;           // rows of the key matrix (2 * nchunks * NC); K block kb starts at row kb * mat_rows
   int out_mask;           // which outputs exist: bit0 = cyc #1, bit1 = cyc #2, bit2 = hi
   const void *a_src;      // DEC1: e rows (uint16), pitch P elements
   const uint8_t *m;       // ENC: message rows
@@ -384,7 +388,7 @@ k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, cons
                 mbar_arrive_expect_tx(full_bar(s), bytes);
                 if (MODE != DEC1)
                   tma_load_2d(smem_base + s * kStageBytes, &tmapA, at * kAtomK, tile * kTileRows, full_bar(s));
-                tma_load_2d(smem_base + s * kStageBytes + kABytes, &tmapB, lk * a.Kp + at * kAtomK, row0, full_bar(s));
+                tma_load_2d(smem_base + s * kStageBytes + kABytes, &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, full_bar(s));
               }
             }
           }
@@ -566,7 +570,10 @@ __global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, int NCo,
     if (mode == ENC) out = ln == 0 ? (uint8_t)(coef & 0xff) : (uint8_t)(coef >> 8);
     else if (mode == DEC1) out = (uint8_t)(int8_t)(lk == 0 ? coef : coef * 64);
     else out = (uint8_t)coef;
-    mat[idx] = out;
+    // tile-major storage: for each 128-byte K block all rows are contiguous (128-byte pitch), so that the box
+    // of one pipeline slice (NC or NC/2 rows x 128 B) is one contiguous run of global memory
+    const size_t rows_total = (size_t)2 * nchunks * nl * NCo;
+    mat[((size_t)(kb / kAtomK) * rows_total + (size_t)(idx / klen)) * kAtomK + (kb % kAtomK)] = out;
   }
 }
 
@@ -638,11 +645,10 @@ int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyM
                                                                (uint8_t *)km.mat.ptr);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
-  int rc = encode_2d(ctx, km.tmap, km.mat.ptr, (uint64_t)km.klen, (uint64_t)rows, (uint64_t)km.klen, kAtomK,
-                     (uint32_t)km.chunk_cols);
+  const uint64_t tiled_rows = (uint64_t)rows * (km.klen / kAtomK);
+  int rc = encode_2d(ctx, km.tmap, km.mat.ptr, kAtomK, tiled_rows, kAtomK, kAtomK, (uint32_t)km.chunk_cols);
   if (rc) return rc;
-  rc = encode_2d(ctx, km.tmap_half, km.mat.ptr, (uint64_t)km.klen, (uint64_t)rows, (uint64_t)km.klen, kAtomK,
-                 (uint32_t)km.chunk_cols / 2);
+  rc = encode_2d(ctx, km.tmap_half, km.mat.ptr, kAtomK, tiled_rows, kAtomK, kAtomK, (uint32_t)km.chunk_cols / 2);
   if (rc) return rc;
   NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   km.ready = true;
@@ -651,14 +657,14 @@ int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyM
 
 template <int MODE>
 int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *a_bytes) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->umma_attr_set & (1 << MODE))) {      // per context: function attributes are per device
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_product<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-    attr_set = true;
+    ctx->umma_attr_set |= 1 << MODE;
   }
   a.N = ctx->N; a.P = ctx->P; a.kl = km.limbs; a.nl = km.nlimbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
   a.NC = km.chunk_cols; a.NCo = km.out_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
+  a.mat_rows = 2 * a.nchunks * a.NC;
   a.ntiles = (int)((a.B + kTileRows - 1) / kTileRows);
   a.npairs = (int)((a.B + 2 * kTileRows - 1) / (2 * kTileRows));
   a.nS = 2;
@@ -670,6 +676,9 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   } else {
     a.a_resident = 0; a.nA = 6; a.nB = avail - 6;
   }
+  // resident A slots are read by both MMA issuer warps (alternating chunks) whenever a tile has >= 2 chunks
+  a.two_issuers = (a.atoms * a.kl < a.nB && (a.with_hi ? 2 : 1) * a.nchunks >= 2) ? 1 : 0;
+  a.a_rel = (a.a_resident && a.two_issuers) ? 2 : 1;
   CUtensorMap tmB, tmA, tmM, tmO[3];
   const bool pair = ctx->tensor_variant == 0;
   memcpy(&tmB, pair ? km.tmap_half : km.tmap, sizeof tmB);
@@ -708,12 +717,13 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
       rc = encode_2d_ex(ctx, &tmO[i], optr[i], oelem[i], P, (uint64_t)a.B, P * oelem[i], (uint32_t)obox[i], 32, oswz[i]);
       if (rc) return rc;
     }
+    if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // timing experiment only: results are not written
   }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
     if (pair) {
       const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
-      k_umma_pair<MODE><<<2 * clusters, kThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+      k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
     } else {
       const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
       k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);

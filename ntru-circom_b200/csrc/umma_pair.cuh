@@ -43,7 +43,8 @@ constexpr int kPairBars = 4 * kPairSlots + 8;   // a_full/a_empty/b_full/b_empty
 // Warp roles: the warp scheduler favours the highest warp id of an SM sub-partition, so the two single-thread
 // roles that sit on the critical path get the highest ids: 16 = TMA producer, 17 = MMA issuer.  Warps 0-15 are
 // epilogue warps (DEC1: 0-7 transform, 8-15 epilogue); an epilogue warp reads TMEM lanes 32*(warp%4)...
-constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17, kPairEpiWarp0Dec1 = 8;
+constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17 /* and 18 */, kPairEpiWarp0Dec1 = 8;
+constexpr int kPairThreads = 19 * 32;
 #ifdef NTRU_TRACE
 constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 1024 + 8 * 3 * 1024;
 #else
@@ -163,7 +164,7 @@ __device__ __forceinline__ void pair_walk(const UmmaArgs &a, F &&f) {
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA,
             const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapO0,
             const __grid_constant__ CUtensorMap tmapO1, const __grid_constant__ CUtensorMap tmapO2) {
@@ -199,7 +200,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.nA; ++i) {
       mbar_init(a_full(i), MODE == DEC1 ? 16 : 2);   // DEC1: 8 transform warps per CTA; else one producer per CTA
-      mbar_init(a_empty(i), 1);                      // tcgen05.commit (multicast)
+      mbar_init(a_empty(i), a.a_rel);                // tcgen05.commit (multicast) from each issuer that reads it
     }
     for (int j = 0; j < a.nB; ++j) {
       mbar_init(b_full(j), 2);                       // one producer arrival per CTA (+ transaction bytes)
@@ -270,7 +271,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 if (elect_one()) {
                   if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
                   else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                  tma_load_2d_pair(b_slot(sb), &tmapB, lk * a.Kp + at * kAtomK, row0, lead_b_full + 8u * sb);
+                  tma_load_2d_pair(b_slot(sb), &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
                   TRACE(3, 2, (hi ? 0 : a.nchunks) + c);
                 }
                 __syncwarp();
@@ -282,65 +283,78 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         }
       }
     }
-  } else if (warp == kPairMmaWarp) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.  The loop
-    // is written with incremental counters: every instruction here sits on the critical path of the tensor
-    // pipe (512 cycles of MMA work per slice), and the first version -- one divergent lane walking the generic
-    // slice iterator, ~150 SASS instructions per slice -- was issue-bound at ~1400 cycles per slice (ncu).
+  } else if (warp == kPairMmaWarp || warp == kPairMmaWarp + 1) {
+    // ===================== MMA issuers (leader CTA only): two warps, alternating chunks =====================
+    // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.  A slice
+    // holds 512 cycles of tensor work but costs one issuer ~600 cycles (mbarrier try_wait latency, ~85 SASS
+    // instructions of uniform-datapath descriptor arithmetic, commits), so ONE issuer left the tensor pipe 58 %
+    // busy.  Issuer w owns chunks cc == w (mod 2), i.e. TMEM buffer w; the B ring is consumed in order, each
+    // stage by exactly one issuer; a resident A slot is freed when BOTH issuers have committed their last read
+    // of it in the tile (a_empty count 2).  Phase parity only tells adjacent uses of a ring stage apart, so the
+    // second issuer is enabled only when a chunk has fewer slices than the B ring has stages (a.two_issuers):
+    // then no issuer can wait on a stage two phases ahead of its oldest unconsumed use.
     if (leader) {
+      const uint32_t w = (uint32_t)(warp - kPairMmaWarp);
       const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.NC);
       const uint64_t desc_hi = make_smem_desc(0) & ~0x3FFFull;             // everything but the start address
       const uint32_t a_addr16 = (smem_base >> 4), b_addr16 = (smem_base + a.nA * kSlotBytes) >> 4;
       const int parts = a.with_hi ? 2 : 1;
+      const int nct = parts * a.nchunks;                                   // chunks per tile
       const bool resident = a.a_resident != 0;
       uint32_t sb = 0, b_par = 0;           // B ring position / phase parity
       uint32_t sas = 0, a_par_s = 0;        // streaming A ring position / phase parity
       uint32_t cc = 0, t_par = 0;           // chunk counter, resident-A phase parity (per tile)
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
-        for (int part = 0; part < parts; ++part) {
-          const int hi = part == 1;
-          for (int c = 0; c < a.nchunks; ++c, ++cc) {
-            const int a0 = first_atom(a, hi, c);
-            const bool first_chunk = part == 0 && c == 0, last_chunk = part == parts - 1 && c == a.nchunks - 1;
-            const bool a_wait = !resident || first_chunk;
-            // resident A slots are freed at their last use in the tile: with the hi chunks last, chunk c is the
-            // last reader of atoms [a0(c), a0(c+1)), so the next tile's loads start several chunks ahead
-            const int rel_end = (!resident || !a.with_hi) ? a.atoms : (c + 1 < a.nchunks ? first_atom(a, 1, c + 1) : a.atoms);
-            const bool rel_chunk = !resident || (a.with_hi ? hi != 0 : last_chunk);
-            const uint32_t buf = cc & 1;
-            if (lane == 0) TRACE(1, 0, cc);
-            mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
-            if (lane == 0) TRACE(1, 1, cc);
-            const uint32_t d_tmem = tmem_base + buf * kAccCols;
-            uint32_t accumulate = 0;
-            for (int at = a0; at < a.atoms; ++at) {
-              for (int lk = 0; lk < a.kl; ++lk) {
-                const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
-                if (lane == 0) TRACE(1, 4, cc);
-                mbar_wait(b_full(sb), b_par);
-                if (lane == 0) TRACE(1, 2, cc);
-                if (a_wait) mbar_wait(a_full(sa), resident ? t_par : a_par_s);
-                if (lane == 0) TRACE(1, 3, cc);
-                tc_fence_after();
-                const uint64_t da = desc_hi | (uint64_t)((a_addr16 + sa * (kSlotBytes >> 4)) & 0x3FFF);
-                const uint64_t db = desc_hi | (uint64_t)((b_addr16 + sb * (kSlotBytes >> 4)) & 0x3FFF);
-                const bool last = at == a.atoms - 1 && lk == a.kl - 1;
-                if (elect_one()) {
-                  umma_i8_pair(d_tmem, da, db, idesc, accumulate);
-                  umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
-                  umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
-                  umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
-                  umma_commit_pair(b_empty(sb));
-                  if (rel_chunk && at < rel_end) umma_commit_pair(a_empty(sa));
-                  if (last) umma_commit_pair(tfull_bar(buf));
-                }
-                __syncwarp();
-                if (lane == 0) TRACE(1, 5, cc);
-                accumulate = 1;
-                if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
-                if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
+        for (int j = 0; j < nct; ++j, ++cc) {
+          const int hi = j >= a.nchunks;
+          const int c = hi ? j - a.nchunks : j;
+          const int a0 = first_atom(a, hi, c);
+          const uint32_t nsl = (uint32_t)((a.atoms - a0) * a.kl);            // slices of this chunk
+          if (a.two_issuers ? (cc & 1) != w : w != 0) {   // not this issuer's chunk: only advance the ring positions
+            sb += nsl;
+            while (sb >= (uint32_t)a.nB) { sb -= a.nB; b_par ^= 1; }
+            if (!resident) {
+              sas += nsl;
+              while (sas >= (uint32_t)a.nA) { sas -= a.nA; a_par_s ^= 1; }
+            }
+            continue;
+          }
+          // this issuer reads atom x again later in the tile iff its next chunk (j+2) does: chunks j+2, j+4, ...
+          // read ever fewer atoms (cyclic chunks read all, hi chunk c reads atoms >= a0(c), a0 non-decreasing)
+          int next_a0 = a.atoms;            // first atom read by chunk j+2 (a.atoms: none)
+          const int jn = j + (a.two_issuers ? 2 : 1);          // this issuer's next chunk in the tile
+          if (jn < nct) next_a0 = (jn >= a.nchunks) ? first_atom(a, 1, jn - a.nchunks) : 0;
+          const uint32_t buf = cc & 1;
+          const uint32_t my = cc >> 1;      // uses of this TMEM buffer so far
+          if (lane == 0) TRACE(1, 0, cc);
+          mbar_wait(tempty_bar(buf), (my & 1) ^ 1);
+          if (lane == 0) TRACE(1, 1, cc);
+          const uint32_t d_tmem = tmem_base + buf * kAccCols;
+          uint32_t accumulate = 0;
+          for (int at = a0; at < a.atoms; ++at) {
+            for (int lk = 0; lk < a.kl; ++lk) {
+              const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
+              mbar_wait(b_full(sb), b_par);
+              mbar_wait(a_full(sa), resident ? t_par : a_par_s);
+              tc_fence_after();
+              const uint64_t da = desc_hi | (uint64_t)((a_addr16 + sa * (kSlotBytes >> 4)) & 0x3FFF);
+              const uint64_t db = desc_hi | (uint64_t)((b_addr16 + sb * (kSlotBytes >> 4)) & 0x3FFF);
+              const bool last = at == a.atoms - 1 && lk == a.kl - 1;
+              const bool release = !resident || at < next_a0;
+              if (elect_one()) {
+                umma_i8_pair(d_tmem, da, db, idesc, accumulate);
+                umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+                umma_commit_pair(b_empty(sb));
+                if (release) umma_commit_pair(a_empty(sa));
+                if (last) umma_commit_pair(tfull_bar(buf));
               }
+              __syncwarp();
+              if (lane == 0) TRACE(1, 5, cc);
+              accumulate = 1;
+              if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
+              if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
             }
           }
         }
