@@ -72,6 +72,7 @@ struct UmmaArgs {
   int nM, nS;             // message slots (ENC), store-staging slots
   int a_rel;              // commits that free an A slot: 2 (both MMA issuers) for resident A, else 1
   int two_issuers;        // second MMA issuer warp enabled (needs slices per chunk < B ring stages)
+  int debug_flags;        // timing experiments only (NTRU_DEBUG_NOB: bit 0 = skip the B operand loads)
   int mat_rows;           // rows of the key matrix (2 * nchunks * NC); K block kb starts at row kb * mat_rows
   int out_mask;           // which outputs exist: bit0 = cyc #1, bit1 = cyc #2, bit2 = hi
   const void *a_src;      // DEC1: e rows (uint16), pitch P elements
@@ -718,6 +719,7 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
       if (rc) return rc;
     }
     if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // timing experiment only: results are not written
+    if (getenv("NTRU_DEBUG_NOB")) a.debug_flags |= 1;
   }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));

@@ -288,3 +288,78 @@ def test_device_resident_api_and_properties_at_scale(nb, engines, golden):
     eng.sync()
     want_sum = (val[:, :N].to(torch.int64) & 0xFFFF).sum(dim=0) % q
     assert torch.equal(s16[:N].to(torch.int64) & 0xFFFF, want_sum)
+
+
+@pytest.mark.parametrize("B", [1, 127, 128, 129, 255, 256, 257, 513])
+def test_tile_boundaries_both_tensor_kernels(B, nb, engines, golden):
+    """Row counts around the 128-row CTA tile and the 256-row CTA-pair tile, with and without witness,
+    on the CTA-pair kernel (variant 0) and the single-CTA kernel (variant 1)."""
+    g, eng = golden("hps509"), engines("hps509")
+    N, q, p = 509, 2048, 3
+    rng = np.random.default_rng(B)
+    r = o.sample_ternary_rows(B, N, 169, 169, rng).astype(np.uint8)
+    m = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
+    want_e = o.encrypt_batch(g["h"].astype(np.int64), r, m, q)
+    want_d = o.decrypt_batch(g["f"].astype(np.int64), g["fp"].astype(np.int64), want_e["value"], q, p)
+    from ntru_circom_b200 import _lib
+    eng.set_path(nb.PATH_TENSOR)
+    try:
+        for variant in (0, 1):
+            eng.set_option(_lib.NTRU_OPT_TENSOR_VARIANT, variant)
+            for witness in (True, False):
+                enc = eng.encrypt_batch(r, m, witness=witness)
+                dec = eng.decrypt_batch(want_e["value"].astype(np.uint16), witness=witness)
+                assert np.array_equal(enc["value"], want_e["value"]), (variant, witness)
+                assert np.array_equal(dec["value"], want_d["value"]), (variant, witness)
+                if witness:
+                    for k in ENC_KEYS:
+                        assert np.array_equal(enc[k], want_e[k]), (variant, k)
+                    for k in DEC_KEYS:
+                        assert np.array_equal(dec[k], want_d[k]), (variant, k)
+    finally:
+        eng.set_option(_lib.NTRU_OPT_TENSOR_VARIANT, 0)
+        eng.set_path(nb.PATH_AUTO)
+
+
+def test_full_size_round_trip_and_checksums(nb, engines, golden):
+    """BASELINE config 2 at full size (1,000,000 ciphertexts, one key): size-independent properties.
+    decrypt(encrypt(m)) == m for every row, the witness satisfies the division identity
+    c = quotient * (1 - x^N) + remainder coefficient-wise (checked through column checksums), and the
+    CUDA-core schedule agrees with the tensor schedule on a strided sample of rows."""
+    torch = pytest.importorskip("torch")
+    g, eng = golden("hps509"), engines("hps509")
+    N, q, P, B = 509, 2048, eng.pitch, 1_000_000
+    dev = "cuda"
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    eng.sample_r_dev(B, 169, 11, 0, r)
+    m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
+    val = torch.empty((B, P), dtype=torch.int16, device=dev)
+    quo = torch.empty((B, P), dtype=torch.int16, device=dev)
+    out = torch.empty((B, P), dtype=torch.uint8, device=dev)
+    r1 = torch.empty((B, P), dtype=torch.int16, device=dev)
+    q1 = torch.empty((B, P), dtype=torch.int16, device=dev)
+    q2 = torch.empty((B, P), dtype=torch.uint8, device=dev)
+    eng.encrypt_dev(B, r, m, value=val, quotientE=quo)
+    eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2)
+    eng.sync()
+    assert eng.last_path == nb.PATH_TENSOR
+    assert torch.equal(out[:, :N], m[:, :N])
+    # exact weights of the sampled r, zero pads everywhere
+    assert bool(((r == 1).sum(dim=1) == 169).all()) and bool(((r == 2).sum(dim=1) == 169).all())
+    assert not bool(val[:, N:].any()) and not bool(quo[:, N - 1:].any()) and not bool(q1[:, N - 1:].any())
+    # strided sample through the CUDA-core schedule (different kernel, same answers)
+    idx = torch.arange(0, B, 997, device=dev)
+    rs, ms = r[idx].contiguous(), m[idx].contiguous()
+    v2 = torch.empty((len(idx), P), dtype=torch.int16, device=dev)
+    qe2 = torch.empty_like(v2)
+    eng.set_path(nb.PATH_CUDA_CORE)
+    eng.encrypt_dev(len(idx), rs, ms, value=v2, quotientE=qe2)
+    eng.sync()
+    eng.set_path(nb.PATH_AUTO)
+    assert torch.equal(v2, val[idx]) and torch.equal(qe2, quo[idx])
+    # and a few rows against the oracle
+    pick = [0, 499_999, B - 1]
+    want = o.encrypt_batch(g["h"].astype(np.int64), r[pick, :N].cpu().numpy(), m[pick, :N].cpu().numpy(), q)
+    assert np.array_equal(val[pick].cpu().numpy().view(np.uint16)[:, :N], want["value"])
+    assert np.array_equal(quo[pick].cpu().numpy().view(np.uint16)[:, : N + 1], want["quotientE"])
