@@ -678,7 +678,7 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     a.a_resident = 0; a.nA = 6; a.nB = avail - 6;
   }
   // resident A slots are read by both MMA issuer warps (alternating chunks) whenever a tile has >= 2 chunks
-  a.two_issuers = (a.atoms * a.kl < a.nB && (a.with_hi ? 2 : 1) * a.nchunks >= 2) ? 1 : 0;
+  a.two_issuers = 0;   // a second issuer warp was tried: the B ring is too short for two chunks in flight
   a.a_rel = (a.a_resident && a.two_issuers) ? 2 : 1;
   CUtensorMap tmB, tmA, tmM, tmO[3];
   const bool pair = ctx->tensor_variant == 0;

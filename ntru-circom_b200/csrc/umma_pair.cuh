@@ -20,7 +20,7 @@
 #ifdef NTRU_TRACE
 // debug timeline of cluster 0 / CTA 0: each traced thread appends (tag << 40 | clock) words to its own
 // shared-memory lane buffer (cheap: one STS), dumped to global memory at kernel end.
-constexpr int kTraceLanes = 3, kTraceCap = 1024;
+constexpr int kTraceLanes = 4, kTraceCap = 448;   // MMA issuer 0, epilogue warp 0, producer, MMA issuer 1
 __device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
 #define TRACE(role, ev, idx)                                                                      \
   do {                                                                                            \
@@ -29,13 +29,23 @@ __device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
           ((unsigned long long)(((ev) << 12) | ((idx) & 0xfff)) << 40) | (clock64() & 0xffffffffffull); \
     }                                                                                             \
   } while (0)
+#define TRACE_NS(role, ev, idx)                                                                   \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && trace_n[role - 1] < kTraceCap) {                                       \
+      unsigned long long _ns;                                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_ns));                                     \
+      trace_buf[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                   \
+          ((unsigned long long)(((ev) << 12) | ((idx) & 0xfff)) << 40) | (_ns & 0xffffffffffull); \
+    }                                                                                             \
+  } while (0)
 #else
 #define TRACE(role, ev, idx) do {} while (0)
+#define TRACE_NS(role, ev, idx) do {} while (0)
 #endif
 
 constexpr int kSlotBytes = 16384;
 #ifdef NTRU_TRACE
-constexpr int kPairSlots = 12;   // 32 KB of shared memory go to the trace buffers
+constexpr int kPairSlots = 13;   // 16 KB of shared memory go to the trace buffers
 #else
 constexpr int kPairSlots = 14;
 #endif
@@ -43,10 +53,10 @@ constexpr int kPairBars = 4 * kPairSlots + 8;   // a_full/a_empty/b_full/b_empty
 // Warp roles: the warp scheduler favours the highest warp id of an SM sub-partition, so the two single-thread
 // roles that sit on the critical path get the highest ids: 16 = TMA producer, 17 = MMA issuer.  Warps 0-15 are
 // epilogue warps (DEC1: 0-7 transform, 8-15 epilogue); an epilogue warp reads TMEM lanes 32*(warp%4)...
-constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17 /* and 18 */, kPairEpiWarp0Dec1 = 8;
+constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17, kPairAuxWarp = 18, kPairEpiWarp0Dec1 = 8;
 constexpr int kPairThreads = 19 * 32;
 #ifdef NTRU_TRACE
-constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 1024 + 8 * 3 * 1024;
+constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 1024 + 8 * kTraceLanes * kTraceCap;
 #else
 constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 8 * kPairBars + 64;
 #endif
@@ -190,7 +200,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 
 #ifdef NTRU_TRACE
   unsigned long long *trace_buf = reinterpret_cast<unsigned long long *>(smem + (size_t)kPairSlots * kSlotBytes + 1024);
-  int trace_n[kTraceLanes] = {0, 0, 0};
+  int trace_n[kTraceLanes] = {0, 0, 0, 0};
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -226,25 +236,71 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   auto lead = [&](uint32_t local_bar) { return mapa_u32(local_bar, 0); };
 
   if (warp == kPairProducerWarp) {
-    // ===================== TMA producer (both CTAs) =====================
-    // Same lean structure as the MMA issuer below: uniform control flow for the whole warp, incremental ring
-    // counters, one elected lane issues.  (The generic slice iterator cost ~900 cycles per slice here, more than
-    // the 512 cycles of MMA work a slice holds, so the ring never filled and every TMA latency was exposed.)
-    {
-      const int half_rows = a.NC >> 1;
-      const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK, a_bytes = 2u * kABytes;
-      const uint32_t lead_a_full = lead(a_full(0)), lead_b_full = lead(b_full(0));
+    // ===================== B producer (both CTAs): key-matrix slices through the ring =====================
+    // Lean on purpose (uniform control flow for the whole warp, incremental ring counters, one elected lane
+    // issues): a slice holds 512 cycles of MMA work, and a producer written over a generic slice iterator cost
+    // ~900 cycles per slice, so the ring never filled.  It waits on nothing but the ring itself: A-operand and
+    // message loads depend on epilogue progress and live in their own warp (below), otherwise a late epilogue
+    // delays the B loads of the next chunk and MMA, epilogue and loads run one after the other (clock trace).
+    const int half_rows = a.NC >> 1;
+    const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK;
+    const uint32_t lead_b_full = lead(b_full(0));
+    const int parts = a.with_hi ? 2 : 1;
+    uint32_t sb = 0, b_par = 0;
+    if (lane == 0) { TRACE(3, 10, 0); TRACE_NS(3, 11, 0); }
+    for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
+      for (int part = 0; part < parts; ++part) {
+        const int hi = part == 1;
+        for (int c = 0; c < a.nchunks; ++c) {
+          const int a0 = first_atom(a, hi, c);
+          const int row0 = (hi * a.nchunks + c) * a.NC + (int)rank * half_rows;
+          for (int at = a0; at < a.atoms; ++at) {
+            for (int lk = 0; lk < a.kl; ++lk) {
+              mbar_wait(b_empty(sb), b_par ^ 1);
+              if (elect_one()) {
+                if (a.debug_flags & 1) {   // timing experiment: no B traffic at all (operands are stale shared memory)
+                  if (leader) mbar_arrive(b_full(sb)); else mbar_arrive_cluster(lead_b_full + 8u * sb);
+                } else {
+                  if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
+                  else mbar_arrive_cluster(lead_b_full + 8u * sb);
+                  tma_load_2d_pair(b_slot(sb), &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
+                }
+              }
+              __syncwarp();
+              if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) { TRACE(3, 12, 0); TRACE_NS(3, 13, 0); }
+  } else if (warp == kPairAuxWarp) {
+    // ===================== A / message producer (both CTAs; ENC and DEC2 only) =====================
+    if (MODE != DEC1) {
+      const uint32_t a_bytes = 2u * kABytes;
+      const uint32_t lead_a_full = lead(a_full(0));
       const int parts = a.with_hi ? 2 : 1;
       const bool resident = a.a_resident != 0;
-      uint32_t sb = 0, b_par = 0, sas = 0, a_par_s = 0, t_par = 0, mc = 0;
+      uint32_t sas = 0, a_par_s = 0, t_par = 0, mc = 0;
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         const int a_row = T * 256 + (int)rank * kTileRows;
         for (int part = 0; part < parts; ++part) {
           const int hi = part == 1;
           for (int c = 0; c < a.nchunks; ++c) {
             const int a0 = first_atom(a, hi, c);
-            const bool a_load = MODE != DEC1 && (!resident || (part == 0 && c == 0));
-            const int row0 = (hi * a.nchunks + c) * a.NC + (int)rank * half_rows;
+            if (!resident || (part == 0 && c == 0)) {
+              for (int at = a0; at < a.atoms; ++at) {
+                const uint32_t sa = resident ? (uint32_t)at : sas;      // kl == 1 in these modes
+                mbar_wait(a_empty(sa), (resident ? t_par : a_par_s) ^ 1);
+                if (elect_one()) {
+                  if (leader) mbar_arrive_expect_tx(a_full(sa), a_bytes);
+                  else mbar_arrive_cluster(lead_a_full + 8u * sa);
+                  tma_load_2d_pair(a_slot(sa), &tmapA, at * kAtomK, a_row, lead_a_full + 8u * sa);
+                }
+                __syncwarp();
+                if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
+              }
+            }
             if (MODE == ENC && !hi) {   // the chunk's 128 message bytes per row, for this CTA's epilogue
               const uint32_t ms = mc & 1;
               mbar_wait(m_empty(ms), ((mc >> 1) & 1) ^ 1);
@@ -255,39 +311,11 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               __syncwarp();
               ++mc;
             }
-            for (int at = a0; at < a.atoms; ++at) {
-              for (int lk = 0; lk < a.kl; ++lk) {
-                if (a_load) {
-                  const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
-                  mbar_wait(a_empty(sa), (resident ? t_par : a_par_s) ^ 1);
-                  if (elect_one()) {
-                    if (leader) mbar_arrive_expect_tx(a_full(sa), a_bytes);
-                    else mbar_arrive_cluster(lead_a_full + 8u * sa);
-                    tma_load_2d_pair(a_slot(sa), &tmapA, at * kAtomK, a_row, lead_a_full + 8u * sa);
-                  }
-                  __syncwarp();
-                }
-                mbar_wait(b_empty(sb), b_par ^ 1);
-                if (elect_one()) {
-                  if (a.debug_flags & 1) {   // timing experiment: no B traffic at all (operands are stale shared memory)
-                    if (leader) mbar_arrive(b_full(sb)); else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                  } else {
-                  if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
-                  else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                  tma_load_2d_pair(b_slot(sb), &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
-                  }
-                  TRACE(3, 2, (hi ? 0 : a.nchunks) + c);
-                }
-                __syncwarp();
-                if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
-                if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
-              }
-            }
           }
         }
       }
     }
-  } else if (warp == kPairMmaWarp || warp == kPairMmaWarp + 1) {
+  } else if (warp == kPairMmaWarp) {
     // ===================== MMA issuers (leader CTA only): two warps, alternating chunks =====================
     // The whole warp runs the (uniform) control flow; one elected lane issues tcgen05.mma / commit.  A slice
     // holds 512 cycles of tensor work but costs one issuer ~600 cycles (mbarrier try_wait latency, ~85 SASS
@@ -298,7 +326,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     // second issuer is enabled only when a chunk has fewer slices than the B ring has stages (a.two_issuers):
     // then no issuer can wait on a stage two phases ahead of its oldest unconsumed use.
     if (leader) {
-      const uint32_t w = (uint32_t)(warp - kPairMmaWarp);
+      const uint32_t w = 0;
       const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.NC);
       const uint64_t desc_hi = make_smem_desc(0) & ~0x3FFFull;             // everything but the start address
       const uint32_t a_addr16 = (smem_base >> 4), b_addr16 = (smem_base + a.nA * kSlotBytes) >> 4;
@@ -330,9 +358,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           if (jn < nct) next_a0 = (jn >= a.nchunks) ? first_atom(a, 1, jn - a.nchunks) : 0;
           const uint32_t buf = cc & 1;
           const uint32_t my = cc >> 1;      // uses of this TMEM buffer so far
-          if (lane == 0) TRACE(1, 0, cc);
+          if (lane == 0) { if (w) TRACE(4, 0, cc); else TRACE(1, 0, cc); }
           mbar_wait(tempty_bar(buf), (my & 1) ^ 1);
-          if (lane == 0) TRACE(1, 1, cc);
+          if (lane == 0) { if (w) TRACE(4, 1, cc); else TRACE(1, 1, cc); }
           const uint32_t d_tmem = tmem_base + buf * kAccCols;
           uint32_t accumulate = 0;
           for (int at = a0; at < a.atoms; ++at) {
@@ -355,7 +383,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 if (last) umma_commit_pair(tfull_bar(buf));
               }
               __syncwarp();
-              if (lane == 0) TRACE(1, 5, cc);
+              if (lane == 0) { if (w) TRACE(4, 5, cc); else TRACE(1, 5, cc); }
               accumulate = 1;
               if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
               if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
@@ -498,20 +526,34 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           for (int u0 = sub * upw; u0 < (sub + 1) * upw; u0 += kPassUnits) {
             uint32_t res[kPassUnits * (MODE == DEC2 ? 4 : 8)];      // packed results of this pass
             uint32_t bres[kPassUnits * 4];                          // DEC1: lifted polynomial b (bytes)
+            // all accumulator reads of the pass first (one round trip), then hand the TMEM buffer back to the
+            // MMA issuers before any arithmetic: short hi chunks otherwise wait for this latency
+            uint32_t acc[kPassUnits][32];
+            {
+              uint32_t acc1[kPassUnits][32];
+#pragma unroll
+              for (int j = 0; j < kPassUnits; ++j) {
+                tmem_ld16(t_addr + (u0 + j) * 16, acc[j]);
+                if (MODE == ENC && a.nl == 2) tmem_ld16(t_addr + a.NCo + (u0 + j) * 16, acc1[j]);
+              }
+              tmem_ld_wait();
+              if (MODE == ENC && a.nl == 2) {
+#pragma unroll
+                for (int j = 0; j < kPassUnits; ++j)
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) acc[j][i] += acc1[j][i] << 8;
+              }
+            }
+            const bool last_pass = u0 + kPassUnits >= (sub + 1) * upw;
+            if (last_pass) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(lead(tempty_bar(buf)));
+            }
 #pragma unroll
             for (int j = 0; j < kPassUnits; ++j) {
               const int u = u0 + j;
-              uint32_t w[32];
-              tmem_ld16(t_addr + u * 16, w);
-              if (MODE == ENC && a.nl == 2) {
-                uint32_t w1[32];
-                tmem_ld16(t_addr + a.NCo + u * 16, w1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) w[i] += w1[i] << 8;
-              } else {
-                tmem_ld_wait();
-              }
+              uint32_t (&w)[32] = acc[j];
               if (MODE == ENC || MODE == DEC1) {
                 uint32_t *pk = res + 8 * j;
 #pragma unroll
@@ -558,14 +600,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 }
               }
             }
-            const bool last_pass = u0 + kPassUnits >= (sub + 1) * upw;
-            if (last_pass) {   // all TMEM reads (and message reads) of this chunk are done: release them early
-              tc_fence_before();
+            if (last_pass && MODE == ENC && !hi) {   // message tile no longer needed by this warp
               __syncwarp();
-              if (lane == 0) {
-                mbar_arrive_cluster(lead(tempty_bar(buf)));
-                if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));
-              }
+              if (lane == 0) mbar_arrive(m_empty(ms));
             }
             // the previous store must have finished reading the staging tile before it is overwritten
             if (store_pending) {

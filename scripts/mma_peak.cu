@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(128, 1) k_peak(int iters, unsigned long long *
 
 template <int KIND, int GROUP>
 void run(const char *name, int sms) {
-  const int iters = 4000;
+  const int iters = getenv("MMA_ITERS") ? atoi(getenv("MMA_ITERS")) : 4000;
   unsigned long long *cyc;
   cudaMalloc(&cyc, sizeof(unsigned long long) * sms);
   cudaMemset(cyc, 0, sizeof(unsigned long long) * sms);

@@ -15,13 +15,14 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "enc"
 g = dict(np.load(os.path.join(ROOT, "tests", "golden", "hps509.npz")))
 eng = nb.Engine(509, 3, 2048, 0)
 eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
-rows = 74 * 256 * 6
+rows = int(os.environ.get('TRACE_ROWS', 74 * 256 * 6))
 P = eng.pitch
 r = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); eng.sample_r_dev(rows, 169, 1, 0, r)
 m = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); m[:, :509] = torch.randint(0, 2, (rows, 509), device="cuda", dtype=torch.uint8)
 val = torch.empty((rows, P), dtype=torch.int16, device="cuda"); quo = torch.empty_like(val)
 out = torch.empty((rows, P), dtype=torch.uint8, device="cuda"); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)
-buf = np.zeros(3 * 1024, dtype=np.uint64)
+LANES, CAP = 4, 448
+buf = np.zeros(LANES * CAP, dtype=np.uint64)
 dump = eng.lib.ntru_debug_trace_dump
 dump.argtypes = [ctypes.c_void_p, ctypes.c_uint]
 for _ in range(2):
@@ -31,17 +32,22 @@ for _ in range(2):
         eng.decrypt_dev(rows, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2); eng.sync()
         n = dump(buf.ctypes.data, buf.size)
 recs = []
-for role in range(3):
-    for w in buf[role * 1024:(role + 1) * 1024]:
+for role in range(LANES):
+    for w in buf[role * CAP:(role + 1) * CAP]:
         w = int(w)
         if w == 0:
             continue
         tag, clk = w >> 40, w & 0xffffffffff
         recs.append((role + 1, tag >> 12, tag & 0xfff, clk))
+marks = {e: t for (role, e, idx, t) in recs if role == 3 and e in (10, 11, 12, 13)}
+if len(marks) == 4:
+    cyc, ns = marks[12] - marks[10], marks[13] - marks[11]
+    print(f"producer warp lifetime: {cyc} SM cycles in {ns} ns -> {cyc / ns * 1000:.0f} MHz")
+recs = [x for x in recs if not (x[0] == 3 and x[1] >= 10)]
 rec = np.array(recs, dtype=np.int64)
 rec[:, 3] -= rec[:, 3].min()
 rec = rec[np.argsort(rec[:, 3], kind="stable")]
-nm = {(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
+nm = {(4,0):"MMA1 chunk start",(4,1):"MMA1 got tempty",(4,5):"MMA1 issued",(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
       (2,0):"epi start",(2,1):"epi got tfull",(2,2):"epi done",(2,3):"epi unit0 loaded",(2,4):"epi unit0 math done",(2,6):"epi unit1 loaded",(2,7):"epi unit1 math done",(3,0):"prod wait b_empty",(3,1):"prod got b_empty",(3,2):"prod issued"}
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 19)
 prev = {}
