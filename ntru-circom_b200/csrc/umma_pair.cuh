@@ -367,7 +367,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             for (int lk = 0; lk < a.kl; ++lk) {
               const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
               mbar_wait(b_full(sb), b_par);
-              mbar_wait(a_full(sa), resident ? t_par : a_par_s);
+              if (!resident || j == 0) mbar_wait(a_full(sa), resident ? t_par : a_par_s);
               tc_fence_after();
               const uint64_t da = desc_hi | (uint64_t)((a_addr16 + sa * (kSlotBytes >> 4)) & 0x3FFF);
               const uint64_t db = desc_hi | (uint64_t)((b_addr16 + sb * (kSlotBytes >> 4)) & 0x3FFF);
