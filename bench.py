@@ -235,6 +235,26 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t.item())
     value_cts = world * B * args.steps / (ms * 1e-3)
 
+    # ---- secondary figures (outside the timed region above): value-only mode, encrypt-only, decrypt-only ----
+    def timed_ms(fn, iters=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(iters):
+            fn()
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        return a0.elapsed_time(a1) / iters
+
+    t_enc = timed_ms(lambda: eng.encrypt_dev(B, r, m, value=value, quotientE=quo))
+    t_dec = timed_ms(lambda: eng.decrypt_dev(B, value, value=out, quotient1=q1, remainder1=r1, quotient2=q2))
+    t_enc_v = timed_ms(lambda: eng.encrypt_dev(B, r, m, value=value))
+    t_dec_v = timed_ms(lambda: eng.decrypt_dev(B, value, value=out))
+    extras = {"encrypt_only_ct_per_s": B / (t_enc * 1e-3), "decrypt_only_ct_per_s": B / (t_dec * 1e-3),
+              "value_only_ct_per_s": B / ((t_enc_v + t_dec_v) * 1e-3), "value_only_ms": {"enc": t_enc_v, "dec": t_dec_v},
+              "value_only_GBps_7N": 7 * N * B / ((t_enc_v + t_dec_v) * 1e-3) / 1e9, "note": "per GPU, measured after the timed region"}
+
     # ---- end to end through the host-buffer ABI (pinned host memory, copies inside the timing) ----
     Be = min(args.e2e_rows, B)
     eng2 = nb.Engine(N, p, q, local_rank)
@@ -319,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD.format(rows=B), "rows_per_gpu": B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "inputs+outputs per step (7 GB at 1M rows) exceed the 126 MB L2; no flush needed",
                    "schedule": {0: "auto", 1: "cuda-core", 2: "tcgen05"}[args.path], "key": "tests/golden/hps509.npz"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extras": extras,
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(g)
