@@ -50,7 +50,8 @@ enum {
 
 /* ntru_set_option keys */
 enum {
-  NTRU_OPT_PATH = 1,        /* 0 auto, 1 force CUDA-core schedule, 2 force tcgen05 tensor schedule (same-key only) */
+  NTRU_OPT_PATH = 1,        /* 0 auto (same key: tcgen05, distinct keys: register-fragment IMMA), 1 force the fp32 CUDA-core
+                               schedule, 2 force the tcgen05 schedule (same-key only), 3 force the register-fragment schedule */
   NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
   NTRU_OPT_TIMING = 3,      /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
   NTRU_OPT_TENSOR_VARIANT = 4 /* tcgen05 schedule: 0 = CTA-pair kernel (cta_group::2, default), 1 = single-CTA kernel */
@@ -65,7 +66,9 @@ enum {
   NTRU_K_DEC_CORE = 4,      /* CUDA-core decrypt (both products) */
   NTRU_K_SUM = 5,           /* ciphertext column sum */
   NTRU_K_OTHER = 6,         /* sampler, finalize, key-matrix build */
-  NTRU_K_COUNT = 7
+  NTRU_K_ENC_IMMA = 7,      /* mma.sync (IMMA) encrypt, one warp per ciphertext: distinct keys */
+  NTRU_K_DEC_IMMA = 8,      /* mma.sync (IMMA) decrypt (both products) */
+  NTRU_K_COUNT = 9
 };
 
 /* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 32768], 8 <= N <= 1024. */
@@ -78,7 +81,7 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value);
 int ntru_pitch(const ntru_ctx *ctx);
 /* number of CUDA kernels this context has launched so far */
 uint64_t ntru_launch_count(const ntru_ctx *ctx);
-/* which schedule the last batch call used: 1 CUDA-core, 2 tcgen05 */
+/* which schedule the last batch call used: 1 CUDA-core (fp32 FMA), 2 tcgen05, 3 register-fragment IMMA */
 int ntru_last_path(const ntru_ctx *ctx);
 /* with NTRU_OPT_TIMING on: synchronises, then returns the summed device time (ms) and launch count of one
  * kernel kind since the last ntru_timing_reset */

@@ -6,14 +6,14 @@ reference, ``class NTRU``, and its named function exports are re-exported here.
 """
 from .ntru import NTRU
 from .engine import Engine, sampler_rand32
-from ._lib import NtruError, PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR
+from ._lib import NtruError, PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR, PATH_IMMA
 from .poly import (addPolynomials, bigintToBits, bitsToBigInt, bitsToString, degree, dividePolynomials,
                    expandArray, expandArrayToMultiple, extendedEuclideanAlgorithm, generateCustomArray,
                    modInverse, multiplyPolynomials, multiplyPolynomialsByScalar, packOutput, polyInv,
                    stringToBits, subtractPolynomials, trimPolynomial, unpackInput)
 
 __all__ = [
-    "NTRU", "Engine", "NtruError", "PATH_AUTO", "PATH_CUDA_CORE", "PATH_TENSOR", "sampler_rand32",
+    "NTRU", "Engine", "NtruError", "PATH_AUTO", "PATH_CUDA_CORE", "PATH_TENSOR", "PATH_IMMA", "sampler_rand32",
     "addPolynomials", "bigintToBits", "bitsToBigInt", "bitsToString", "degree", "dividePolynomials",
     "expandArray", "expandArrayToMultiple", "extendedEuclideanAlgorithm", "generateCustomArray",
     "modInverse", "multiplyPolynomials", "multiplyPolynomialsByScalar", "packOutput", "polyInv",

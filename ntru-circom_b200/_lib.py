@@ -16,8 +16,8 @@ NTRU_OK = 0
 NTRU_E_PARAM, NTRU_E_LENGTH, NTRU_E_NOKEY, NTRU_E_CUDA = -1, -2, -3, -4
 NTRU_E_NCCL, NTRU_E_NOMEM, NTRU_E_UNSUPPORTED = -5, -6, -7
 NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING, NTRU_OPT_TENSOR_VARIANT = 1, 2, 3, 4
-KERNEL_KINDS = ["enc_tensor", "dec1_tensor", "dec2_tensor", "enc_core", "dec_core", "sum", "other"]
-PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR = 0, 1, 2
+KERNEL_KINDS = ["enc_tensor", "dec1_tensor", "dec2_tensor", "enc_core", "dec_core", "sum", "other", "enc_imma", "dec_imma"]
+PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR, PATH_IMMA = 0, 1, 2, 3
 
 #: every symbol include/ntru_b200.h declares: name -> (restype, argtypes)
 _P = c_void_p

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libntru_b200.so")
-SOURCES = ["api.cu", "generic_kernels.cu", "umma_kernels.cu"]
+SOURCES = ["api.cu", "generic_kernels.cu", "imma_kernels.cu", "umma_kernels.cu"]
 HEADERS = ["ntru_internal.cuh", "umma_pair.cuh", os.path.join("..", "..", "include", "ntru_b200.h")]
 
 NVCC_FLAGS = [

@@ -127,10 +127,22 @@ void set_out(HostArr &a, void *p, size_t elem, size_t width) {
 
 bool want_tensor(ntru_ctx *ctx, bool same_key, bool ready, int *rc) {
   *rc = NTRU_OK;
-  if (ctx->opt_path == 1) return false;
+  if (ctx->opt_path == 1 || ctx->opt_path == 3) return false;
   const bool ok = same_key && ctx->tensor_ok && ready;
   if (ctx->opt_path == 2 && !ok) {
     *rc = fail(ctx, NTRU_E_UNSUPPORTED, "tensor schedule forced but not available for this call");
+    return false;
+  }
+  return ok;
+}
+
+// register-fragment (IMMA) schedule: the default whenever the tcgen05 same-key schedule does not apply
+bool want_imma(ntru_ctx *ctx, bool wide_message, int *rc) {
+  *rc = NTRU_OK;
+  if (ctx->opt_path == 1) return false;
+  const bool ok = ctx->tensor_ok && imma_supported(ctx) && !wide_message;
+  if (ctx->opt_path == 3 && !ok) {
+    *rc = fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment schedule forced but not available for this call");
     return false;
   }
   return ok;
@@ -144,6 +156,12 @@ int encrypt_dispatch(ntru_ctx *ctx, size_t B, const uint16_t *h_rows, const uint
   if (want_tensor(ctx, same_key && !m_wide, ctx->km_h.ready, &rc)) {
     ctx->last_path = 2;
     return umma_encrypt(ctx, B, r, (const uint8_t *)m, value, quo, rem);
+  }
+  if (rc != NTRU_OK) return rc;
+  if (want_imma(ctx, m_wide != 0, &rc)) {
+    ctx->last_path = 3;
+    return launch_encrypt_imma(ctx, B, same_key ? (const uint16_t *)ctx->d_h.ptr : h_rows, same_key ? 0 : (size_t)ctx->P, r,
+                               (const uint8_t *)m, value, quo, rem);
   }
   if (rc != NTRU_OK) return rc;
   ctx->last_path = 1;
@@ -160,6 +178,13 @@ int decrypt_dispatch(ntru_ctx *ctx, size_t B, const int8_t *f_rows, const uint8_
   if (want_tensor(ctx, same_key, ctx->km_f.ready && ctx->km_fp.ready, &rc)) {
     ctx->last_path = 2;
     return umma_decrypt(ctx, B, e, value, q1, r1, q2, r2);
+  }
+  if (rc != NTRU_OK) return rc;
+  if (want_imma(ctx, false, &rc)) {
+    ctx->last_path = 3;
+    return launch_decrypt_imma(ctx, B, same_key ? (const int8_t *)ctx->d_f.ptr : f_rows,
+                               same_key ? (const uint8_t *)ctx->d_fp.ptr : fp_rows, same_key ? 0 : (size_t)ctx->P, e, value, q1,
+                               r1, q2, r2);
   }
   if (rc != NTRU_OK) return rc;
   ctx->last_path = 1;
@@ -268,7 +293,7 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
   if (!ctx) return NTRU_E_PARAM;
   switch (key) {
     case NTRU_OPT_PATH:
-      if (value < 0 || value > 2) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_PATH must be 0, 1 or 2");
+      if (value < 0 || value > 3) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_PATH must be 0, 1, 2 or 3");
       ctx->opt_path = (int)value;
       return NTRU_OK;
     case NTRU_OPT_CHUNK_ROWS:

@@ -1,0 +1,424 @@
+// Register-fragment tensor schedule (mma.sync.m16n8k32, SASS IMMA.16832): ONE WARP PER CIPHERTEXT.
+//
+// Used for distinct-key batches: every row brings its own h (or f and fp), so nothing is shared between
+// ciphertexts and the 128-row operand tiles of tcgen05 do not apply.  The per-ciphertext linear product
+// c = lin(x, y) (multiplyPolynomials, index.js:319-355), x = the small polynomial (r, f or b; one byte), y = h, e
+// (two byte limbs) or fp, is cut into 16 x 16 Toeplitz blocks and evaluated as a small GEMM on the warp-level
+// tensor path (measured 570 TMAC/s on B200, scripts/imma_peak.cu; the fp32 FMA schedule it replaces ran at 17):
+//
+//     k = 16 K1 + k0,  i = 16 i1 + i0,  t = K1 - i1:      c[k] = sum_{t, i0} y[16 t + k0 - i0] * x[16 (K1 - t) + i0]
+//     D[k0][K1] = sum_{(t,i0)} A[k0][(t,i0)] * B[(t,i0)][K1]      A = Toeplitz(y) (16 rows),  B = Hankel blocks of x
+//
+// One mma.sync covers 16 outputs k0 x 8 blocks K1 x 32 positions (two t values).  The A fragment of a K step is
+// the same for every column block, so it is loaded once per step: 9 consecutive bytes of the REVERSED y limb
+// array per lane (three aligned LDS.32 + funnel shifts).  The B fragment is one aligned LDS.64 of the zero-padded
+// x array per (column block, step), shared by both limbs of y.  Blocks with K1 - t outside [0, ceil(N/16)) are
+// all zero and skipped (warp-uniform), which leaves 1.25 N^2 executed MACs per limb product.
+// Index maps (chosen so that every shared-memory access is aligned and the accumulator pairs pack into words):
+//     row m = g + 8 rh  <->  k0 = 2 g + rh          (g = lane / 4, t' = lane % 4)
+//     K slot (hf, t', j) <-> t = 2 s + (t' >> 1),  i0 = 8 (t' & 1) + 4 hf + j
+//     column n = g       <->  K1 = 8 jn + g
+// The full linear product (2N - 1 coefficients, mod 2^16) goes to a per-warp shared buffer; the output pass reads
+// lo[k] = c[k] and hi[k] = c[k + N] and applies the closed form of dividePolynomials(., 1 - x^N, .)
+// (index.js:358-401): remainder = lo + hi, quotient = -hi, then the message add (encrypt) or
+// the reference's lift (index.js:117) and the second product (decrypt).  All global accesses are 16-byte vectors
+// of the packed uint16 / byte rows.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ntru_internal.cuh"
+
+namespace ntru {
+
+namespace {
+
+constexpr int kImmaWarps = 4;      // warps (= ciphertexts in flight) per CTA
+constexpr int kXPad = 112;         // zero bytes in front of x: block index K1 - t reaches -7
+
+struct ImmaGeom {
+  int N, P, q, logq;
+  uint32_t qmask;
+  int I1;            // 16-blocks of x: ceil(N / 16)
+  int S;             // K steps (two t values each): t = 0 .. floor((N + 14) / 16)
+  int NJ;            // 8-column blocks: ceil(ceil((2N - 1) / 16) / 8)
+  int Z;             // reversed limb arrays: yrev[z] = y[Z - z]
+  int Ly, Lx, Lc;    // bytes of one limb array, of the padded x array, of the product buffer
+  int warp_bytes;
+};
+
+__device__ __forceinline__ void imma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t mod3_16(uint32_t v) {   // v < 65536
+  return v - 3u * ((v * 0xAAABu) >> 17);
+}
+
+// acc[jn][l] += Toeplitz(y limb l) x Hankel(x) for every non-zero block; acc starts at zero.
+template <int NJ, int LIMBS>
+__device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, const uint8_t *y1, const uint8_t *xb, int lane,
+                                          int (&acc)[NJ][LIMBS][4]) {
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int jn = 0; jn < NJ; ++jn)
+#pragma unroll
+    for (int l = 0; l < LIMBS; ++l) acc[jn][l][0] = acc[jn][l][1] = acc[jn][l][2] = acc[jn][l][3] = 0;
+  // A fragment: bytes z0-1 .. z0+7 of the reversed array, z0 = Z - 32 s - 16 (t'>>1) - 2 g + 8 (t'&1):
+  // a1 = [z0-1, z0+3)  a0 = [z0, z0+4)  a3 = [z0+3, z0+7)  a2 = [z0+4, z0+8)
+  const int zfirst = G.Z - 16 * (tq >> 1) - 2 * g + 8 * (tq & 1) - 1;
+  const int zb = zfirst & ~3;
+  const uint32_t sh0 = 8u * (uint32_t)(zfirst - zb), sh1 = sh0 + 8u;
+  const uint8_t *pa0 = y0 + zb, *pa1 = y1 + zb;
+  const uint8_t *pb = xb + kXPad + 16 * (g - (tq >> 1)) + 8 * (tq & 1);
+  for (int s = 0; s < G.S; ++s) {
+    uint32_t a[LIMBS][4];
+    {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(pa0 - 32 * s);
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      a[0][0] = __funnelshift_rc(w0, w1, sh1);
+      a[0][1] = __funnelshift_r(w0, w1, sh0);
+      a[0][2] = __funnelshift_rc(w1, w2, sh1);
+      a[0][3] = __funnelshift_r(w1, w2, sh0);
+    }
+    if (LIMBS == 2) {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(pa1 - 32 * s);
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      a[LIMBS - 1][0] = __funnelshift_rc(w0, w1, sh1);
+      a[LIMBS - 1][1] = __funnelshift_r(w0, w1, sh0);
+      a[LIMBS - 1][2] = __funnelshift_rc(w1, w2, sh1);
+      a[LIMBS - 1][3] = __funnelshift_r(w1, w2, sh0);
+    }
+    // column blocks with some K1 - t in [0, I1):  8 jn + 7 - 2 s >= 0  and  8 jn - 2 s - 1 <= I1 - 1
+    const int jlo = s >> 2;
+    int jhi = (2 * s + G.I1) >> 3;
+    jhi = jhi < G.NJ - 1 ? jhi : G.NJ - 1;
+    const uint8_t *pbs = pb - 32 * s;
+#pragma unroll
+    for (int jn = 0; jn < NJ; ++jn) {
+      if (jn >= jlo && jn <= jhi) {
+        const uint2 b = *reinterpret_cast<const uint2 *>(pbs + 128 * jn);
+        imma_u8s8(acc[jn][0], a[0], b.x, b.y);
+        if (LIMBS == 2) imma_u8s8(acc[jn][LIMBS - 1], a[LIMBS - 1], b.x, b.y);
+      }
+    }
+  }
+}
+
+// accumulators -> product buffer: cbuf[k] = c[k] mod 2^16, k = 16 (8 jn + 2 t' + {0,1}) + 2 g + {0,1}
+template <int NJ, int LIMBS>
+__device__ __forceinline__ void store_product(const ImmaGeom &G, int lane, const int (&acc)[NJ][LIMBS][4], uint16_t *cbuf) {
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t *dst = reinterpret_cast<uint32_t *>(cbuf) + 16 * tq + g;      // u16 index 32 t' + 2 g
+#pragma unroll
+  for (int jn = 0; jn < NJ; ++jn) {
+    if (jn < G.NJ) {
+      uint32_t v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t x = (uint32_t)acc[jn][0][i];
+        if (LIMBS == 2) x += (uint32_t)acc[jn][LIMBS - 1][i] << 8;
+        v[i] = x;
+      }
+      dst[64 * jn] = __byte_perm(v[0], v[2], 0x5410);          // (K1 = 8 jn + 2 t'    ; k0 = 2 g, 2 g + 1)
+      dst[64 * jn + 8] = __byte_perm(v[1], v[3], 0x5410);      // (K1 = 8 jn + 2 t' + 1; k0 = 2 g, 2 g + 1)
+    }
+  }
+}
+
+// y (uint16, mod q) -> reversed byte-limb arrays: yrev_l[Z - j] = limb l of y[j]
+template <int LIMBS>
+__device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__restrict__ src, uint8_t *y0, uint8_t *y1, int lane) {
+  for (int j0 = 8 * lane; j0 < G.N; j0 += 256) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+    const int nv = G.N - j0;                                     // valid coefficients in this vector
+    if (nv < 8) {
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = 2 * i + 1 < nv ? w[i] : (2 * i < nv ? (w[i] & 0xffffu) : 0u);
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    const int z = G.Z - j0 - 7;                                  // multiple of 8
+    *reinterpret_cast<uint2 *>(y0 + z) = make_uint2(__byte_perm(v.w, v.z, 0x4602), __byte_perm(v.y, v.x, 0x4602));
+    if (LIMBS == 2) *reinterpret_cast<uint2 *>(y1 + z) = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
+  }
+}
+
+// y (bytes) -> reversed array
+__device__ __forceinline__ void stage_y8(const ImmaGeom &G, const uint8_t *__restrict__ src, uint8_t *y0, int lane) {
+  for (int j0 = 16 * lane; j0 < G.N; j0 += 512) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+    const int nv = G.N - j0;
+    if (nv < 16) {
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nb = nv - 4 * i;
+        w[i] = nb >= 4 ? w[i] : (nb <= 0 ? 0u : (w[i] & (0xffffffffu >> (8 * (4 - nb)))));
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4 *>(y0 + (G.Z - j0 - 15)) =
+        make_uint4(__byte_perm(v.w, 0u, 0x0123), __byte_perm(v.z, 0u, 0x0123), __byte_perm(v.y, 0u, 0x0123), __byte_perm(v.x, 0u, 0x0123));
+  }
+}
+
+// x (bytes) -> zero-padded array
+__device__ __forceinline__ void stage_x8(const ImmaGeom &G, const uint8_t *__restrict__ src, uint8_t *xb, int lane) {
+  for (int j0 = 16 * lane; j0 < G.N; j0 += 512) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+    const int nv = G.N - j0;
+    if (nv < 16) {
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nb = nv - 4 * i;
+        w[i] = nb >= 4 ? w[i] : (nb <= 0 ? 0u : (w[i] & (0xffffffffu >> (8 * (4 - nb)))));
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4 *>(xb + kXPad + j0) = v;
+  }
+}
+
+// lo = c[k0 .. k0+8), hi = c[k0+N .. k0+N+8) as packed uint16 pairs
+__device__ __forceinline__ void load_lo_hi(const ImmaGeom &G, const uint16_t *cbuf, int k0, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
+  const uint4 l = *reinterpret_cast<const uint4 *>(cbuf + k0);
+  lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; lo[3] = l.w;
+  const int kh = k0 + G.N;
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(cbuf + (kh & ~1));
+  const uint32_t sh = (kh & 1) ? 16u : 0u;
+  uint32_t x[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) x[i] = w[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hi[i] = __funnelshift_r(x[i], x[i + 1], sh);
+}
+
+// keeps the first nv (of 8) packed uint16 lanes
+__device__ __forceinline__ void mask_lanes(uint32_t (&v)[4], int nv) {
+  if (nv >= 8) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = 2 * i + 1 < nv ? v[i] : (2 * i < nv ? (v[i] & 0xffffu) : 0u);
+}
+
+struct ImmaEncArgs {
+  ImmaGeom G;
+  size_t B;
+  const uint16_t *h;
+  size_t h_stride;
+  const uint8_t *r;
+  const uint8_t *m;
+  uint16_t *value, *quo, *rem;
+};
+
+template <int NJ, int LIMBS>
+__global__ void __launch_bounds__(kImmaWarps * 32) k_encrypt_imma(const ImmaEncArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const ImmaGeom &G = a.G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
+  uint8_t *y0 = base, *y1 = base + G.Ly, *xb = base + 2 * G.Ly;
+  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 2 * G.Ly + G.Lx);
+  for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const uint32_t Q2 = G.qmask | (G.qmask << 16);
+  const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
+  for (size_t row = (size_t)blockIdx.x * kImmaWarps + warp; row < a.B; row += nwarps) {
+    stage_y16<LIMBS>(G, a.h + row * a.h_stride, y0, y1, lane);
+    stage_x8(G, a.r + row * (size_t)G.P, xb, lane);
+    __syncwarp();
+    {
+      int acc[NJ][LIMBS][4];
+      conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
+      store_product<NJ, LIMBS>(G, lane, acc, cbuf);
+    }
+    __syncwarp();
+    const size_t rbase = row * (size_t)G.P;
+    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+      uint32_t lo[4], hi[4], rem[4], quo[4];
+      load_lo_hi(G, cbuf, k0, lo, hi);
+      const uint2 mm = __ldg(reinterpret_cast<const uint2 *>(a.m + rbase + k0));
+      const uint32_t mp[4] = {__byte_perm(mm.x, 0u, 0x4140), __byte_perm(mm.x, 0u, 0x4342), __byte_perm(mm.y, 0u, 0x4140),
+                              __byte_perm(mm.y, 0u, 0x4342)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rem[i] = ((lo[i] & Q2) + (hi[i] & Q2) + mp[i]) & Q2;
+        quo[i] = ((~hi[i] & Q2) + 0x00010001u) & Q2;
+      }
+      mask_lanes(rem, G.N - k0);
+      mask_lanes(quo, G.N - k0);
+      const uint4 rv = make_uint4(rem[0], rem[1], rem[2], rem[3]);
+      if (a.value) *reinterpret_cast<uint4 *>(a.value + rbase + k0) = rv;
+      if (a.rem) *reinterpret_cast<uint4 *>(a.rem + rbase + k0) = rv;
+      if (a.quo) *reinterpret_cast<uint4 *>(a.quo + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
+    }
+    __syncwarp();
+  }
+}
+
+struct ImmaDecArgs {
+  ImmaGeom G;
+  size_t B;
+  const int8_t *f;
+  const uint8_t *fp;
+  size_t key_stride;
+  const uint16_t *e;
+  uint8_t *value, *q2, *r2;
+  uint16_t *q1, *r1;
+};
+
+template <int NJ, int LIMBS>
+__global__ void __launch_bounds__(kImmaWarps * 32) k_decrypt_imma(const ImmaDecArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const ImmaGeom &G = a.G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
+  uint8_t *y0 = base, *y1 = base + G.Ly, *y2 = base + 2 * G.Ly, *xb = base + 3 * G.Ly;
+  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 3 * G.Ly + G.Lx);
+  for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const uint32_t Q2 = G.qmask | (G.qmask << 16);
+  const uint32_t LA2 = (((uint32_t)G.q >> 1) - 1u) * 0x00010001u;       // x > q/2  <=>  bit logq of x + q/2 - 1
+  const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
+  for (size_t row = (size_t)blockIdx.x * kImmaWarps + warp; row < a.B; row += nwarps) {
+    const size_t rbase = row * (size_t)G.P;
+    stage_y16<LIMBS>(G, a.e + rbase, y0, y1, lane);
+    stage_y8(G, a.fp + row * a.key_stride, y2, lane);
+    stage_x8(G, reinterpret_cast<const uint8_t *>(a.f) + row * a.key_stride, xb, lane);
+    __syncwarp();
+    {   // product 1: a = lin(f, e) mod q
+      int acc[NJ][LIMBS][4];
+      conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
+      store_product<NJ, LIMBS>(G, lane, acc, cbuf);
+    }
+    __syncwarp();
+    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+      uint32_t lo[4], hi[4], rem[4], quo[4];
+      load_lo_hi(G, cbuf, k0, lo, hi);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rem[i] = ((lo[i] & Q2) + (hi[i] & Q2)) & Q2;
+        quo[i] = ((~hi[i] & Q2) + 0x00010001u) & Q2;
+      }
+      mask_lanes(rem, G.N - k0);
+      mask_lanes(quo, G.N - k0);
+      if (a.r1) *reinterpret_cast<uint4 *>(a.r1 + rbase + k0) = make_uint4(rem[0], rem[1], rem[2], rem[3]);
+      if (a.q1) *reinterpret_cast<uint4 *>(a.q1 + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
+      // b = (remainder1 + [remainder1 > q/2]) mod 3  (index.js:117), the multiplier of product 2
+      uint32_t bw[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t p0 = rem[2 * i] + (((rem[2 * i] + LA2) >> G.logq) & 0x00010001u);
+        const uint32_t p1 = rem[2 * i + 1] + (((rem[2 * i + 1] + LA2) >> G.logq) & 0x00010001u);
+        bw[i] = mod3_16(p0 & 0xffffu) | (mod3_16(p0 >> 16) << 8) | (mod3_16(p1 & 0xffffu) << 16) | (mod3_16(p1 >> 16) << 24);
+      }
+      *reinterpret_cast<uint2 *>(xb + kXPad + k0) = make_uint2(bw[0], bw[1]);
+    }
+    __syncwarp();
+    {   // product 2: c = lin(fp, b) mod 3
+      int acc[NJ][1][4];
+      conv_imma<NJ, 1>(G, y2, y2, xb, lane, acc);
+      store_product<NJ, 1>(G, lane, acc, cbuf);
+    }
+    __syncwarp();
+    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+      uint32_t lo[4], hi[4];
+      load_lo_hi(G, cbuf, k0, lo, hi);
+      uint32_t rem[2] = {0, 0}, quo[2] = {0, 0};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t l3 = mod3_16((lo[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        const uint32_t h3 = mod3_16((hi[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        const bool in = k0 + i < G.N;
+        const uint32_t rr = in ? mod3_16(l3 + h3) : 0u;
+        const uint32_t qq = in ? mod3_16(3u - h3) : 0u;
+        rem[i >> 2] |= rr << (8 * (i & 3));
+        quo[i >> 2] |= qq << (8 * (i & 3));
+      }
+      const uint2 rv = make_uint2(rem[0], rem[1]);
+      if (a.value) *reinterpret_cast<uint2 *>(a.value + rbase + k0) = rv;
+      if (a.r2) *reinterpret_cast<uint2 *>(a.r2 + rbase + k0) = rv;
+      if (a.q2) *reinterpret_cast<uint2 *>(a.q2 + rbase + k0) = make_uint2(quo[0], quo[1]);
+    }
+    __syncwarp();
+  }
+}
+
+ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays) {
+  ImmaGeom G;
+  G.N = ctx->N; G.P = ctx->P; G.q = ctx->q; G.logq = ctx->logq; G.qmask = (uint32_t)ctx->q - 1;
+  G.I1 = (G.N + 15) / 16;
+  const int tmax = (G.N + 14) / 16;
+  G.S = tmax / 2 + 1;
+  G.NJ = ((2 * G.N - 1 + 15) / 16 + 7) / 8;
+  G.Z = 32 * G.S + 15;
+  G.Ly = 32 * G.S + 48;
+  G.Lx = 16 * (G.I1 + 15);
+  G.Lc = 2 * (128 * G.NJ + 32);
+  G.warp_bytes = ylimb_arrays * G.Ly + G.Lx + G.Lc;
+  return G;
+}
+
+template <class K, class A>
+int launch_imma(ntru_ctx *ctx, K kernel, const A &args, int kind, size_t B, int regs_hint) {
+  const size_t smem = (size_t)kImmaWarps * args.G.warp_bytes;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(imma)");
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kImmaWarps * 32, smem);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(imma)");
+  if (per_sm < 1) per_sm = 1;
+  (void)regs_hint;
+  const size_t want = (B + kImmaWarps - 1) / kImmaWarps;
+  const size_t cap = (size_t)ctx->sm_count * per_sm;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  {
+    LaunchTimer timer(ctx, kind);
+    kernel<<<grid, kImmaWarps * 32, smem, ctx->stream>>>(args);
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+}  // namespace
+
+bool imma_supported(const ntru_ctx *ctx) {
+  // 13 column blocks of accumulators (104 registers for two limbs) is the largest instantiation: N <= 832
+  return ((2 * ctx->N - 1 + 15) / 16 + 7) / 8 <= 13 && ctx->q <= 65536;
+}
+
+#define NTRU_IMMA_DISPATCH(KERNEL, ARGS, KIND)                                                        \
+  do {                                                                                                \
+    const int nj = (ARGS).G.NJ;                                                                       \
+    const bool two = ctx->q > 256;                                                                    \
+    if (nj <= 3) return two ? launch_imma(ctx, KERNEL<3, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<3, 1>, ARGS, KIND, B, 0);   \
+    if (nj <= 8) return two ? launch_imma(ctx, KERNEL<8, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<8, 1>, ARGS, KIND, B, 0);   \
+    if (nj <= 11) return two ? launch_imma(ctx, KERNEL<11, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<11, 1>, ARGS, KIND, B, 0); \
+    return two ? launch_imma(ctx, KERNEL<13, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<13, 1>, ARGS, KIND, B, 0);              \
+  } while (0)
+
+int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r, const uint8_t *m,
+                        uint16_t *value, uint16_t *quo, uint16_t *rem) {
+  if (B == 0) return NTRU_OK;
+  if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
+  ImmaEncArgs a;
+  a.G = make_geom(ctx, 2);
+  a.B = B; a.h = h; a.h_stride = h_stride; a.r = r; a.m = m; a.value = value; a.quo = quo; a.rem = rem;
+  NTRU_IMMA_DISPATCH(k_encrypt_imma, a, NTRU_K_ENC_IMMA);
+}
+
+int launch_decrypt_imma(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, size_t key_stride, const uint16_t *e,
+                        uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2) {
+  if (B == 0) return NTRU_OK;
+  if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
+  ImmaDecArgs a;
+  a.G = make_geom(ctx, 3);
+  a.B = B; a.f = f; a.fp = fp; a.key_stride = key_stride; a.e = e;
+  a.value = value; a.q1 = q1; a.r1 = r1; a.q2 = q2; a.r2 = r2;
+  NTRU_IMMA_DISPATCH(k_decrypt_imma, a, NTRU_K_DEC_IMMA);
+}
+
+}  // namespace ntru

@@ -107,6 +107,13 @@ int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
 int launch_repitch(ntru_ctx *ctx, const void *src, void *dst, size_t rows, int width, int elem, bool to_pitched);
 
+// ---- register-fragment tensor schedule (imma_kernels.cu): one warp per ciphertext, distinct keys ----
+bool imma_supported(const ntru_ctx *ctx);
+int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r, const uint8_t *m,
+                        uint16_t *value, uint16_t *quo, uint16_t *rem);
+int launch_decrypt_imma(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, size_t key_stride, const uint16_t *e,
+                        uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2);
+
 // ---- tcgen05 schedule (umma_kernels.cu) ----
 int umma_init(ntru_ctx *ctx);                    // probes the device, sets ctx->tensor_ok
 int umma_prepare_public(ntru_ctx *ctx);          // builds km_h from d_h

@@ -48,8 +48,9 @@ def same_key(cfg, B):
     eng.close()
 
 
-def distinct_key(cfg, B):
+def distinct_key(cfg, B, path=0):
     g, eng, N, q, dr = setup(cfg)
+    eng.set_path(path)
     P = eng.pitch
     h = torch.zeros((B, P), dtype=torch.int16, device=dev); h[:, :N] = torch.randint(0, q, (B, N), device=dev, dtype=torch.int16)
     f = torch.zeros((B, P), dtype=torch.int8, device=dev); f[:, :N] = torch.randint(-1, 2, (B, N), device=dev, dtype=torch.int8)
@@ -61,7 +62,16 @@ def distinct_key(cfg, B):
     t_enc = timed(lambda: eng.encrypt_dev(B, r, m, value=val, quotientE=quo, h_rows=h), iters=3, warm=1)
     t_dec = timed(lambda: eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2, f_rows=f, fp_rows=fp), iters=3, warm=1)
     tot = t_enc + t_dec
-    print(json.dumps({"config": cfg, "mode": "distinct-key CUDA-core", "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
+    # the decrypted plaintext is compared with the fp32 CUDA-core schedule on a prefix (oracle parity is tests/)
+    nchk = min(B, 4096)
+    eng.set_path(1)
+    val2 = torch.empty((nchk, P), dtype=torch.int16, device=dev); out2 = torch.empty((nchk, P), dtype=torch.uint8, device=dev)
+    eng.encrypt_dev(nchk, r[:nchk], m[:nchk], value=val2, h_rows=h[:nchk])
+    eng.decrypt_dev(nchk, val2, value=out2, f_rows=f[:nchk], fp_rows=fp[:nchk])
+    torch.cuda.synchronize()
+    same = bool(torch.equal(val2[:, :N], val[:nchk, :N]) and torch.equal(out2[:, :N], out[:nchk, :N]))
+    print(json.dumps({"config": cfg, "mode": "distinct-key " + {0: "auto", 1: "CUDA-core fp32", 3: "IMMA"}[path], "rows": B, "last_path": eng.last_path,
+                      "matches_cuda_core_schedule": same, "TMAC_per_s_3N2": 3 * N * N * B / (tot * 1e-3) / 1e12, "enc_ms": t_enc, "dec_ms": t_dec,
                       "ct_per_s": B / (tot * 1e-3), "GBps_18N": 18 * N * B / (tot * 1e-3) / 1e9, "frac_hbm": 18 * N * B / (tot * 1e-3) / 1e9 / HBM,
                       "GFMA_per_s": 3 * N * N * B / (tot * 1e-3) / 1e9}))
     eng.close()
@@ -89,6 +99,10 @@ which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
 if "c1" in which: same_key("default167", 1 << 20)
 if "c2" in which: same_key("hps509", 1 << 20)
 if "c3" in which: distinct_key("hps677", 1 << 18)
+if "c3core" in which: distinct_key("hps677", 1 << 16, 1)
+if "c3_509" in which: distinct_key("hps509", 1 << 18)
+if "c3_821" in which: distinct_key("hps821", 1 << 18)
+if "c3_167" in which: distinct_key("default167", 1 << 20)
 if "c3s" in which: same_key("hps677", 1 << 20)
 if "c4" in which: same_key("hps821", 1 << 20)
 if "c5" in which: sum_rows("hrss701", 10_000_000)

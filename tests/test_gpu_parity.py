@@ -37,15 +37,17 @@ def engines(nb, golden):
 
 
 def _paths(nb, eng):
-    """Schedules to test: the CUDA-core one always, the tcgen05 one when the library built it."""
+    """Schedules to test: the fp32 CUDA-core one always, the two tensor schedules (register-fragment IMMA, tcgen05)
+    when the device supports them."""
     out = [nb.PATH_CUDA_CORE]
-    try:
-        eng.set_path(nb.PATH_TENSOR)
-        g = np.zeros((1, eng.N), dtype=np.uint8)
-        eng.encrypt_batch(g, g, witness=False)
-        out.append(nb.PATH_TENSOR)
-    except nb.NtruError:
-        pass
+    for path in (nb.PATH_IMMA, nb.PATH_TENSOR):
+        try:
+            eng.set_path(path)
+            g = np.zeros((1, eng.N), dtype=np.uint8)
+            eng.encrypt_batch(g, g, witness=False)
+            out.append(path)
+        except nb.NtruError:
+            pass
     eng.set_path(nb.PATH_AUTO)
     return out
 
@@ -98,14 +100,17 @@ def test_random_batch_vs_oracle(cfg, nb, engines, golden):
         assert np.array_equal(want_d["value"][6:], m[6:])   # tiny17 (q=32) has genuine decryption failures
 
 
-@pytest.mark.parametrize("cfg", ["default167", "hps677"])
+@pytest.mark.parametrize("cfg", CFGS)
 def test_distinct_keys(cfg, nb, engines, golden):
-    """Config 3: a different key per row (CUDA-core schedule), full witness; 8 valid keys + random ones."""
+    """Config 3: a different key per row, full witness; valid keys + random ones (incl. extreme coefficients), on the
+    register-fragment IMMA schedule (the default for distinct keys) and on the fp32 CUDA-core schedule."""
     g, eng = golden(cfg), engines(cfg)
     N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
-    keys = [o.make_key(cfg, 100 + i) for i in range(8)]
+    nvalid = 8
+    keys = [o.make_key(cfg, 100 + i) for i in range(nvalid)]
+    keys += [keys[-1]] * (8 - nvalid)
     rng = np.random.default_rng(5)
-    B = 8 + 40
+    B = 8 + 131
     h = np.zeros((B, N), dtype=np.int64)
     f = np.zeros((B, N), dtype=np.int64)
     fp = np.zeros((B, N), dtype=np.int64)
@@ -114,18 +119,31 @@ def test_distinct_keys(cfg, nb, engines, golden):
     h[8:] = rng.integers(0, q, size=(B - 8, N))
     f[8:] = o.sample_ternary_rows(B - 8, N, dr, dr - 1, rng, neg_value=-1)
     fp[8:] = rng.integers(0, p, size=(B - 8, N))
+    h[9], f[9], fp[9] = q - 1, 1, p - 1                      # largest possible accumulators
+    f[10] = -1
+    h[11], f[11], fp[11] = 0, 0, 0
     r = o.sample_ternary_rows(B, N, dr, dr, rng)
+    r[9] = 2
     m = rng.integers(0, 2, size=(B, N))
+    m[9] = 255
     want_e = o.encrypt_batch(h, r, m, q)
-    enc = eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8), h=h.astype(np.uint16))
-    assert eng.last_path == nb.PATH_CUDA_CORE
-    for k in ENC_KEYS:
-        assert np.array_equal(enc[k], want_e[k]), k
     want_d = o.decrypt_batch(f, fp, want_e["value"], q, p)
-    dec = eng.decrypt_batch(enc["value"], f=f.astype(np.int8), fp=fp.astype(np.uint8))
-    for k in DEC_KEYS:
-        assert np.array_equal(dec[k], want_d[k]), k
-    assert np.array_equal(dec["value"][:8], m[:8])           # valid keys round-trip (q % 3 == 2 here)
+    for path in (nb.PATH_AUTO, nb.PATH_IMMA, nb.PATH_CUDA_CORE):
+        eng.set_path(path)
+        enc = eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8), h=h.astype(np.uint16))
+        assert eng.last_path == (nb.PATH_CUDA_CORE if path == nb.PATH_CUDA_CORE else nb.PATH_IMMA)
+        for k in ENC_KEYS:
+            assert np.array_equal(enc[k], want_e[k]), (path, k)
+        dec = eng.decrypt_batch(enc["value"], f=f.astype(np.int8), fp=fp.astype(np.uint8))
+        for k in DEC_KEYS:
+            assert np.array_equal(dec[k], want_d[k]), (path, k)
+        assert np.array_equal(eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8), h=h.astype(np.uint16), witness=False)["value"],
+                              want_e["value"])
+        assert np.array_equal(eng.decrypt_batch(enc["value"], f=f.astype(np.int8), fp=fp.astype(np.uint8), witness=False)["value"],
+                              want_d["value"])
+    eng.set_path(nb.PATH_AUTO)
+    if q % 3 == 2 and cfg != "tiny17":
+        assert np.array_equal(want_d["value"][:nvalid], m[:nvalid])   # valid keys round-trip
 
 
 def test_empty_batch_and_errors(nb, engines):
