@@ -44,6 +44,7 @@ struct ImmaGeom {
   int NJ;            // 8-column blocks: ceil(ceil((2N - 1) / 16) / 8)
   int Z;             // reversed limb arrays: yrev[z] = y[Z - z]
   int Ly, Lx, Lc;    // bytes of one limb array, of the padded x array, of the product buffer
+  int Lraw;          // bytes of the prefetch area: the next row's inputs as they lie in global memory (4 P)
   int warp_bytes;
 };
 
@@ -57,7 +58,16 @@ __device__ __forceinline__ uint32_t mod3_16(uint32_t v) {   // v < 65536
   return v - 3u * ((v * 0xAAABu) >> 17);
 }
 
-// acc[jn][l] += Toeplitz(y limb l) x Hankel(x) for every non-zero block; acc starts at zero.
+// Column blocks visited per K step: jn = (s >> 2) + d, d = 0 .. kDMax.  Some K1 - t of block (jn, s) lies in [0, I1)
+// iff  s >> 2 <= jn <= (2 s + I1) >> 3; with I1 <= 4 NJ that is d <= (6 + 4 NJ) >> 3.  The few visited blocks outside
+// the exact range multiply zero padding (about 10 % extra MMAs) and buy a loop body without branches.
+template <int NJ> struct ImmaShape {
+  static constexpr int kDMax = (6 + 4 * NJ) >> 3;
+  static constexpr int kSGroups = (2 * NJ + 1 + 3) / 4;     // S <= 2 NJ + 1 K steps, four per group
+};
+
+// acc[jn][l] = Toeplitz(y limb l) x Hankel(x).  Fully unrolled over (s, jn): every shared-memory address is
+// base register + immediate and the accumulator index is static.
 template <int NJ, int LIMBS>
 __device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, const uint8_t *y1, const uint8_t *xb, int lane,
                                           int (&acc)[NJ][LIMBS][4]) {
@@ -73,35 +83,38 @@ __device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, 
   const uint32_t sh0 = 8u * (uint32_t)(zfirst - zb), sh1 = sh0 + 8u;
   const uint8_t *pa0 = y0 + zb, *pa1 = y1 + zb;
   const uint8_t *pb = xb + kXPad + 16 * (g - (tq >> 1)) + 8 * (tq & 1);
-  for (int s = 0; s < G.S; ++s) {
-    uint32_t a[LIMBS][4];
-    {
-      const uint32_t *w = reinterpret_cast<const uint32_t *>(pa0 - 32 * s);
-      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-      a[0][0] = __funnelshift_rc(w0, w1, sh1);
-      a[0][1] = __funnelshift_r(w0, w1, sh0);
-      a[0][2] = __funnelshift_rc(w1, w2, sh1);
-      a[0][3] = __funnelshift_r(w1, w2, sh0);
-    }
-    if (LIMBS == 2) {
-      const uint32_t *w = reinterpret_cast<const uint32_t *>(pa1 - 32 * s);
-      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-      a[LIMBS - 1][0] = __funnelshift_rc(w0, w1, sh1);
-      a[LIMBS - 1][1] = __funnelshift_r(w0, w1, sh0);
-      a[LIMBS - 1][2] = __funnelshift_rc(w1, w2, sh1);
-      a[LIMBS - 1][3] = __funnelshift_r(w1, w2, sh0);
-    }
-    // column blocks with some K1 - t in [0, I1):  8 jn + 7 - 2 s >= 0  and  8 jn - 2 s - 1 <= I1 - 1
-    const int jlo = s >> 2;
-    int jhi = (2 * s + G.I1) >> 3;
-    jhi = jhi < G.NJ - 1 ? jhi : G.NJ - 1;
-    const uint8_t *pbs = pb - 32 * s;
 #pragma unroll
-    for (int jn = 0; jn < NJ; ++jn) {
-      if (jn >= jlo && jn <= jhi) {
-        const uint2 b = *reinterpret_cast<const uint2 *>(pbs + 128 * jn);
-        imma_u8s8(acc[jn][0], a[0], b.x, b.y);
-        if (LIMBS == 2) imma_u8s8(acc[jn][LIMBS - 1], a[LIMBS - 1], b.x, b.y);
+  for (int sg = 0; sg < ImmaShape<NJ>::kSGroups; ++sg) {
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int s = 4 * sg + s4;
+      if (s < G.S) {
+        uint32_t a[LIMBS][4];
+        {
+          const uint32_t *w = reinterpret_cast<const uint32_t *>(pa0 - 32 * s);
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+          a[0][0] = __funnelshift_rc(w0, w1, sh1);
+          a[0][1] = __funnelshift_r(w0, w1, sh0);
+          a[0][2] = __funnelshift_rc(w1, w2, sh1);
+          a[0][3] = __funnelshift_r(w1, w2, sh0);
+        }
+        if (LIMBS == 2) {
+          const uint32_t *w = reinterpret_cast<const uint32_t *>(pa1 - 32 * s);
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+          a[LIMBS - 1][0] = __funnelshift_rc(w0, w1, sh1);
+          a[LIMBS - 1][1] = __funnelshift_r(w0, w1, sh0);
+          a[LIMBS - 1][2] = __funnelshift_rc(w1, w2, sh1);
+          a[LIMBS - 1][3] = __funnelshift_r(w1, w2, sh0);
+        }
+#pragma unroll
+        for (int d = 0; d <= ImmaShape<NJ>::kDMax; ++d) {
+          const int jn = sg + d;
+          if (jn < NJ) {
+            const uint2 b = *reinterpret_cast<const uint2 *>(pb + 128 * jn - 32 * s);
+            imma_u8s8(acc[jn][0], a[0], b.x, b.y);
+            if (LIMBS == 2) imma_u8s8(acc[jn][LIMBS - 1], a[LIMBS - 1], b.x, b.y);
+          }
+        }
       }
     }
   }
@@ -132,7 +145,7 @@ __device__ __forceinline__ void store_product(const ImmaGeom &G, int lane, const
 template <int LIMBS>
 __device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__restrict__ src, uint8_t *y0, uint8_t *y1, int lane) {
   for (int j0 = 8 * lane; j0 < G.N; j0 += 256) {
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+    uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
     const int nv = G.N - j0;                                     // valid coefficients in this vector
     if (nv < 8) {
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -149,7 +162,7 @@ __device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__r
 // y (bytes) -> reversed array
 __device__ __forceinline__ void stage_y8(const ImmaGeom &G, const uint8_t *__restrict__ src, uint8_t *y0, int lane) {
   for (int j0 = 16 * lane; j0 < G.N; j0 += 512) {
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+    uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
     const int nv = G.N - j0;
     if (nv < 16) {
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -168,7 +181,7 @@ __device__ __forceinline__ void stage_y8(const ImmaGeom &G, const uint8_t *__res
 // x (bytes) -> zero-padded array
 __device__ __forceinline__ void stage_x8(const ImmaGeom &G, const uint8_t *__restrict__ src, uint8_t *xb, int lane) {
   for (int j0 = 16 * lane; j0 < G.N; j0 += 512) {
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + j0));
+    uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
     const int nv = G.N - j0;
     if (nv < 16) {
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -181,6 +194,19 @@ __device__ __forceinline__ void stage_x8(const ImmaGeom &G, const uint8_t *__res
     }
     *reinterpret_cast<uint4 *>(xb + kXPad + j0) = v;
   }
+}
+
+// asynchronous copy of `bytes` (multiple of 16) from global to this warp's prefetch area; completion: prefetch_wait
+__device__ __forceinline__ void prefetch_row(uint8_t *dst, const void *src, int bytes, int lane) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const char *s = reinterpret_cast<const char *>(src);
+  for (int o = 16 * lane; o < bytes; o += 512)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + o), "l"(s + o) : "memory");
+}
+__device__ __forceinline__ void prefetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 }
 
 // lo = c[k0 .. k0+8), hi = c[k0+N .. k0+N+8) as packed uint16 pairs
@@ -222,14 +248,27 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_encrypt_imma(const ImmaEncA
   uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
   uint8_t *y0 = base, *y1 = base + G.Ly, *xb = base + 2 * G.Ly;
   uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 2 * G.Ly + G.Lx);
+  uint8_t *raw = base + 2 * G.Ly + G.Lx + G.Lc;       // [h: 2P][r: P][m: P] of the NEXT row (cp.async)
+  uint8_t *mcur = raw + G.Lraw;                       // message of the current row
   for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
   const uint32_t Q2 = G.qmask | (G.qmask << 16);
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  for (size_t row = (size_t)blockIdx.x * kImmaWarps + warp; row < a.B; row += nwarps) {
-    stage_y16<LIMBS>(G, a.h + row * a.h_stride, y0, y1, lane);
-    stage_x8(G, a.r + row * (size_t)G.P, xb, lane);
+  auto prefetch = [&](size_t row) {
+    prefetch_row(raw, a.h + row * a.h_stride, 2 * G.P, lane);
+    prefetch_row(raw + 2 * G.P, a.r + row * (size_t)G.P, G.P, lane);
+    prefetch_row(raw + 3 * G.P, a.m + row * (size_t)G.P, G.P, lane);
+    prefetch_commit();
+  };
+  size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
+  if (row < a.B) prefetch(row);
+  for (; row < a.B; row += nwarps) {
+    prefetch_wait();
+    stage_y16<LIMBS>(G, reinterpret_cast<const uint16_t *>(raw), y0, y1, lane);
+    stage_x8(G, raw + 2 * G.P, xb, lane);
+    for (int o = 16 * lane; o < G.P; o += 512) *reinterpret_cast<uint4 *>(mcur + o) = *reinterpret_cast<const uint4 *>(raw + 3 * G.P + o);
     __syncwarp();
+    if (row + nwarps < a.B) prefetch(row + nwarps);    // the next row's loads fly during this row's products
     {
       int acc[NJ][LIMBS][4];
       conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
@@ -240,7 +279,7 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_encrypt_imma(const ImmaEncA
     for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
       uint32_t lo[4], hi[4], rem[4], quo[4];
       load_lo_hi(G, cbuf, k0, lo, hi);
-      const uint2 mm = __ldg(reinterpret_cast<const uint2 *>(a.m + rbase + k0));
+      const uint2 mm = *reinterpret_cast<const uint2 *>(mcur + k0);
       const uint32_t mp[4] = {__byte_perm(mm.x, 0u, 0x4140), __byte_perm(mm.x, 0u, 0x4342), __byte_perm(mm.y, 0u, 0x4140),
                               __byte_perm(mm.y, 0u, 0x4342)};
 #pragma unroll
@@ -278,17 +317,28 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_decrypt_imma(const ImmaDecA
   uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
   uint8_t *y0 = base, *y1 = base + G.Ly, *y2 = base + 2 * G.Ly, *xb = base + 3 * G.Ly;
   uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 3 * G.Ly + G.Lx);
+  uint8_t *raw = base + 3 * G.Ly + G.Lx + G.Lc;       // [e: 2P][f: P][fp: P] of the NEXT row (cp.async)
   for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
   const uint32_t Q2 = G.qmask | (G.qmask << 16);
   const uint32_t LA2 = (((uint32_t)G.q >> 1) - 1u) * 0x00010001u;       // x > q/2  <=>  bit logq of x + q/2 - 1
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  for (size_t row = (size_t)blockIdx.x * kImmaWarps + warp; row < a.B; row += nwarps) {
+  auto prefetch = [&](size_t row) {
+    prefetch_row(raw, a.e + row * (size_t)G.P, 2 * G.P, lane);
+    prefetch_row(raw + 2 * G.P, a.f + row * a.key_stride, G.P, lane);
+    prefetch_row(raw + 3 * G.P, a.fp + row * a.key_stride, G.P, lane);
+    prefetch_commit();
+  };
+  size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
+  if (row < a.B) prefetch(row);
+  for (; row < a.B; row += nwarps) {
     const size_t rbase = row * (size_t)G.P;
-    stage_y16<LIMBS>(G, a.e + rbase, y0, y1, lane);
-    stage_y8(G, a.fp + row * a.key_stride, y2, lane);
-    stage_x8(G, reinterpret_cast<const uint8_t *>(a.f) + row * a.key_stride, xb, lane);
+    prefetch_wait();
+    stage_y16<LIMBS>(G, reinterpret_cast<const uint16_t *>(raw), y0, y1, lane);
+    stage_x8(G, raw + 2 * G.P, xb, lane);
+    stage_y8(G, raw + 3 * G.P, y2, lane);
     __syncwarp();
+    if (row + nwarps < a.B) prefetch(row + nwarps);    // the next row's loads fly during this row's products
     {   // product 1: a = lin(f, e) mod q
       int acc[NJ][LIMBS][4];
       conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
@@ -347,7 +397,7 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_decrypt_imma(const ImmaDecA
   }
 }
 
-ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays) {
+ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays, int nj_bucket) {
   ImmaGeom G;
   G.N = ctx->N; G.P = ctx->P; G.q = ctx->q; G.logq = ctx->logq; G.qmask = (uint32_t)ctx->q - 1;
   G.I1 = (G.N + 15) / 16;
@@ -356,9 +406,12 @@ ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays) {
   G.NJ = ((2 * G.N - 1 + 15) / 16 + 7) / 8;
   G.Z = 32 * G.S + 15;
   G.Ly = 32 * G.S + 48;
-  G.Lx = 16 * (G.I1 + 15);
+  // x is read at block indices K1 - t in [-7, 8 kDMax + 7] and, as the lifted polynomial b, written up to P
+  const int dmax = (6 + 4 * nj_bucket) >> 3;
+  G.Lx = kXPad + (128 * (dmax + 1) > G.P ? 128 * (dmax + 1) : G.P);
   G.Lc = 2 * (128 * G.NJ + 32);
-  G.warp_bytes = ylimb_arrays * G.Ly + G.Lx + G.Lc;
+  G.Lraw = 4 * G.P;
+  G.warp_bytes = ylimb_arrays * G.Ly + G.Lx + G.Lc + G.Lraw + (ylimb_arrays == 2 ? G.P : 0);
   return G;
 }
 
@@ -385,6 +438,11 @@ int launch_imma(ntru_ctx *ctx, K kernel, const A &args, int kind, size_t B, int 
 
 }  // namespace
 
+static int imma_bucket(const ntru_ctx *ctx) {
+  const int nj = ((2 * ctx->N - 1 + 15) / 16 + 7) / 8;
+  return nj <= 3 ? 3 : (nj <= 8 ? 8 : (nj <= 11 ? 11 : 13));
+}
+
 bool imma_supported(const ntru_ctx *ctx) {
   // 13 column blocks of accumulators (104 registers for two limbs) is the largest instantiation: N <= 832
   return ((2 * ctx->N - 1 + 15) / 16 + 7) / 8 <= 13 && ctx->q <= 65536;
@@ -405,7 +463,7 @@ int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_str
   if (B == 0) return NTRU_OK;
   if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
   ImmaEncArgs a;
-  a.G = make_geom(ctx, 2);
+  a.G = make_geom(ctx, 2, imma_bucket(ctx));
   a.B = B; a.h = h; a.h_stride = h_stride; a.r = r; a.m = m; a.value = value; a.quo = quo; a.rem = rem;
   NTRU_IMMA_DISPATCH(k_encrypt_imma, a, NTRU_K_ENC_IMMA);
 }
@@ -415,7 +473,7 @@ int launch_decrypt_imma(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t 
   if (B == 0) return NTRU_OK;
   if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
   ImmaDecArgs a;
-  a.G = make_geom(ctx, 3);
+  a.G = make_geom(ctx, 3, imma_bucket(ctx));
   a.B = B; a.f = f; a.fp = fp; a.key_stride = key_stride; a.e = e;
   a.value = value; a.q1 = q1; a.r1 = r1; a.q2 = q2; a.r2 = r2;
   NTRU_IMMA_DISPATCH(k_decrypt_imma, a, NTRU_K_DEC_IMMA);
