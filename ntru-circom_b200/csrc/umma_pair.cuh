@@ -111,6 +111,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
                "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -218,9 +226,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 2 * kEpiWarps);       // every epilogue warp of both CTAs
+      mbar_init(tempty_bar(b), kEpiWarps);           // the epilogue group of this buffer, both CTAs (2 x kEpiWarps / 2)
       mbar_init(m_full(b), 1);                       // this CTA's producer (+ transaction bytes)
-      mbar_init(m_empty(b), kEpiWarps);              // this CTA's epilogue warps
+      mbar_init(m_empty(b), kEpiWarps / 2);          // the epilogue group that drains the chunk, this CTA
     }
     fence_barrier_init();
   }
@@ -326,67 +334,65 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     // second issuer is enabled only when a chunk has fewer slices than the B ring has stages (a.two_issuers):
     // then no issuer can wait on a stage two phases ahead of its oldest unconsumed use.
     if (leader) {
-      const uint32_t w = 0;
+      // One flat loop per chunk with running slot / stage / descriptor counters: the first version walked
+      // (atom, K limb) in nested loops with run-time bounds and cost ~95 SASS instructions per slice on a single
+      // warp (~600 cycles against the 512 cycles of tensor work a slice holds; clock trace, ncu source counters).
+      // Slices of a chunk use consecutive resident A slots: sa = (first atom) * kl + i.
       const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.NC);
       const uint64_t desc_hi = make_smem_desc(0) & ~0x3FFFull;             // everything but the start address
-      const uint32_t a_addr16 = (smem_base >> 4), b_addr16 = (smem_base + a.nA * kSlotBytes) >> 4;
-      const int parts = a.with_hi ? 2 : 1;
-      const int nct = parts * a.nchunks;                                   // chunks per tile
+      const uint32_t a_lo0 = smem_base >> 4, b_lo0 = (smem_base + a.nA * kSlotBytes) >> 4;   // 16-byte units
+      const int nct = (a.with_hi ? 2 : 1) * a.nchunks;                     // chunks per tile
       const bool resident = a.a_resident != 0;
+      const uint32_t nB = (uint32_t)a.nB, nA = (uint32_t)a.nA;
+      const uint32_t bfull0 = b_full(0), bempty0 = b_empty(0), afull0 = a_full(0), aempty0 = a_empty(0);
       uint32_t sb = 0, b_par = 0;           // B ring position / phase parity
       uint32_t sas = 0, a_par_s = 0;        // streaming A ring position / phase parity
       uint32_t cc = 0, t_par = 0;           // chunk counter, resident-A phase parity (per tile)
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         for (int j = 0; j < nct; ++j, ++cc) {
           const int hi = j >= a.nchunks;
-          const int c = hi ? j - a.nchunks : j;
-          const int a0 = first_atom(a, hi, c);
+          const int a0 = first_atom(a, hi, hi ? j - a.nchunks : j);
           const uint32_t nsl = (uint32_t)((a.atoms - a0) * a.kl);            // slices of this chunk
-          if (a.two_issuers ? (cc & 1) != w : w != 0) {   // not this issuer's chunk: only advance the ring positions
-            sb += nsl;
-            while (sb >= (uint32_t)a.nB) { sb -= a.nB; b_par ^= 1; }
-            if (!resident) {
-              sas += nsl;
-              while (sas >= (uint32_t)a.nA) { sas -= a.nA; a_par_s ^= 1; }
-            }
-            continue;
-          }
-          // this issuer reads atom x again later in the tile iff its next chunk (j+2) does: chunks j+2, j+4, ...
-          // read ever fewer atoms (cyclic chunks read all, hi chunk c reads atoms >= a0(c), a0 non-decreasing)
-          int next_a0 = a.atoms;            // first atom read by chunk j+2 (a.atoms: none)
-          const int jn = j + (a.two_issuers ? 2 : 1);          // this issuer's next chunk in the tile
-          if (jn < nct) next_a0 = (jn >= a.nchunks) ? first_atom(a, 1, jn - a.nchunks) : 0;
+          // resident A slot sa is read again later in the tile iff the next chunk reads it: chunks read ever fewer
+          // atoms (cyclic chunks read all, hi chunk c reads atoms >= a0(c), a0 non-decreasing)
+          const int jn = j + 1;
+          const int next_a0 = jn < nct ? (jn >= a.nchunks ? first_atom(a, 1, jn - a.nchunks) : 0) : a.atoms;
+          const uint32_t rel_lim = resident ? (uint32_t)(next_a0 * a.kl) : 0xffffffffu;   // release slots sa < rel_lim
+          const bool wait_a = !resident || j == 0;
+          const uint32_t a_par = resident ? t_par : a_par_s;
           const uint32_t buf = cc & 1;
-          const uint32_t my = cc >> 1;      // uses of this TMEM buffer so far
-          if (lane == 0) { if (w) TRACE(4, 0, cc); else TRACE(1, 0, cc); }
-          mbar_wait(tempty_bar(buf), (my & 1) ^ 1);
-          if (lane == 0) { if (w) TRACE(4, 1, cc); else TRACE(1, 1, cc); }
+          if (lane == 0) TRACE(1, 0, cc);
+          mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
+          if (lane == 0) TRACE(1, 1, cc);
           const uint32_t d_tmem = tmem_base + buf * kAccCols;
+          const uint32_t tfull = tfull_bar(buf);
+          uint32_t sa = resident ? (uint32_t)(a0 * a.kl) : sas;
           uint32_t accumulate = 0;
-          for (int at = a0; at < a.atoms; ++at) {
-            for (int lk = 0; lk < a.kl; ++lk) {
-              const uint32_t sa = resident ? (uint32_t)(at * a.kl + lk) : sas;
-              mbar_wait(b_full(sb), b_par);
-              if (!resident || j == 0) mbar_wait(a_full(sa), resident ? t_par : a_par_s);
-              tc_fence_after();
-              const uint64_t da = desc_hi | (uint64_t)((a_addr16 + sa * (kSlotBytes >> 4)) & 0x3FFF);
-              const uint64_t db = desc_hi | (uint64_t)((b_addr16 + sb * (kSlotBytes >> 4)) & 0x3FFF);
-              const bool last = at == a.atoms - 1 && lk == a.kl - 1;
-              const bool release = !resident || at < next_a0;
-              if (elect_one()) {
-                umma_i8_pair(d_tmem, da, db, idesc, accumulate);
-                umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
-                umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
-                umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
-                umma_commit_pair(b_empty(sb));
-                if (release) umma_commit_pair(a_empty(sa));
-                if (last) umma_commit_pair(tfull_bar(buf));
-              }
-              __syncwarp();
-              if (lane == 0) { if (w) TRACE(4, 5, cc); else TRACE(1, 5, cc); }
-              accumulate = 1;
-              if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
-              if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
+          for (uint32_t i = 0; i < nsl; ++i) {
+            mbar_wait(bfull0 + 8u * sb, b_par);
+            if (lane == 0) TRACE(1, 2, cc);
+            if (wait_a) mbar_wait(afull0 + 8u * sa, resident ? a_par : a_par_s);
+            tc_fence_after();
+            const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
+            const uint64_t db = desc_hi | (uint64_t)(b_lo0 + sb * (kSlotBytes >> 4));
+            if (elect_one()) {
+              umma_i8_pair(d_tmem, da, db, idesc, accumulate);
+              umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+              umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+              umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+              umma_commit_pair(bempty0 + 8u * sb);
+              if (sa < rel_lim) umma_commit_pair(aempty0 + 8u * sa);
+              if (i == nsl - 1) umma_commit_pair(tfull);
+            }
+            __syncwarp();
+            if (lane == 0) TRACE(1, 5, cc);
+            accumulate = 1;
+            if (++sb == nB) { sb = 0; b_par ^= 1; }
+            if (resident) {
+              ++sa;
+            } else {
+              if (++sas == nA) { sas = 0; a_par_s ^= 1; }
+              sa = sas;
             }
           }
         }
@@ -487,27 +493,34 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     }
   } else {
     // ===================== epilogue (both CTAs): TMEM -> registers -> shared staging -> TMA store ==========
-    // Each warp owns 32 rows (its TMEM lane quadrant) and a contiguous run of 16-coefficient units per chunk.
-    // Results are staged in a small per-warp shared-memory tile and written with cp.async.bulk.tensor stores:
-    // the first version stored straight from registers (each lane its own row), 32 cache lines per warp
-    // instruction, and the epilogue warps spent their time in LSU back-pressure (ncu: lg_throttle; trace:
-    // ~3000 cycles per chunk against ~2000 cycles of MMA work).  ENC reads the message bytes from a TMA-loaded
-    // shared tile for the same reason.
-    constexpr int kSub = MODE == DEC1 ? 2 : 4;
+    // Two GROUPS of epilogue warps, one per TMEM accumulator buffer: group g drains the chunks with cc & 1 == g, so
+    // the two buffers are drained concurrently and every warp pays the fixed cost of a chunk (barrier waits, fences,
+    // store issue) once per TWO chunks.  The first version put all warps on every chunk: ~275 instructions per
+    // warp and chunk, 170 of them fixed cost, and the kernel was bound by the epilogue's instruction issue
+    // (ncu: IPC 0.74 per scheduler; clock trace: 2450 cycles per chunk against 2048 cycles of MMA work or less).
+    // Inside a group a warp owns 32 rows (its TMEM lane quadrant) and a contiguous run of 16-coefficient units;
+    // results are staged in a per-warp shared-memory tile and written with cp.async.bulk.tensor stores (per-lane
+    // row stores cost 32 cache lines per warp instruction).  ENC reads the message bytes from a TMA-loaded tile.
+    constexpr int kGroupWarps = kEpiWarps / 2;                     // 8 (ENC, DEC2) or 4 (DEC1)
+    constexpr int kSub = kGroupWarps / 4;                          // warps per TMEM lane quadrant within a group
     constexpr int kPassUnits = MODE == DEC2 ? 4 : 2;               // units staged per TMA store (64-byte rows)
     const int ew = warp - (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0);
     const int quad = warp & 3;
-    const int sub = ew >> 2;
+    const uint32_t grp = (uint32_t)(ew >> 2) & 1u;
+    const int sub = ew >> 3;
     const int parts = a.with_hi ? 2 : 1;
     const int upw = (a.NCo >> 4) / kSub;                           // units per warp per chunk
+    const int npass = upw / kPassUnits;
     const uint32_t Q2 = a.qmask | (a.qmask << 16);
-    const uint32_t lift_add = ((uint32_t)a.q >> 1) - 1;
+    const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;   // x > q/2  <=>  bit log2(q) of x + q/2 - 1
     const int logq = 31 - __clz(a.q);
     const uint32_t stage = stage_base + (uint32_t)ew * (MODE == DEC1 ? 4096u : 2048u);   // this warp's staging tile
-    uint8_t *stage_ptr = smem + (stage - smem_base);
     // swizzled position of 16-byte chunk `ch` of this lane's 64-byte staging row (SWIZZLE_64B)
-    auto st64 = [&](int ch) { return (uint32_t)(lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4)); };
+    const uint32_t st_row = stage + (uint32_t)lane * 64u, st_x = (uint32_t)(lane >> 1) & 3u;
     const int row_in_tile = quad * 32 + lane;
+    const uint32_t m_row = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128), m_x = (uint32_t)row_in_tile & 7u;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * kAccCols;
+    const uint32_t my_tfull = tfull_bar(grp), lead_tempty = lead(tempty_bar(grp));
     uint32_t cc = 0, mc = 0;
     bool store_pending = false;
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
@@ -515,19 +528,27 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       for (int part = 0; part < parts; ++part) {
         const int hi = part == 1;
         for (int c = 0; c < a.nchunks; ++c, ++cc) {
-          const uint32_t buf = cc & 1;
-          const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
+          const uint32_t ms = mc & 1, m_par = (mc >> 1) & 1;
+          if (MODE == ENC && !hi) ++mc;
+          if ((cc & 1u) != grp) continue;
           if (lane == 0 && ew == 0) TRACE(2, 0, cc);
-          mbar_wait(tfull_bar(buf), (cc >> 1) & 1);
+          mbar_wait(my_tfull, (cc >> 1) & 1);
           tc_fence_after();
           if (lane == 0 && ew == 0) TRACE(2, 1, cc);
-          const uint32_t ms = mc & 1;
-          if (MODE == ENC && !hi) mbar_wait(m_full(ms), (mc >> 1) & 1);
-          for (int u0 = sub * upw; u0 < (sub + 1) * upw; u0 += kPassUnits) {
+          if (MODE == ENC && !hi) mbar_wait(m_full(ms), m_par);
+          if (lane == 0 && ew == 0) TRACE(2, 3, cc);
+          for (int ps = 0; ps < npass; ++ps) {
+            const int u0 = sub * upw + ps * kPassUnits;
+            const bool last_pass = ps == npass - 1;
             uint32_t res[kPassUnits * (MODE == DEC2 ? 4 : 8)];      // packed results of this pass
             uint32_t bres[kPassUnits * 4];                          // DEC1: lifted polynomial b (bytes)
-            // all accumulator reads of the pass first (one round trip), then hand the TMEM buffer back to the
-            // MMA issuers before any arithmetic: short hi chunks otherwise wait for this latency
+            uint4 mm[kPassUnits];                                   // ENC: message bytes of the pass
+            if (MODE == ENC && !hi) {
+#pragma unroll
+              for (int j = 0; j < kPassUnits; ++j) mm[j] = lds128(m_slot(ms) + m_row + ((((uint32_t)(u0 + j)) ^ m_x) << 4));
+            }
+            // all accumulator reads of the pass first (one round trip); after the last pass's reads the TMEM buffer
+            // goes back to the MMA issuer before any arithmetic
             uint32_t acc[kPassUnits][32];
             {
               uint32_t acc1[kPassUnits][32];
@@ -537,6 +558,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 if (MODE == ENC && a.nl == 2) tmem_ld16(t_addr + a.NCo + (u0 + j) * 16, acc1[j]);
               }
               tmem_ld_wait();
+              if (lane == 0 && ew == 0) TRACE(2, 4, cc);
               if (MODE == ENC && a.nl == 2) {
 #pragma unroll
                 for (int j = 0; j < kPassUnits; ++j)
@@ -544,15 +566,16 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                   for (int i = 0; i < 16; ++i) acc[j][i] += acc1[j][i] << 8;
               }
             }
-            const bool last_pass = u0 + kPassUnits >= (sub + 1) * upw;
             if (last_pass) {
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(lead(tempty_bar(buf)));
+              if (lane == 0) {
+                mbar_arrive_cluster(lead_tempty);
+                if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));   // message tile is in registers
+              }
             }
 #pragma unroll
             for (int j = 0; j < kPassUnits; ++j) {
-              const int u = u0 + j;
               uint32_t (&w)[32] = acc[j];
               if (MODE == ENC || MODE == DEC1) {
                 uint32_t *pk = res + 8 * j;
@@ -562,9 +585,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 #pragma unroll
                   for (int jj = 0; jj < 8; ++jj) pk[jj] = ((~pk[jj] & Q2) + 0x00010001u) & Q2;
                 } else if (MODE == ENC) {
-                  const int off = (row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128 + ((u ^ (row_in_tile & 7)) << 4);
-                  const uint4 mm = *reinterpret_cast<const uint4 *>(smem + (m_slot(ms) - smem_base) + off);
-                  const uint32_t mw[4] = {mm.x, mm.y, mm.z, mm.w};
+                  const uint32_t mw[4] = {mm[j].x, mm[j].y, mm[j].z, mm[j].w};
 #pragma unroll
                   for (int jj = 0; jj < 8; ++jj) {
                     const uint32_t mp = __byte_perm(mw[jj >> 1], 0u, (jj & 1) ? 0x4342 : 0x4140);
@@ -574,16 +595,19 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 #pragma unroll
                   for (int jj = 0; jj < 8; ++jj) pk[jj] &= Q2;
                   if (a.o8_cyc) {
+                    // multiplier of the second product: any byte congruent to b = (x + [x > q/2]) mod 3 (index.js:117)
+                    // will do, the reduction mod 3 happens on the accumulators of DEC2.  y = x + [x > q/2] <= q, and
+                    // 64 = 1 (mod 3):  b' = (y & 63) + (y >> 6) <= 63 + 128, two coefficients per 32-bit word.
 #pragma unroll
                     for (int wd = 0; wd < 4; ++wd) {
-                      uint32_t bb[4];
+                      uint32_t y2[2];
 #pragma unroll
-                      for (int i = 0; i < 4; ++i) {
-                        const uint32_t x = w[4 * wd + i] & a.qmask;
-                        const uint32_t y = x + ((x + lift_add) >> logq);          // index.js:117
-                        bb[i] = y - 3u * __umulhi(y, 0x55555556u);
+                      for (int i = 0; i < 2; ++i) {
+                        const uint32_t x = pk[2 * wd + i];
+                        const uint32_t y = x + (((x + LA2) >> logq) & 0x00010001u);
+                        y2[i] = (y & 0x003F003Fu) + ((y >> 6) & 0x00FF00FFu);
                       }
-                      bres[4 * j + wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
+                      bres[4 * j + wd] = __byte_perm(y2[0], y2[1], 0x6420);
                     }
                   }
                 }
@@ -600,10 +624,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 }
               }
             }
-            if (last_pass && MODE == ENC && !hi) {   // message tile no longer needed by this warp
-              __syncwarp();
-              if (lane == 0) mbar_arrive(m_empty(ms));
-            }
+            if (lane == 0 && ew == 0) TRACE(2, 5, cc);
             // the previous store must have finished reading the staging tile before it is overwritten
             if (store_pending) {
               if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -612,22 +633,24 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             if (MODE == DEC2) {
 #pragma unroll
               for (int j = 0; j < kPassUnits; ++j)
-                *reinterpret_cast<uint4 *>(stage_ptr + st64(j)) = make_uint4(res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]);
+                sts128(st_row + ((((uint32_t)j) ^ st_x) << 4), make_uint4(res[4 * j], res[4 * j + 1], res[4 * j + 2], res[4 * j + 3]));
             } else {
 #pragma unroll
               for (int j = 0; j < kPassUnits; ++j) {
-                *reinterpret_cast<uint4 *>(stage_ptr + st64(2 * j)) = make_uint4(res[8 * j], res[8 * j + 1], res[8 * j + 2], res[8 * j + 3]);
-                *reinterpret_cast<uint4 *>(stage_ptr + st64(2 * j + 1)) = make_uint4(res[8 * j + 4], res[8 * j + 5], res[8 * j + 6], res[8 * j + 7]);
+                sts128(st_row + ((((uint32_t)(2 * j)) ^ st_x) << 4), make_uint4(res[8 * j], res[8 * j + 1], res[8 * j + 2], res[8 * j + 3]));
+                sts128(st_row + ((((uint32_t)(2 * j + 1)) ^ st_x) << 4), make_uint4(res[8 * j + 4], res[8 * j + 5], res[8 * j + 6], res[8 * j + 7]));
               }
               if (MODE == DEC1 && !hi && a.o8_cyc) {   // b: 32-byte rows, no swizzle needed
 #pragma unroll
                 for (int j = 0; j < kPassUnits; ++j)
-                  *reinterpret_cast<uint4 *>(stage_ptr + 2048 + lane * 32 + j * 16) =
-                      make_uint4(bres[4 * j], bres[4 * j + 1], bres[4 * j + 2], bres[4 * j + 3]);
+                  sts128(stage + 2048u + (uint32_t)lane * 32u + (uint32_t)j * 16u,
+                         make_uint4(bres[4 * j], bres[4 * j + 1], bres[4 * j + 2], bres[4 * j + 3]));
               }
             }
+            if (lane == 0 && ew == 0) TRACE(2, 6, cc);
             fence_proxy_async();
             __syncwarp();
+            if (lane == 0 && ew == 0) TRACE(2, 7, cc);
             if (lane == 0) {
               const int col = c * a.NCo + u0 * 16;
               if (hi) {
@@ -644,7 +667,6 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             }
             store_pending = true;
           }
-          if (MODE == ENC && !hi) ++mc;
           if (lane == 0 && ew == 0) TRACE(2, 2, cc);
         }
       }

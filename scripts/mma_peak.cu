@@ -19,7 +19,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // KIND: 0 = i8 (K=32), 1 = f16/bf16 (K=16), 2 = f8f6f4 e4m3 (K=32).  GROUP: 1 or 2 CTAs.
 template <int KIND, int GROUP>
-__global__ void __launch_bounds__(128, 1) k_peak(int iters, unsigned long long *cycles) {
+__global__ void __launch_bounds__(128, 1) k_peak(int iters, unsigned long long *cycles, int ncols) {
   extern __shared__ uint8_t raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128, 1) k_peak(int iters, unsigned long long *
   const uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem) + 16384);
   // instruction descriptor: N = 256, M = 128 * GROUP, K-major operands
   const uint32_t mdim = (128 * GROUP) >> 4;
-  uint32_t idesc = ((256u >> 3) << 17) | (mdim << 24);
+  uint32_t idesc = (((uint32_t)ncols >> 3) << 17) | (mdim << 24);
   if (KIND == 0) idesc |= (2u << 4);                               // S32 accumulate, u8 x u8
   if (KIND == 1) idesc |= (1u << 4) | (1u << 7) | (1u << 10);      // F32 accumulate, bf16 x bf16
   if (KIND == 2) idesc |= (1u << 4);                               // F32 accumulate, e4m3 x e4m3
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128, 1) k_peak(int iters, unsigned long long *
 }
 
 template <int KIND, int GROUP>
-void run(const char *name, int sms) {
+void run(const char *name, int sms, int ncols = 256) {
   const int iters = getenv("MMA_ITERS") ? atoi(getenv("MMA_ITERS")) : 4000;
   unsigned long long *cyc;
   cudaMalloc(&cyc, sizeof(unsigned long long) * sms);
@@ -105,7 +105,7 @@ void run(const char *name, int sms) {
   for (int rep = 0; rep < 2; ++rep) {
     cudaEventRecord(e0);
     if (GROUP == 1) {
-      k_peak<KIND, GROUP><<<sms, 128, smem>>>(iters, cyc);
+      k_peak<KIND, GROUP><<<sms, 128, smem>>>(iters, cyc, ncols);
     } else {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(sms);
@@ -116,7 +116,7 @@ void run(const char *name, int sms) {
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      cudaLaunchKernelEx(&cfg, k_peak<KIND, GROUP>, iters, cyc);
+      cudaLaunchKernelEx(&cfg, k_peak<KIND, GROUP>, iters, cyc, ncols);
     }
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
@@ -127,7 +127,7 @@ void run(const char *name, int sms) {
   unsigned long long h[256];
   cudaMemcpy(h, cyc, sizeof(unsigned long long) * sms, cudaMemcpyDeviceToHost);
   const int K = KIND == 1 ? 16 : 32;
-  const double macs_per_instr = 128.0 * GROUP * 256 * K;
+  const double macs_per_instr = 128.0 * GROUP * ncols * K;
   const double instrs = (double)iters * 4 * (GROUP == 1 ? sms : sms / 2);
   printf("%-28s %8.3f ms  %8.1f TMAC/s (%.1f T-op/s)  cycles/instr (CTA 0) = %.1f\n", name, ms,
          instrs * macs_per_instr / (ms * 1e-3) / 1e12, 2 * instrs * macs_per_instr / (ms * 1e-3) / 1e12,
@@ -146,5 +146,9 @@ int main() {
   run<1, 2>("bf16 cta_group::2 M256 N256", sms);
   run<2, 1>("e4m3 cta_group::1 M128 N256", sms);
   run<2, 2>("e4m3 cta_group::2 M256 N256", sms);
+  // narrower accumulator tiles (the lo / hi split of the same-key schedule issues N = 128 MMAs)
+  run<0, 2>("i8   cta_group::2 M256 N128", sms, 128);
+  run<0, 2>("i8   cta_group::2 M256 N64", sms, 64);
+  run<0, 1>("i8   cta_group::1 M128 N128", sms, 128);
   return 0;
 }

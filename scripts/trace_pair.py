@@ -4,13 +4,15 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 csrc = os.path.join(ROOT, "ntru-circom_b200", "csrc")
-lib_path = os.path.join(ROOT, "gpurun_out", "libntru_trace.so")
-if not os.path.exists(lib_path):
+lib_path = os.path.join(ROOT, "ntru-circom_b200", "libntru_trace.so")   # *.so: git-ignored, travels with gpurun
+if not os.path.exists(lib_path) or "--build" in sys.argv:
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DNTRU_TRACE", "-Xcompiler", "-fPIC",
-                    "-shared", "-o", lib_path] + [os.path.join(csrc, f) for f in ("api.cu", "generic_kernels.cu", "umma_kernels.cu")], check=True)
+                    "-shared", "-o", lib_path] + [os.path.join(csrc, f) for f in ("api.cu", "generic_kernels.cu", "imma_kernels.cu", "umma_kernels.cu")], check=True)
 import ntru_circom_b200 as nb
 from ntru_circom_b200 import _lib
 _lib.LIB_PATH = lib_path
+if "--build" in sys.argv:
+    sys.exit(0)
 mode = sys.argv[1] if len(sys.argv) > 1 else "enc"
 g = dict(np.load(os.path.join(ROOT, "tests", "golden", "hps509.npz")))
 eng = nb.Engine(509, 3, 2048, 0)
@@ -48,10 +50,12 @@ rec = np.array(recs, dtype=np.int64)
 rec[:, 3] -= rec[:, 3].min()
 rec = rec[np.argsort(rec[:, 3], kind="stable")]
 nm = {(4,0):"MMA1 chunk start",(4,1):"MMA1 got tempty",(4,5):"MMA1 issued",(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
-      (2,0):"epi start",(2,1):"epi got tfull",(2,2):"epi done",(2,3):"epi unit0 loaded",(2,4):"epi unit0 math done",(2,6):"epi unit1 loaded",(2,7):"epi unit1 math done",(3,0):"prod wait b_empty",(3,1):"prod got b_empty",(3,2):"prod issued"}
+      (2,0):"epi start",(2,1):"epi got tfull",(2,2):"epi done",(2,3):"epi got m_full",(2,4):"epi tmem loaded",(2,5):"epi math done",(2,6):"epi staged (after wait_group.read + STS)",(2,7):"epi fenced",(3,0):"prod wait b_empty",(3,1):"prod got b_empty",(3,2):"prod issued"}
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 19)
 prev = {}
 for role, e, idx, t in rec:
+    if "--mma" in sys.argv and role != 1:
+        continue
     if lo <= idx <= hi:
         d = t - prev.get(role, t)
         prev[role] = t
