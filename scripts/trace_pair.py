@@ -14,13 +14,15 @@ _lib.LIB_PATH = lib_path
 if "--build" in sys.argv:
     sys.exit(0)
 mode = sys.argv[1] if len(sys.argv) > 1 else "enc"
-g = dict(np.load(os.path.join(ROOT, "tests", "golden", "hps509.npz")))
-eng = nb.Engine(509, 3, 2048, 0)
+cfg = os.environ.get("TRACE_CFG", "hps509")
+g = dict(np.load(os.path.join(ROOT, "tests", "golden", cfg + ".npz")))
+NN, QQ = int(g["N"]), int(g["q"])
+eng = nb.Engine(NN, 3, QQ, 0)
 eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
 rows = int(os.environ.get('TRACE_ROWS', 74 * 256 * 6))
 P = eng.pitch
-r = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); eng.sample_r_dev(rows, 169, 1, 0, r)
-m = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); m[:, :509] = torch.randint(0, 2, (rows, 509), device="cuda", dtype=torch.uint8)
+r = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); eng.sample_r_dev(rows, int(g["dr"]), 1, 0, r)
+m = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); m[:, :NN] = torch.randint(0, 2, (rows, NN), device="cuda", dtype=torch.uint8)
 val = torch.empty((rows, P), dtype=torch.int16, device="cuda"); quo = torch.empty_like(val)
 out = torch.empty((rows, P), dtype=torch.uint8, device="cuda"); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)
 LANES, CAP = 4, 448
@@ -55,6 +57,8 @@ lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 19)
 prev = {}
 for role, e, idx, t in rec:
     if "--mma" in sys.argv and role != 1:
+        continue
+    if "--ring" in sys.argv and not (role == 3 or (role == 1 and e in (2, 4, 5))):
         continue
     if lo <= idx <= hi:
         d = t - prev.get(role, t)
