@@ -132,6 +132,21 @@ int ntru_sum_finalize_dev(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out)
  * the same Fisher-Yates shuffle driven by a counter-based generator (seed, row, i) instead of WebCrypto */
 int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
 
+/* ---- cross-GPU homomorphic sum (one context = one rank = one GPU of the same node) ----
+ * The only exchange step of the hot path: every rank reduces its rows to N column sums mod q and all ranks need the
+ * total (fold of addPolynomials over the whole batch, test/reference.test.js:58).  The exchange runs inside the
+ * library's own kernels over peer memory (NVLink / NVSwitch): the CTA that finishes a rank's column sums stores them
+ * straight into every peer's exchange window and raises a flag there; a one-CTA kernel waits for all flags and adds
+ * the slots.  No collective library on the data path. */
+#define NTRU_XCHG_HANDLE_BYTES 64
+/* allocates this rank's exchange window and returns its CUDA IPC handle (to be all-gathered by the caller) */
+int ntru_xchg_create(ntru_ctx *ctx, int world, int rank, unsigned char handle_out[NTRU_XCHG_HANDLE_BYTES]);
+/* handles: world x NTRU_XCHG_HANDLE_BYTES, rank-major, as gathered from ntru_xchg_create on every rank */
+int ntru_xchg_connect(ntru_ctx *ctx, const unsigned char *handles);
+/* out[k] = (sum over every rank's rows of e[b][k]) mod q for k < N (0 up to pitch), on every rank; asynchronous on
+ * the context's stream.  Every rank must call it the same number of times.  Without ntru_xchg_create: world = 1. */
+int ntru_sum_allreduce_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
+
 void *ntru_stream(ntru_ctx *ctx);              /* cudaStream_t */
 int ntru_set_stream(ntru_ctx *ctx, void *stream);
 int ntru_sync(ntru_ctx *ctx);

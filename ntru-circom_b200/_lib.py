@@ -45,6 +45,9 @@ SYMBOLS = {
     "ntru_sum_partial_dev": (c_int, [_P, c_size_t, _P, _P]),
     "ntru_sum_finalize_dev": (c_int, [_P, _P, _P]),
     "ntru_sample_r_dev": (c_int, [_P, c_size_t, c_int, c_uint64, c_uint64, _P]),
+    "ntru_xchg_create": (c_int, [_P, c_int, c_int, _P]),
+    "ntru_xchg_connect": (c_int, [_P, _P]),
+    "ntru_sum_allreduce_dev": (c_int, [_P, c_size_t, _P, _P]),
     "ntru_stream": (c_void_p, [_P]),
     "ntru_set_stream": (c_int, [_P, _P]),
     "ntru_sync": (c_int, [_P]),

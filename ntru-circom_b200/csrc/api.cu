@@ -265,6 +265,8 @@ int ntru_create(ntru_ctx **out, int N, int p, int q, int device) {
   return NTRU_OK;
 }
 
+static int xchg_release(ntru_ctx *ctx);
+
 void ntru_destroy(ntru_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -276,6 +278,7 @@ void ntru_destroy(ntru_ctx *ctx) {
     for (auto &b : ctx->slot_bufs[s]) b.release();
     for (auto &b : ctx->slot_packed[s]) b.release();
   }
+  xchg_release(ctx);
   ctx->d_h.release(); ctx->d_f.release(); ctx->d_fp.release(); ctx->d_b.release(); ctx->d_partial.release();
   ctx->km_h.mat.release(); ctx->km_f.mat.release(); ctx->km_fp.mat.release();
   for (auto &t : ctx->timed) {
@@ -519,6 +522,79 @@ int ntru_sum_finalize_dev(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out)
   if (rc) return rc;
   if (!partial || !out) return fail(ctx, NTRU_E_PARAM, "partial and out are required");
   return launch_sum_finalize(ctx, partial, out);
+}
+
+static int xchg_release(ntru_ctx *ctx) {
+  for (int r = 0; r < ntru_ctx::kMaxRanks; ++r) {
+    if (ctx->peer_opened[r] && ctx->peer_window[r]) cudaIpcCloseMemHandle(ctx->peer_window[r]);
+    ctx->peer_opened[r] = false;
+    ctx->peer_window[r] = nullptr;
+  }
+  ctx->d_window.release();
+  ctx->xchg_connected = false;
+  ctx->xchg_world = 1;
+  ctx->xchg_rank = 0;
+  ctx->xchg_epoch = 0;
+  return NTRU_OK;
+}
+
+static int xchg_alloc(ntru_ctx *ctx, int world, int rank) {
+  xchg_release(ctx);
+  const size_t bytes = xchg_window_bytes(ctx, world);
+  NTRU_CUDA(ctx, ctx->d_window.reserve(bytes));
+  NTRU_CUDA(ctx, cudaMemset(ctx->d_window.ptr, 0, bytes));
+  NTRU_CUDA(ctx, cudaMemsetAsync(ctx->d_partial.ptr, 0, (size_t)ctx->P * 4, ctx->stream));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->xchg_world = world;
+  ctx->xchg_rank = rank;
+  ctx->peer_window[rank] = ctx->d_window.ptr;
+  return NTRU_OK;
+}
+
+int ntru_xchg_create(ntru_ctx *ctx, int world, int rank, unsigned char handle_out[NTRU_XCHG_HANDLE_BYTES]) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (world < 1 || world > ntru_ctx::kMaxRanks || rank < 0 || rank >= world || !handle_out)
+    return fail(ctx, NTRU_E_PARAM, "bad world / rank / handle buffer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == NTRU_XCHG_HANDLE_BYTES, "IPC handle size");
+  rc = xchg_alloc(ctx, world, rank);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  NTRU_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_window.ptr));
+  memcpy(handle_out, &h, sizeof h);
+  ctx->xchg_connected = world == 1;
+  return NTRU_OK;
+}
+
+int ntru_xchg_connect(ntru_ctx *ctx, const unsigned char *handles) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!handles) return fail(ctx, NTRU_E_PARAM, "handles is NULL");
+  if (!ctx->d_window.ptr) return fail(ctx, NTRU_E_PARAM, "ntru_xchg_create has not been called");
+  for (int r = 0; r < ctx->xchg_world; ++r) {
+    if (r == ctx->xchg_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * NTRU_XCHG_HANDLE_BYTES, sizeof h);
+    void *p = nullptr;
+    NTRU_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_window[r] = p;
+    ctx->peer_opened[r] = true;
+  }
+  ctx->xchg_connected = true;
+  return NTRU_OK;
+}
+
+int ntru_sum_allreduce_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if ((B > 0 && !e) || !out) return fail(ctx, NTRU_E_PARAM, "e and out are required");
+  if (!ctx->d_window.ptr) {                      // no exchange set up: a world of one rank
+    rc = xchg_alloc(ctx, 1, 0);
+    if (rc) return rc;
+    ctx->xchg_connected = true;
+  }
+  if (!ctx->xchg_connected) return fail(ctx, NTRU_E_PARAM, "ntru_xchg_connect has not been called");
+  return launch_sum_allreduce(ctx, B, e, out);
 }
 
 int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r) {

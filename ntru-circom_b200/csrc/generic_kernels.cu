@@ -300,6 +300,120 @@ __global__ void __launch_bounds__(512) k_sum_partial(const uint16_t *__restrict_
   }
 }
 
+// ---- cross-GPU sum: column sums fused with the exchange over peer memory --------------------------------------
+// Window of one rank: slots[2][world][P] uint32 (parity of the call number, sender rank), flags[world], ticket, error.
+// k_sum_push   = k_sum_partial + the LAST CTA to finish (ticket) reduces nothing further: it masks the N totals,
+//                stores them into slot[parity][rank] of EVERY rank's window (plain stores over NVLink for the peers),
+//                fences system-wide and raises flag[rank] = epoch in every window; it also re-zeroes partial[] and
+//                the ticket for the next call.
+//                Then the same CTA gathers: it waits until flag[r] == epoch for every r (acquire loads of its own
+//                window), adds the world slots per column, masks, writes out[].  A rank cannot run two calls ahead
+//                of a peer (it needs the peer's flag of call n to finish call n), so two slot parities are enough.
+// One launch per call: HBM streaming, exchange and final sum.
+struct XchgPeers {
+  uint32_t *window[ntru_ctx::kMaxRanks];   // only indexed with compile-time-unrolled, bounded loops (stays in the constant bank)
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e, size_t B, int P, uint32_t *__restrict__ partial,
+                                                  const XchgPeers peers, uint32_t *__restrict__ ticket, int world, int rank,
+                                                  uint32_t epoch, uint32_t qmask, int N, uint16_t *__restrict__ out) {
+  extern __shared__ __align__(16) uint32_t red[];
+  __shared__ bool is_last;
+  const int VX = P / 8;
+  const int vx = threadIdx.x, ry = threadIdx.y;
+  uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+  const int RY = blockDim.y;
+  const size_t step = (size_t)gridDim.x * RY;
+  size_t row = (size_t)blockIdx.x * RY + ry;
+  const uint4 *base = reinterpret_cast<const uint4 *>(e) + vx;
+  for (; row + (kSumUnroll - 1) * step < B; row += kSumUnroll * step) {
+    uint4 v[kSumUnroll];
+#pragma unroll
+    for (int u = 0; u < kSumUnroll; ++u) v[u] = __ldcs(base + (row + u * step) * (size_t)VX);
+#pragma unroll
+    for (int u = 0; u < kSumUnroll; ++u) {
+      lo[0] += v[u].x; hi[0] += v[u].x >> 16;
+      lo[1] += v[u].y; hi[1] += v[u].y >> 16;
+      lo[2] += v[u].z; hi[2] += v[u].z >> 16;
+      lo[3] += v[u].w; hi[3] += v[u].w >> 16;
+    }
+  }
+  for (; row < B; row += step) {
+    const uint4 v = __ldcs(base + row * (size_t)VX);
+    lo[0] += v.x; hi[0] += v.x >> 16;
+    lo[1] += v.y; hi[1] += v.y >> 16;
+    lo[2] += v.z; hi[2] += v.z >> 16;
+    lo[3] += v.w; hi[3] += v.w >> 16;
+  }
+  uint32_t *mine = red + ((size_t)ry * VX + vx) * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mine[2 * j] = lo[j] & 0xffffu;
+    mine[2 * j + 1] = hi[j];
+  }
+  __syncthreads();
+  if (ry == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t s = 0;
+      for (int y = 0; y < RY; ++y) s += red[((size_t)y * VX + vx) * 8 + j];
+      atomicAdd(partial + vx * 8 + j, s);
+    }
+  }
+  // ---- the last CTA to get here owns the exchange ----
+  __syncthreads();                                            // this CTA's atomics are issued
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  if (tid == 0) {
+    __threadfence();                                          // release: they are visible before the ticket moves
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __threadfence();                                          // acquire: the last CTA sees every CTA's atomics
+  }
+  __syncthreads();
+  if (!is_last) return;
+  const size_t slot = ((size_t)(epoch & 1u) * world + rank) * P;
+  for (int k = tid; k < P; k += nthr) {
+    const uint32_t v = __ldcg(partial + k) & qmask;
+    partial[k] = 0;                                           // ready for the next call
+#pragma unroll
+    for (int r = 0; r < ntru_ctx::kMaxRanks; ++r)
+      if (r < world) peers.window[r][slot + k] = v;           // peer stores travel over NVLink
+  }
+  __syncthreads();
+  if (tid == 0) *ticket = 0;
+  // release at system scope, cumulative over the stores the barrier above ordered before it
+#pragma unroll
+  for (int r = 0; r < ntru_ctx::kMaxRanks; ++r)
+    if (r == tid && r < world) st_release_sys(peers.window[r] + (size_t)2 * world * P + rank, epoch);
+  // ---- gather: wait for every rank's flag in this rank's window, add the slots ----
+  const uint32_t *window = ticket - ((size_t)2 * world * P + world);
+  const uint32_t *flags = window + (size_t)2 * world * P;
+  if (tid < world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + tid) != epoch) {
+      if (clock64() - t0 > 8000000000ll) {                    // ~4 s: a peer never arrived; do not hang the GPU
+        atomicExch(ticket + 1, 1u);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t *slots = window + (size_t)(epoch & 1u) * world * P;
+  for (int k = tid; k < P; k += nthr) {
+    uint32_t s = 0;
+    for (int r = 0; r < world; ++r) s += __ldcv(slots + (size_t)r * P + k);
+    out[k] = k < N ? (uint16_t)(s & qmask) : (uint16_t)0;
+  }
+}
+
 __global__ void k_sum_finalize(const uint32_t *__restrict__ partial, int N, int P, uint32_t qmask,
                                uint16_t *__restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,6 +561,33 @@ int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *par
   {
     LaunchTimer timer(ctx, NTRU_K_SUM);
     k_sum_partial<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, partial);
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+size_t xchg_window_bytes(const ntru_ctx *ctx, int world) {
+  return ((size_t)2 * world * ctx->P + world + 2) * sizeof(uint32_t);
+}
+
+int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
+  const int world = ctx->xchg_world, rank = ctx->xchg_rank;
+  XchgPeers peers = {};
+  for (int r = 0; r < world; ++r) peers.window[r] = (uint32_t *)ctx->peer_window[r];
+  const uint32_t epoch = ++ctx->xchg_epoch;
+  const int VX = ctx->P / 8;
+  const int RY = VX * kSumRows <= 512 ? kSumRows : 512 / VX;
+  dim3 block(VX, RY);
+  const size_t smem = (size_t)VX * RY * 8 * sizeof(uint32_t);
+  size_t blocks = (B + RY - 1) / RY;
+  const size_t cap = (size_t)ctx->sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;                                   // an empty shard still takes part in the exchange
+  {
+    LaunchTimer timer(ctx, NTRU_K_SUM);
+    uint32_t *ticket = (uint32_t *)ctx->peer_window[rank] + (size_t)2 * world * ctx->P + world;
+    k_sum_push<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, (uint32_t *)ctx->d_partial.ptr, peers, ticket, world, rank,
+                                                               epoch, (uint32_t)ctx->q - 1, ctx->N, out);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;

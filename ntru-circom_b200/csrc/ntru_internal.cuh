@@ -59,6 +59,14 @@ struct ntru_ctx {
   ntru::DevBuf slot_bufs[ntru::kNumSlots][10];     // pitched device arrays of the host pipeline
   ntru::DevBuf slot_packed[ntru::kNumSlots][10];   // packed staging (what the 1-D H2D / D2H copies move)
   ntru::DevBuf d_partial;
+  // cross-GPU sum: exchange window (this rank's, cudaMalloc + IPC) and the mapped windows of the peers
+  static constexpr int kMaxRanks = 16;
+  int xchg_world = 1, xchg_rank = 0;
+  bool xchg_connected = false;
+  ntru::DevBuf d_window;           // [2 parities][world][P] uint32 slots, then [world] uint32 flags, then ticket + error word
+  void *peer_window[kMaxRanks] = {};
+  bool peer_opened[kMaxRanks] = {};
+  uint32_t xchg_epoch = 0;
   size_t chunk_rows = 32768;
   int opt_path = 0;
   int umma_attr_set = 0;           // bit per kernel mode: dynamic shared memory attribute applied on this device
@@ -104,6 +112,8 @@ int launch_decrypt_generic(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8
                            uint8_t *r2);
 int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial);
 int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
+size_t xchg_window_bytes(const ntru_ctx *ctx, int world);
+int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
 int launch_repitch(ntru_ctx *ctx, const void *src, void *dst, size_t rows, int width, int elem, bool to_pitched);
 

@@ -192,6 +192,22 @@ class Engine:
     def sum_finalize_dev(self, partial, out):
         self._check(self.lib.ntru_sum_finalize_dev(self._h, _ptr(partial), _ptr(out)))
 
+    # ---- cross-GPU sum over peer memory (include/ntru_b200.h: ntru_xchg_*, ntru_sum_allreduce_dev) ----
+    def xchg_create(self, world: int, rank: int) -> bytes:
+        """Allocates this rank's exchange window; returns its 64-byte CUDA IPC handle (all-gather it)."""
+        buf = (ctypes.c_ubyte * 64)()
+        self._check(self.lib.ntru_xchg_create(self._h, int(world), int(rank), buf))
+        return bytes(buf)
+
+    def xchg_connect(self, handles: bytes):
+        """handles: world x 64 bytes, rank-major."""
+        buf = (ctypes.c_ubyte * len(handles)).from_buffer_copy(handles)
+        self._check(self.lib.ntru_xchg_connect(self._h, buf))
+
+    def sum_allreduce_dev(self, B, e, out):
+        """out[k] = column sums mod q over every rank's rows (local rows only when no exchange is connected)."""
+        self._check(self.lib.ntru_sum_allreduce_dev(self._h, B, _ptr(e) if B else None, _ptr(out)))
+
     def sample_r_dev(self, B, dr, seed, row0, r):
         self._check(self.lib.ntru_sample_r_dev(self._h, B, int(dr), int(seed), int(row0), _ptr(r)))
 

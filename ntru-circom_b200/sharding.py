@@ -33,8 +33,41 @@ def all_reduce_sum_mod_q(local_sums, q: int, group=None):
     return t & (q - 1)
 
 
+def connect_exchange(engine, group=None) -> None:
+    """Sets up the peer-memory exchange of the cross-GPU sum: every rank allocates its window
+    (ntru_xchg_create), the 64-byte CUDA IPC handles are all-gathered over the process group (control
+    plane only), and every rank maps the windows of its peers (ntru_xchg_connect)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        engine.xchg_create(1, 0)
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = engine.xchg_create(world, rank)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t, group=group)
+    engine.xchg_connect(b"".join(bytes(g.cpu().tolist()) for g in gathered))
+    dist.barrier(group=group)
+
+
+def sum_ciphertexts_exchange(engine, e_dev, rows: int, out=None):
+    """Column sums mod q of a sharded batch over the peer-memory exchange (after connect_exchange): local
+    column sums, stores into every peer's window over NVLink, one-CTA gather -- all in the library's kernels."""
+    import torch
+
+    if out is None:
+        out = torch.empty(engine.pitch, dtype=torch.int16, device=e_dev.device)
+    engine.sum_allreduce_dev(rows, e_dev, out)
+    return out
+
+
 def sum_ciphertexts_sharded(engine, e_dev, rows: int, group=None):
-    """Column sums mod q of a sharded batch.  e_dev: this rank's (rows, pitch) uint16/int16 CUDA tensor."""
+    """Column sums mod q of a sharded batch through a library all-reduce (NCCL on GPUs, gloo in the CPU tests);
+    the baseline the peer-memory exchange above is measured against.
+    e_dev: this rank's (rows, pitch) uint16/int16 CUDA tensor."""
     import torch
 
     partial = torch.zeros(engine.pitch, dtype=torch.int32, device=e_dev.device)

@@ -252,6 +252,33 @@ def test_sum_many_rows(nb, engines):
     assert np.array_equal((a.astype(np.int64) + b) % 8192, want)
 
 
+@pytest.mark.parametrize("cfg", ["default167", "hrss701"])
+def test_sum_over_exchange_window_single_rank(cfg, nb, golden):
+    """ntru_sum_allreduce_dev with a world of one rank (the exchange window is this GPU's own memory): the fused
+    column-sum + push kernel and the gather kernel against the oracle fold, repeated calls (both slot parities,
+    re-zeroed partials), ragged and empty shards.  The multi-rank path is scripts/bench_multi.py (gpurun --gpus N)."""
+    torch = pytest.importorskip("torch")
+    from ntru_circom_b200 import sharding
+    g = golden(cfg)
+    N, q = int(g["N"]), int(g["q"])
+    eng = nb.Engine(N, 3, q, 0)
+    sharding.connect_exchange(eng)
+    rng = np.random.default_rng(8)
+    P = eng.pitch
+    for rows in (5003, 1, 0, 20011, 777):
+        e = rng.integers(0, q, size=(rows, N), dtype=np.uint16)
+        ed = torch.zeros((max(rows, 1), P), dtype=torch.int16, device="cuda")
+        if rows:
+            ed[:rows, :N] = torch.from_numpy(e.astype(np.int16)).cuda()
+        out = sharding.sum_ciphertexts_exchange(eng, ed, rows)
+        eng.sync()
+        got = out.cpu().numpy().astype(np.uint16)
+        want = o.sum_batch(e, q) if rows else np.zeros(N, dtype=np.int64)
+        assert np.array_equal(got[:N], want), (cfg, rows)
+        assert not got[N:].any()
+    eng.close()
+
+
 def test_device_sampler_matches_host_fisher_yates(nb, engines):
     torch = pytest.importorskip("torch")
     eng = engines("hps509")
