@@ -305,10 +305,11 @@ def run_ours(args, rank, world, local_rank):
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
     except OSError:
         prof = {"bytes_per_ciphertext": {}, "int8_peak_tops": None}
-    alg_bytes = {"enc_tensor": 6 * N, "dec1_tensor": 6 * N, "dec2_tensor": 2 * N, "enc_core": 6 * N, "dec_core": 8 * N}
+    alg_bytes = {"enc_tensor": 6 * N, "dec1_tensor": 6 * N, "dec2_tensor": 2 * N, "enc_core": 6 * N, "dec_core": 8 * N,
+                 "enc_imma": 6 * N, "dec_imma": 8 * N}
     limbs = 2 if q > 256 else 1
     alg_ops = {"enc_tensor": 2 * N * N * limbs, "dec1_tensor": 2 * N * N * limbs, "dec2_tensor": 2 * N * N,
-               "enc_core": 2 * N * N, "dec_core": 4 * N * N}
+               "enc_core": 2 * N * N, "dec_core": 4 * N * N, "enc_imma": 2 * N * N * limbs, "dec_imma": 2 * N * N * (limbs + 1)}
     kernels = {}
     for name, (tot, n) in kt.items():
         if name not in alg_bytes:
@@ -338,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": WORKLOAD.format(rows=B), "rows_per_gpu": B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "inputs+outputs per step (7 GB at 1M rows) exceed the 126 MB L2; no flush needed",
-                   "schedule": {0: "auto", 1: "cuda-core", 2: "tcgen05"}[args.path], "key": "tests/golden/hps509.npz"},
+                   "schedule": {0: "auto", 1: "cuda-core", 2: "tcgen05", 3: "imma"}[args.path], "key": "tests/golden/hps509.npz"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extras": extras,
     }
     if not args.no_cpu:
@@ -357,7 +358,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000, help="ciphertexts per GPU per step")
     ap.add_argument("--e2e-rows", type=int, default=262_144)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 CUDA-core schedule, 2 tcgen05 schedule")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 fp32 CUDA-core schedule, 2 tcgen05 schedule, 3 register-fragment IMMA schedule")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

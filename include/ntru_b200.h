@@ -68,7 +68,8 @@ enum {
   NTRU_K_OTHER = 6,         /* sampler, finalize, key-matrix build */
   NTRU_K_ENC_IMMA = 7,      /* mma.sync (IMMA) encrypt, one warp per ciphertext: distinct keys */
   NTRU_K_DEC_IMMA = 8,      /* mma.sync (IMMA) decrypt (both products) */
-  NTRU_K_COUNT = 9
+  NTRU_K_MULDIV = 9,        /* mma.sync (IMMA) multiply + divide by 1 - x^N (verifyKeysInputs products) */
+  NTRU_K_COUNT = 10
 };
 
 /* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 32768], 8 <= N <= 1024. */
@@ -113,6 +114,20 @@ int ntru_decrypt_batch(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *valu
 int ntru_decrypt_batch_keys(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, const uint16_t *e,
                             uint8_t *value, uint16_t *quotient1, uint16_t *remainder1,
                             uint8_t *quotient2, uint8_t *remainder2);
+
+/* verifyKeysInputs, B keys at once -- index.js:141-197: the three multiplyPolynomials + dividePolynomials(., I, .)
+ * pairs behind the VerifyInverse witness (circuits/ntru.circom:242-256):
+ *   fq case: (fq * f) / I mod q      fp case: (fp * f) / I mod p      h case: ((p fq) * g) / I mod q
+ * f, g: B x N ternary in {-1,0,1}; fq: B x N in [0,q); fp: B x N in [0,p).  Outputs are N+1 entries per row
+ * (quotientI / remainderI of each case); any output may be NULL.  The echoed inputs of the witness (f with -1 as
+ * q-1 or p-1, fq, fp, p*fq un-reduced) and the reference's validity checks are the wrapper's concern. */
+int ntru_verify_keys_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const uint16_t *fq, const uint8_t *fp, const int8_t *g,
+                           uint16_t *quotient_fq, uint16_t *remainder_fq, uint8_t *quotient_fp, uint8_t *remainder_fp,
+                           uint16_t *quotient_h, uint16_t *remainder_h);
+/* the primitive, device-resident: multiplyPolynomials(x, y, mod) then dividePolynomials(., 1 - x^N, mod) for B
+ * independent pairs.  x: int8 in [-1, 2]; mod_p == 0: y uint16 (any value), outputs uint16 mod q;
+ * mod_p != 0: y bytes in [0, p), outputs bytes mod p.  Pitch ntru_pitch() elements everywhere. */
+int ntru_muldiv_dev(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quotient, void *remainder);
 
 /* fold of addPolynomials(.,.,q) over B ciphertexts -- index.js:235-244, test/reference.test.js:58.  out: N entries */
 int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);

@@ -468,6 +468,61 @@ int ntru_decrypt_batch_keys(ntru_ctx *ctx, size_t B, const int8_t *f, const uint
   return decrypt_host(ctx, B, f, fp, e, value, quotient1, remainder1, quotient2, remainder2);
 }
 
+__global__ void k_scale_u16(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, size_t n, uint32_t mul) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (uint16_t)(src[i] * mul);
+}
+
+int ntru_muldiv_dev(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quotient, void *remainder) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (B > 0 && (!x || !y)) return fail(ctx, NTRU_E_PARAM, "x and y are required");
+  if (!ctx->tensor_ok) return fail(ctx, NTRU_E_UNSUPPORTED, "multiply + divide needs the sm_100 tensor path");
+  return launch_muldiv_imma(ctx, B, x, y, mod_p, quotient, remainder);
+}
+
+int ntru_verify_keys_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const uint16_t *fq, const uint8_t *fp, const int8_t *g,
+                           uint16_t *quotient_fq, uint16_t *remainder_fq, uint8_t *quotient_fp, uint8_t *remainder_fp,
+                           uint16_t *quotient_h, uint16_t *remainder_h) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (!f || !fq || !fp || !g) return fail(ctx, NTRU_E_PARAM, "f, fq, fp and g are required");
+  if (!ctx->tensor_ok) return fail(ctx, NTRU_E_UNSUPPORTED, "verify_keys needs the sm_100 tensor path");
+  if (B == 0) return NTRU_OK;
+  const size_t N = (size_t)ctx->N;
+  HostArr arr[kMaxArr];
+  set_in(arr[0], f, 1, N);
+  set_in(arr[1], fq, 2, N);
+  set_in(arr[2], fp, 1, N);
+  set_in(arr[3], g, 1, N);
+  set_out(arr[4], quotient_fq, 2, N + 1);
+  set_out(arr[5], remainder_fq, 2, N + 1);
+  set_out(arr[6], quotient_fp, 1, N + 1);
+  set_out(arr[7], remainder_fp, 1, N + 1);
+  set_out(arr[8], quotient_h, 2, N + 1);
+  set_out(arr[9], remainder_h, 2, N + 1);
+  return run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
+    int r2 = NTRU_OK;
+    if (dev[4] || dev[5]) r2 = launch_muldiv_imma(ctx, rows, (const int8_t *)dev[0], dev[1], 0, dev[4], dev[5]);
+    if (r2) return r2;
+    // fp case: x = f (the value p-1 of a -1 is the same residue), y = fp
+    if (dev[6] || dev[7]) r2 = launch_muldiv_imma(ctx, rows, (const int8_t *)dev[0], dev[2], 1, dev[6], dev[7]);
+    if (r2) return r2;
+    if (dev[8] || dev[9]) {
+      // h case: y = p * fq, NOT reduced mod q (index.js:155); 3 * (q - 1) < 65536 for q <= 16384
+      NTRU_CUDA(ctx, ctx->d_b.reserve(rows * (size_t)ctx->P * 2));
+      {
+        LaunchTimer timer(ctx, NTRU_K_OTHER);
+        k_scale_u16<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((const uint16_t *)dev[1], (uint16_t *)ctx->d_b.ptr,
+                                                               rows * (size_t)ctx->P, (uint32_t)ctx->p);
+      }
+      NTRU_CUDA(ctx, cudaGetLastError());
+      r2 = launch_muldiv_imma(ctx, rows, (const int8_t *)dev[3], ctx->d_b.ptr, 0, dev[8], dev[9]);
+    }
+    return r2;
+  });
+}
+
 int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
   int rc = check(ctx);
   if (rc) return rc;

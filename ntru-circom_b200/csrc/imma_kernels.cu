@@ -397,6 +397,90 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_decrypt_imma(const ImmaDecA
   }
 }
 
+// ---- multiplyPolynomials(a, b, mod) + dividePolynomials(., 1 - x^N, mod) for B independent pairs -----------------
+// The primitive under verifyKeysInputs (index.js:141-197): (f, fq) and (g, p * fq) modulo q, (f mod p, fp) modulo p.
+// x is the small operand (int8 in [-1, 2]; the witness value q-1 or p-1 of a -1 is the wrapper's concern: the
+// product is the same modulo q or p), y the wide one: uint16 (any value: p * fq is NOT reduced mod q, index.js:155)
+// in mod-q mode, one byte in mod-p mode.
+struct ImmaMulDivArgs {
+  ImmaGeom G;
+  size_t B;
+  const int8_t *x;
+  const void *y;
+  void *quo, *rem;      // uint16 (mod q) or uint8 (mod p), pitch P
+};
+
+template <int NJ, bool kModP>
+__global__ void __launch_bounds__(kImmaWarps * 32) k_muldiv_imma(const ImmaMulDivArgs a) {
+  constexpr int LIMBS = kModP ? 1 : 2;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const ImmaGeom &G = a.G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
+  uint8_t *y0 = base, *y1 = base + G.Ly, *xb = base + 2 * G.Ly;
+  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 2 * G.Ly + G.Lx);
+  uint8_t *raw = base + 2 * G.Ly + G.Lx + G.Lc;       // [y: 2P or P][x: P] of the NEXT row (cp.async)
+  for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const uint32_t Q2 = G.qmask | (G.qmask << 16);
+  const int ybytes = kModP ? G.P : 2 * G.P;
+  const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
+  auto prefetch = [&](size_t row) {
+    prefetch_row(raw, reinterpret_cast<const uint8_t *>(a.y) + row * (size_t)ybytes, ybytes, lane);
+    prefetch_row(raw + 2 * G.P, a.x + row * (size_t)G.P, G.P, lane);
+    prefetch_commit();
+  };
+  size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
+  if (row < a.B) prefetch(row);
+  for (; row < a.B; row += nwarps) {
+    prefetch_wait();
+    if (kModP) stage_y8(G, raw, y0, lane);
+    else stage_y16<2>(G, reinterpret_cast<const uint16_t *>(raw), y0, y1, lane);
+    stage_x8(G, raw + 2 * G.P, xb, lane);
+    __syncwarp();
+    if (row + nwarps < a.B) prefetch(row + nwarps);
+    {
+      int acc[NJ][LIMBS][4];
+      conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
+      store_product<NJ, LIMBS>(G, lane, acc, cbuf);
+    }
+    __syncwarp();
+    const size_t rbase = row * (size_t)G.P;
+    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+      uint32_t lo[4], hi[4];
+      load_lo_hi(G, cbuf, k0, lo, hi);
+      if (kModP) {
+        uint32_t rem[2] = {0, 0}, quo[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // x may hold -1: the 16-bit product is then c mod 65536 with c in (-2N, 4N); 65536 = 1 (mod 3), so the
+          // representative c + 65536 keeps the residue up to that 1, which is removed again for negative c
+          const uint32_t lw = (lo[i >> 1] >> (16 * (i & 1))) & 0xffffu, hw = (hi[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+          const uint32_t l3 = mod3_16(lw + (lw >> 15) * 2u);
+          const uint32_t h3 = mod3_16(hw + (hw >> 15) * 2u);
+          const bool in = k0 + i < G.N;
+          rem[i >> 2] |= (in ? mod3_16(l3 + h3) : 0u) << (8 * (i & 3));
+          quo[i >> 2] |= (in ? mod3_16(3u - h3) : 0u) << (8 * (i & 3));
+        }
+        if (a.rem) *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.rem) + rbase + k0) = make_uint2(rem[0], rem[1]);
+        if (a.quo) *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.quo) + rbase + k0) = make_uint2(quo[0], quo[1]);
+      } else {
+        uint32_t rem[4], quo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rem[i] = ((lo[i] & Q2) + (hi[i] & Q2)) & Q2;
+          quo[i] = ((~hi[i] & Q2) + 0x00010001u) & Q2;
+        }
+        mask_lanes(rem, G.N - k0);
+        mask_lanes(quo, G.N - k0);
+        if (a.rem) *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(a.rem) + rbase + k0) = make_uint4(rem[0], rem[1], rem[2], rem[3]);
+        if (a.quo) *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(a.quo) + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays, int nj_bucket) {
   ImmaGeom G;
   G.N = ctx->N; G.P = ctx->P; G.q = ctx->q; G.logq = ctx->logq; G.qmask = (uint32_t)ctx->q - 1;
@@ -457,6 +541,25 @@ bool imma_supported(const ntru_ctx *ctx) {
     if (nj <= 11) return two ? launch_imma(ctx, KERNEL<11, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<11, 1>, ARGS, KIND, B, 0); \
     return two ? launch_imma(ctx, KERNEL<13, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<13, 1>, ARGS, KIND, B, 0);              \
   } while (0)
+
+int launch_muldiv_imma(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quo, void *rem) {
+  if (B == 0) return NTRU_OK;
+  if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
+  ImmaMulDivArgs a;
+  a.G = make_geom(ctx, 2, imma_bucket(ctx));
+  a.B = B; a.x = x; a.y = y; a.quo = quo; a.rem = rem;
+  const int nj = a.G.NJ;
+  if (mod_p) {
+    if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, true>, a, NTRU_K_MULDIV, B, 0);
+    if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, true>, a, NTRU_K_MULDIV, B, 0);
+    if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, true>, a, NTRU_K_MULDIV, B, 0);
+    return launch_imma(ctx, k_muldiv_imma<13, true>, a, NTRU_K_MULDIV, B, 0);
+  }
+  if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, false>, a, NTRU_K_MULDIV, B, 0);
+  if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, false>, a, NTRU_K_MULDIV, B, 0);
+  if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, false>, a, NTRU_K_MULDIV, B, 0);
+  return launch_imma(ctx, k_muldiv_imma<13, false>, a, NTRU_K_MULDIV, B, 0);
+}
 
 int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r, const uint8_t *m,
                         uint16_t *value, uint16_t *quo, uint16_t *rem) {

@@ -124,6 +124,8 @@ int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_str
 int launch_decrypt_imma(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, size_t key_stride, const uint16_t *e,
                         uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2);
 
+int launch_muldiv_imma(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quo, void *rem);
+
 // ---- tcgen05 schedule (umma_kernels.cu) ----
 int umma_init(ntru_ctx *ctx);                    // probes the device, sets ctx->tensor_ok
 int umma_prepare_public(ntru_ctx *ctx);          // builds km_h from d_h

@@ -167,6 +167,27 @@ class Engine:
         self._check(rc)
         return {"value": value, "quotient1": q1, "remainder1": r1, "quotient2": q2, "remainder2": r2}
 
+    def verify_keys_batch(self, f, fq, fp, g):
+        """verifyKeysInputs (index.js:141-197) for B keys: the quotientI / remainderI of the three
+        multiply + divide-by-(1 - x^N) pairs (fq case and h case mod q, fp case mod p)."""
+        N = self.N
+        f = np.ascontiguousarray(f, dtype=np.int8)
+        B = f.shape[0]
+        f = _host(f, np.int8, (B, N))
+        fq = _host(fq, np.uint16, (B, N))
+        fp = _host(fp, np.uint8, (B, N))
+        g = _host(g, np.int8, (B, N))
+        out = {k: np.empty((B, N + 1), dtype=np.uint8 if k.endswith("_fp") else np.uint16)
+               for k in ("quotient_fq", "remainder_fq", "quotient_fp", "remainder_fp", "quotient_h", "remainder_h")}
+        self._check(self.lib.ntru_verify_keys_batch(self._h, B, _ptr(f), _ptr(fq), _ptr(fp), _ptr(g),
+                                                    *[_ptr(out[k]) for k in ("quotient_fq", "remainder_fq", "quotient_fp",
+                                                                             "remainder_fp", "quotient_h", "remainder_h")]))
+        return out
+
+    def muldiv_dev(self, B, x, y, mod_p, quotient=None, remainder=None):
+        """multiplyPolynomials(x, y, mod) + dividePolynomials(., 1 - x^N, mod), device-resident rows."""
+        self._check(self.lib.ntru_muldiv_dev(self._h, B, _ptr(x), _ptr(y), int(bool(mod_p)), _ptr(quotient), _ptr(remainder)))
+
     def sum(self, e):
         e = np.ascontiguousarray(e, dtype=np.uint16)
         B = e.shape[0]

@@ -222,13 +222,20 @@ class NTRU:
         fq, fp = self.fq, self.fp
         fqp = [x * p for x in fq]
         g = [q - 1 if x == -1 else x for x in self.g]
-        fqDiv = poly.dividePolynomials(poly.multiplyPolynomials(fq, fmodq, q), self.I, q)
+        # the three multiplyPolynomials + dividePolynomials(., I, .) pairs (index.js:158-166) run on the GPU
+        # (ntru_verify_keys_batch); trimming and the reference's checks stay here
+        ex0 = lambda a: poly.expandArray(a, N, 0)   # noqa: E731
+        if any(abs(int(x)) > 1 for x in self.f) or any(abs(int(x)) > 1 for x in self.g):
+            raise NtruError(-7, "the engine needs ternary f and g in {-1,0,1}")
+        gpu = self.engine().verify_keys_batch(np.array([ex0(self.f)], dtype=np.int8), np.array([ex0(fq)], dtype=np.uint16),
+                                              np.array([ex0(fp)], dtype=np.uint8), np.array([ex0(self.g)], dtype=np.int8))
+        div = lambda c: {"quotient": poly.trimPolynomial([int(x) for x in gpu["quotient_" + c][0]]),   # noqa: E731
+                         "remainder": poly.trimPolynomial([int(x) for x in gpu["remainder_" + c][0]])}
+        fqDiv, fpDiv, hDiv = div("fq"), div("fp"), div("h")
         if len(fqDiv["remainder"]) != 1 and fqDiv["remainder"][0] != 1:
             raise ValueError("invalid fq")
-        fpDiv = poly.dividePolynomials(poly.multiplyPolynomials(fp, fmodp, p), self.I, p)
         if len(fpDiv["remainder"]) != 1 and fpDiv["remainder"][0] != 1:
             raise ValueError("invalid fp")
-        hDiv = poly.dividePolynomials(poly.multiplyPolynomials(fqp, g, q), self.I, q)
         if any((hDiv["remainder"][i] if i < len(hDiv["remainder"]) else None) != cur for i, cur in enumerate(self.h)):
             raise ValueError("invalid h")
         ex = poly.expandArray

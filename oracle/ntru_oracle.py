@@ -422,6 +422,29 @@ class NTRU:
         p_fq_g = self._mul(p_fq, self.g, self.q)
         self.h = trim_polynomial(self._div_I(p_fq_g, self.I, self.q)["remainder"])
 
+    def verifyKeysInputs(self) -> dict:
+        """index.js:141-197: the VerifyInverse witness for the fq, fp and h cases."""
+        for name, label in (("f", "private key F"), ("fq", "private key Fq"), ("fp", "private key Fp"),
+                            ("g", "private key G")):
+            if not getattr(self, name):
+                raise ValueError(f"missing {label}")
+        if not self.h:
+            raise ValueError("missing public key H")
+        q, p, N = self.q, self.p, self.N
+        fmodq = [q - 1 if x == -1 else x for x in self.f]
+        fmodp = [p - 1 if x == -1 else x for x in self.f]
+        fqp = [x * p for x in self.fq]                       # index.js:155: NOT reduced mod q
+        g = [q - 1 if x == -1 else x for x in self.g]
+        fq_div = self._div_I(self._mul(self.fq, fmodq, q), self.I, q)
+        fp_div = self._div_I(self._mul(self.fp, fmodp, p), self.I, p)
+        h_div = self._div_I(self._mul(fqp, g, q), self.I, q)
+        case = lambda mod, nbits, a, b, d: {"params": [mod, nbits, N], "inputs": {       # noqa: E731
+            "f": expand_array(a, N, 0), "fq": expand_array(b, N, 0),
+            "quotientI": expand_array(d["quotient"], N + 1, 0), "remainderI": expand_array(d["remainder"], N + 1, 0)}}
+        return {"fq": case(q, self.calculateNq(), fmodq, self.fq, fq_div),
+                "fp": case(p, self.calculateNp(), fmodp, self.fp, fp_div),
+                "h": case(q, self.calculateNq(), g, fqp, h_div)}
+
     def key_is_valid(self) -> bool:
         """f*fq == 1 (mod q, x^N-1) and f*fp == 1 (mod p, x^N-1) -- what the reference *meant* to check."""
         N = self.N
@@ -634,6 +657,19 @@ def verify_decrypt(inputs: dict, params: Sequence[int]) -> bool:
     c = np.mod(np.convolve(fp, b), p)
     I[N] = p - 1
     return _verify_divide(c, I, inputs["quotient2"], inputs["remainder2"], p)
+
+
+def verify_inverse(inputs: dict, params: Sequence[int]) -> bool:
+    """VerifyInverse(q, nq, N) -- ntru.circom:242-256 (q is the case's modulus: q for fq / h, p for fp)."""
+    q, _nq, N = params
+    f = np.asarray(inputs["f"], dtype=np.int64)
+    fq = np.asarray(inputs["fq"], dtype=np.int64)
+    if not (len(f) == len(fq) == N):
+        return False
+    a = np.mod(np.convolve(f, fq), q)
+    I = np.zeros(N + 1, dtype=np.int64)
+    I[0], I[N] = 1, q - 1
+    return _verify_divide(a, I, inputs["quotientI"], inputs["remainderI"], q)
 
 
 # ----------------------------------------------------------------------------

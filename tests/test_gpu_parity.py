@@ -146,6 +146,39 @@ def test_distinct_keys(cfg, nb, engines, golden):
         assert np.array_equal(want_d["value"][:nvalid], m[:nvalid])   # valid keys round-trip
 
 
+@pytest.mark.parametrize("cfg", CFGS)
+def test_verify_keys_inputs_vs_oracle(cfg, nb, engines, golden):
+    """verifyKeysInputs (index.js:141-197).  The class API against the oracle's restatement field by field
+    (and the VerifyInverse constraint checker, ntru.circom:242-256), then the batched entry point on valid keys plus
+    random / extreme operands against the oracle's multiply + divide."""
+    g, eng = golden(cfg), engines(cfg)
+    N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
+    keys = [o.make_key(cfg, 200 + i) for i in range(3)]
+    k = keys[0]
+    mine = nb.NTRU(dict(o.CONFIGS[cfg]), f=list(k.f), fq=list(k.fq), fp=list(k.fp), g=list(k.g), h=list(k.h))
+    got, want = mine.verifyKeysInputs(), k.verifyKeysInputs()
+    assert got == want
+    for case in ("fq", "fp", "h"):
+        assert o.verify_inverse(got[case]["inputs"], got[case]["params"]), case
+    rng = np.random.default_rng(17)
+    B = 3 + 70
+    f = np.zeros((B, N), dtype=np.int64); fq = np.zeros((B, N), dtype=np.int64)
+    fp = np.zeros((B, N), dtype=np.int64); gg = np.zeros((B, N), dtype=np.int64)
+    for i, kk in enumerate(keys):
+        f[i], fq[i], fp[i], gg[i] = kk.f, o.expand_array(kk.fq, N, 0), o.expand_array(kk.fp, N, 0), kk.g
+    f[3:] = rng.integers(-1, 2, size=(B - 3, N)); gg[3:] = rng.integers(-1, 2, size=(B - 3, N))
+    fq[3:] = rng.integers(0, q, size=(B - 3, N)); fp[3:] = rng.integers(0, p, size=(B - 3, N))
+    f[4], gg[4], fq[4], fp[4] = -1, -1, q - 1, p - 1         # most negative products
+    f[5], gg[5], fq[5], fp[5] = 1, 1, q - 1, p - 1           # largest products (3 (q-1) un-reduced in the h case)
+    out = eng.verify_keys_batch(f.astype(np.int8), fq.astype(np.uint16), fp.astype(np.uint8), gg.astype(np.int8))
+    for i in list(range(8)) + [B - 1]:
+        for case, a, b, mod in (("fq", fq[i], f[i], q), ("fp", fp[i], f[i], p), ("h", fq[i] * p, gg[i], q)):
+            # the reference multiplies by the witness value of a -1 (q-1 / p-1, index.js:151-156)
+            d = o.divide_by_I_closed(o.multiply_polynomials_exact(list(map(int, a)), [mod - 1 if x == -1 else int(x) for x in b], mod), N, mod)
+            assert out["quotient_" + case][i].tolist() == o.expand_array(d["quotient"], N + 1, 0), (cfg, i, case)
+            assert out["remainder_" + case][i].tolist() == o.expand_array(d["remainder"], N + 1, 0), (cfg, i, case)
+
+
 def test_empty_batch_and_errors(nb, engines):
     eng = engines("default167")
     z8 = np.zeros((0, 167), dtype=np.uint8)

@@ -97,10 +97,21 @@ def test_host_keygen_matches_oracle(cfg):
     mine.generateNewPublicKeyGH()
     assert (mine.f, mine.fq, mine.fp, mine.g, mine.h) == (ref.f, ref.fq, ref.fp, ref.g, ref.h)
     assert mine.calculateNq() == ref.calculateNq() and mine.calculateNp() == ref.calculateNp()
-    w = mine.verifyKeysInputs()
-    assert w["fq"]["inputs"]["remainderI"] == [1] + [0] * mine.N
-    assert w["fp"]["inputs"]["remainderI"] == [1] + [0] * mine.N
-    assert w["h"]["inputs"]["remainderI"][: len(mine.h)] == mine.h
+    # the oracle's verifyKeysInputs (index.js:141-197) satisfies the VerifyInverse constraints (ntru.circom:242-256)
+    w = ref.verifyKeysInputs()
+    assert w["fq"]["inputs"]["remainderI"] == [1] + [0] * ref.N
+    assert w["fp"]["inputs"]["remainderI"] == [1] + [0] * ref.N
+    assert w["h"]["inputs"]["remainderI"][: len(ref.h)] == ref.h
+    for case in ("fq", "fp", "h"):
+        assert o.verify_inverse(w[case]["inputs"], w[case]["params"]), case
+        bad = {k: list(v) for k, v in w[case]["inputs"].items()}
+        bad["remainderI"][0] = (bad["remainderI"][0] + 1) % w[case]["params"][0]
+        assert not o.verify_inverse(bad, w[case]["params"]), case
+    # the product's verifyKeysInputs runs its three products on the GPU: without a device it must fail loudly
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(nb.NtruError):
+            mine.verifyKeysInputs()
 
 
 def test_constructor_defaults_and_errors():
