@@ -69,7 +69,8 @@ enum {
   NTRU_K_ENC_IMMA = 7,      /* mma.sync (IMMA) encrypt, one warp per ciphertext: distinct keys */
   NTRU_K_DEC_IMMA = 8,      /* mma.sync (IMMA) decrypt (both products) */
   NTRU_K_MULDIV = 9,        /* mma.sync (IMMA) multiply + divide by 1 - x^N (verifyKeysInputs products) */
-  NTRU_K_COUNT = 10
+  NTRU_K_PACK = 10,         /* packOutput / unpackInput bit packing */
+  NTRU_K_COUNT = 11
 };
 
 /* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 32768], 8 <= N <= 1024. */
@@ -128,6 +129,21 @@ int ntru_verify_keys_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const uint1
  * independent pairs.  x: int8 in [-1, 2]; mod_p == 0: y uint16 (any value), outputs uint16 mod q;
  * mod_p != 0: y bytes in [0, p), outputs bytes mod p.  Pitch ntru_pitch() elements everywhere. */
 int ntru_muldiv_dev(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quotient, void *remainder);
+
+/* packOutput / unpackInput -- index.js:572-620: coefficients <-> BN254 field elements (CombineArray / UnpackArray,
+ * circuits/ntru.circom:259-306).  A field element is 32 bytes, little-endian.
+ * ntru_pack_geometry is packOutput's header: maxInputBits = floor(log2(maxVal) + 1), n = floor(252 / maxInputBits),
+ * arrLen = max(ceil(dataLen / n) n, 3 n), outputSize = max(ceil(arrLen / n), 3). */
+int ntru_pack_geometry(uint32_t max_val, int data_len, int *max_input_bits, int *inputs_per_output, int *arr_len,
+                       int *output_size);
+/* data: B rows of data_len coefficients (elem_bytes 1 or 2, row pitch `pitch` elements), every value < 2^maxInputBits;
+ * out: B x outputSize x 32 bytes.  Device pointers, asynchronous on the context's stream. */
+int ntru_pack_output_dev(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch,
+                         uint32_t max_val, void *out);
+/* data: B x n_elems field elements; out: B rows of floor(packed_bits / maxInputBits) * n_elems coefficients
+ * (un-trimmed), row pitch `pitch` elements */
+int ntru_unpack_input_dev(ntru_ctx *ctx, size_t B, const void *data, int n_elems, uint32_t max_val, int packed_bits,
+                          void *out, int elem_bytes, size_t pitch);
 
 /* fold of addPolynomials(.,.,q) over B ciphertexts -- index.js:235-244, test/reference.test.js:58.  out: N entries */
 int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);

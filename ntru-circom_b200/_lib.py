@@ -17,7 +17,7 @@ NTRU_E_PARAM, NTRU_E_LENGTH, NTRU_E_NOKEY, NTRU_E_CUDA = -1, -2, -3, -4
 NTRU_E_NCCL, NTRU_E_NOMEM, NTRU_E_UNSUPPORTED = -5, -6, -7
 NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING, NTRU_OPT_TENSOR_VARIANT = 1, 2, 3, 4
 KERNEL_KINDS = ["enc_tensor", "dec1_tensor", "dec2_tensor", "enc_core", "dec_core", "sum", "other", "enc_imma", "dec_imma",
-                "muldiv"]
+                "muldiv", "pack"]
 PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR, PATH_IMMA = 0, 1, 2, 3
 
 #: every symbol include/ntru_b200.h declares: name -> (restype, argtypes)
@@ -41,6 +41,9 @@ SYMBOLS = {
     "ntru_decrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "ntru_decrypt_batch_keys": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ntru_sum": (c_int, [_P, c_size_t, _P, _P]),
+    "ntru_pack_geometry": (c_int, [ctypes.c_uint32, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "ntru_pack_output_dev": (c_int, [_P, c_size_t, _P, c_int, c_int, c_size_t, ctypes.c_uint32, _P]),
+    "ntru_unpack_input_dev": (c_int, [_P, c_size_t, _P, c_int, ctypes.c_uint32, c_int, _P, c_int, c_size_t]),
     "ntru_verify_keys_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ntru_muldiv_dev": (c_int, [_P, c_size_t, _P, _P, c_int, _P, _P]),
     "ntru_encrypt_dev": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),

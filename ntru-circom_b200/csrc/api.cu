@@ -523,6 +523,54 @@ int ntru_verify_keys_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const uint1
   });
 }
 
+static int bit_length(uint32_t v) {   // floor(log2(v) + 1) for v >= 1 (index.js:573, 601)
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b;
+}
+
+int ntru_pack_geometry(uint32_t max_val, int data_len, int *max_input_bits, int *inputs_per_output, int *arr_len,
+                       int *output_size) {
+  if (max_val == 0 || data_len < 0) return NTRU_E_PARAM;
+  const int bits = bit_length(max_val);
+  const int n = 252 / bits;
+  int arr = ((data_len + n - 1) / n) * n;
+  if (arr < 3 * n) arr = 3 * n;
+  int outs = (arr + n - 1) / n;
+  if (outs < 3) outs = 3;
+  if (max_input_bits) *max_input_bits = bits;
+  if (inputs_per_output) *inputs_per_output = n;
+  if (arr_len) *arr_len = arr;
+  if (output_size) *output_size = outs;
+  return NTRU_OK;
+}
+
+int ntru_pack_output_dev(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch,
+                         uint32_t max_val, void *out) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  int bits, n, arr, outs;
+  if (ntru_pack_geometry(max_val, data_len, &bits, &n, &arr, &outs) != NTRU_OK || (elem_bytes != 1 && elem_bytes != 2))
+    return fail(ctx, NTRU_E_PARAM, "bad maxVal / dataLen / element size");
+  if (bits > 8 * elem_bytes + 16) return fail(ctx, NTRU_E_PARAM, "maxVal does not fit the element type");
+  if (B > 0 && (!data || !out)) return fail(ctx, NTRU_E_PARAM, "data and out are required");
+  return launch_pack_fields(ctx, B, data, elem_bytes, data_len, pitch, bits, n, outs, (uint32_t *)out);
+}
+
+int ntru_unpack_input_dev(ntru_ctx *ctx, size_t B, const void *data, int n_elems, uint32_t max_val, int packed_bits,
+                          void *out, int elem_bytes, size_t pitch) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (max_val == 0 || n_elems < 0 || packed_bits < 1 || packed_bits > 256 || (elem_bytes != 1 && elem_bytes != 2))
+    return fail(ctx, NTRU_E_PARAM, "bad maxVal / packedBits / element size");
+  const int bits = bit_length(max_val);
+  const int n = packed_bits / bits;
+  if (n < 1) return fail(ctx, NTRU_E_PARAM, "packedBits is smaller than one coefficient");
+  if (bits > 8 * elem_bytes) return fail(ctx, NTRU_E_PARAM, "maxVal does not fit the element type");
+  if (B > 0 && (!data || !out)) return fail(ctx, NTRU_E_PARAM, "data and out are required");
+  return launch_unpack_fields(ctx, B, (const uint32_t *)data, n_elems, bits, n, pitch, out, elem_bytes);
+}
+
 int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
   int rc = check(ctx);
   if (rc) return rc;

@@ -465,6 +465,54 @@ __global__ void __launch_bounds__(kSampleRows) k_sample_r(int N, int P, int dr, 
 
 }  // namespace
 
+// ---- packOutput / unpackInput (index.js:572-620): coefficients <-> BN254 field elements ---------------------------
+// packOutput puts n = floor(252 / bits) coefficients of `bits` bits each into one field element, little-endian in the
+// bit string: element o = sum_j data[o n + j] << (j bits).  A field element is stored as 32 bytes, little-endian
+// (eight uint32 words).  One thread per output word: it gathers the (at most 32 / bits + 2) coefficients that
+// overlap its 32 bits.  Values must fit `bits` bits (the reference adds BigInts, so larger values would carry).
+template <typename T>
+__global__ void k_pack_fields(const T *__restrict__ data, size_t B, int data_len, size_t pitch, int bits, int n,
+                              int out_elems, uint32_t *__restrict__ out) {
+  const size_t total = B * (size_t)out_elems * 8;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx & 7);
+    const size_t eo = idx >> 3;
+    const int o = (int)(eo % out_elems);
+    const size_t row = eo / out_elems;
+    const int bit0 = 32 * w;                       // first bit of this word inside the element
+    uint32_t word = 0;
+    if (bit0 < n * bits) {
+      const int j0 = bit0 / bits;
+      for (int j = j0; j < n && j * bits < bit0 + 32; ++j) {
+        const int i = o * n + j;
+        const uint32_t v = i < data_len ? (uint32_t)data[row * pitch + i] : 0u;
+        const int sh = j * bits - bit0;            // position of the coefficient's bit 0 relative to this word
+        word |= sh >= 0 ? (v << sh) : (v >> (-sh));
+      }
+    }
+    out[idx] = word;
+  }
+}
+
+// unpackInput: coefficient (i, j) = (element i >> (j bits)) & mask, n = floor(packedBits / bits) per element
+template <typename T>
+__global__ void k_unpack_fields(const uint32_t *__restrict__ data, size_t B, int in_elems, int bits, int n, size_t pitch,
+                                T *__restrict__ out) {
+  const size_t per_row = (size_t)in_elems * n;
+  const size_t total = B * per_row;
+  const uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / per_row;
+    const int k = (int)(idx % per_row);
+    const int i = k / n, j = k % n;
+    const uint32_t *el = data + (row * in_elems + i) * 8;
+    const int bit0 = j * bits, w = bit0 >> 5, sh = bit0 & 31;
+    uint64_t two = el[w];
+    if (w + 1 < 8) two |= (uint64_t)el[w + 1] << 32;
+    out[row * pitch + k] = (T)((uint32_t)(two >> sh) & mask);
+  }
+}
+
 // ---- pitch conversion for the host-buffer entry points --------------------------------------------
 // Host rows are packed (N or N+1 elements), device rows are pitched (P elements).  A 2-D DMA copy with ~1 KB
 // rows runs at a fraction of PCIe speed (measured 12 GB/s D2H), so the pipeline moves packed buffers with
@@ -500,6 +548,42 @@ int launch_repitch(ntru_ctx *ctx, const void *src, void *dst, size_t rows, int w
       if (to_pitched) k_repitch<uint8_t, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint8_t *)src, (uint8_t *)dst, rows, width, ctx->P);
       else k_repitch<uint8_t, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint8_t *)src, (uint8_t *)dst, rows, width, ctx->P);
     }
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_pack_fields(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch, int bits, int n,
+                       int out_elems, uint32_t *out) {
+  if (B == 0) return NTRU_OK;
+  const size_t total = B * (size_t)out_elems * 8;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  {
+    LaunchTimer timer(ctx, NTRU_K_PACK);
+    if (elem_bytes == 2)
+      k_pack_fields<uint16_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint16_t *)data, B, data_len, pitch, bits, n, out_elems, out);
+    else
+      k_pack_fields<uint8_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const uint8_t *)data, B, data_len, pitch, bits, n, out_elems, out);
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_unpack_fields(ntru_ctx *ctx, size_t B, const uint32_t *data, int in_elems, int bits, int n, size_t pitch, void *out,
+                         int elem_bytes) {
+  if (B == 0) return NTRU_OK;
+  const size_t total = B * (size_t)in_elems * n;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  {
+    LaunchTimer timer(ctx, NTRU_K_PACK);
+    if (elem_bytes == 2)
+      k_unpack_fields<uint16_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>(data, B, in_elems, bits, n, pitch, (uint16_t *)out);
+    else
+      k_unpack_fields<uint8_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>(data, B, in_elems, bits, n, pitch, (uint8_t *)out);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;

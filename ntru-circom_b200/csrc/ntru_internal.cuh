@@ -115,6 +115,10 @@ int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
 size_t xchg_window_bytes(const ntru_ctx *ctx, int world);
 int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
+int launch_pack_fields(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch, int bits, int n,
+                       int out_elems, uint32_t *out);
+int launch_unpack_fields(ntru_ctx *ctx, size_t B, const uint32_t *data, int in_elems, int bits, int n, size_t pitch, void *out,
+                         int elem_bytes);
 int launch_repitch(ntru_ctx *ctx, const void *src, void *dst, size_t rows, int width, int elem, bool to_pitched);
 
 // ---- register-fragment tensor schedule (imma_kernels.cu): one warp per ciphertext, distinct keys ----

@@ -188,6 +188,20 @@ class Engine:
         """multiplyPolynomials(x, y, mod) + dividePolynomials(., 1 - x^N, mod), device-resident rows."""
         self._check(self.lib.ntru_muldiv_dev(self._h, B, _ptr(x), _ptr(y), int(bool(mod_p)), _ptr(quotient), _ptr(remainder)))
 
+    # -- packOutput / unpackInput (index.js:572-620) on device rows --------------------------------------
+    def pack_geometry(self, max_val: int, data_len: int):
+        v = [ctypes.c_int() for _ in range(4)]
+        self._check(self.lib.ntru_pack_geometry(int(max_val), int(data_len), *[ctypes.byref(x) for x in v]))
+        return tuple(x.value for x in v)     # maxInputBits, inputsPerOutput, arrLen, outputSize
+
+    def pack_output_dev(self, B, data, elem_bytes, data_len, pitch, max_val, out):
+        self._check(self.lib.ntru_pack_output_dev(self._h, B, _ptr(data), int(elem_bytes), int(data_len), int(pitch), int(max_val),
+                                                  _ptr(out)))
+
+    def unpack_input_dev(self, B, data, n_elems, max_val, packed_bits, out, elem_bytes, pitch):
+        self._check(self.lib.ntru_unpack_input_dev(self._h, B, _ptr(data), int(n_elems), int(max_val), int(packed_bits), _ptr(out),
+                                                   int(elem_bytes), int(pitch)))
+
     def sum(self, e):
         e = np.ascontiguousarray(e, dtype=np.uint16)
         B = e.shape[0]

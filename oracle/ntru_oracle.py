@@ -659,6 +659,41 @@ def verify_decrypt(inputs: dict, params: Sequence[int]) -> bool:
     return _verify_divide(c, I, inputs["quotient2"], inputs["remainder2"], p)
 
 
+def pack_output(max_val: int, data_len: int, data: Sequence[int]) -> dict:
+    """packOutput -- index.js:572-598: n = floor(252 / bits) coefficients per BN254 field element."""
+    max_input_bits = math.floor(math.log2(max_val) + 1)
+    per = 252 // max_input_bits
+    arr_len = max(math.ceil(data_len / per) * per, per * 3)
+    output_size = max(math.ceil(arr_len / per), 3)
+    in_arr = expand_array(data, arr_len, 0)
+    expected = [0] * output_size
+    for i, v in enumerate(in_arr):
+        expected[i // per] += int(v) << ((i % per) * max_input_bits)
+    return {"maxInputBits": max_input_bits, "maxOutputBits": per * max_input_bits, "outputSize": output_size,
+            "arrLen": arr_len, "expected": expected}
+
+
+def unpack_input(max_val: int, packed_bits: int, data: Sequence[int]) -> dict:
+    """unpackInput -- index.js:600-620."""
+    max_input_bits = math.floor(math.log2(max_val) + 1)
+    per = packed_bits // max_input_bits
+    mask = (1 << max_input_bits) - 1
+    unpacked = [0] * (per * len(data))
+    for i, d in enumerate(data):
+        for j in range(per):
+            unpacked[i * per + j] = (int(d) >> (j * max_input_bits)) & mask
+    return {"maxInputBits": max_input_bits, "packedBits": packed_bits, "packedSize": len(data),
+            "unpackedSize": len(unpacked), "unpacked": trim_polynomial(unpacked)}
+
+
+def combine_array(in_arr: Sequence[int], max_input_bits: int, per: int) -> List[int]:
+    """CombineArray as the reference's own test computes its expectation (test/circuits.test.js:27-31)."""
+    out = [0] * math.ceil(len(in_arr) / per)
+    for i, cur in enumerate(in_arr):
+        out[i // per] += int(cur) * (2 ** ((i % per) * max_input_bits))
+    return out
+
+
 def verify_inverse(inputs: dict, params: Sequence[int]) -> bool:
     """VerifyInverse(q, nq, N) -- ntru.circom:242-256 (q is the case's modulus: q for fq / h, p for fp)."""
     q, _nq, N = params

@@ -179,6 +179,42 @@ def test_verify_keys_inputs_vs_oracle(cfg, nb, engines, golden):
             assert out["remainder_" + case][i].tolist() == o.expand_array(d["remainder"], N + 1, 0), (cfg, i, case)
 
 
+@pytest.mark.parametrize("cfg", ["default167", "hps509", "hrss701"])
+def test_pack_output_unpack_input_vs_oracle(cfg, nb, engines, golden):
+    """packOutput / unpackInput (index.js:572-620) on device rows: ciphertext rows -> BN254 field
+    elements and back, against the oracle's BigInt restatement, for mod-q rows and for byte rows (mod-p outputs)."""
+    torch = pytest.importorskip("torch")
+    g, eng = golden(cfg), engines(cfg)
+    N, q, P = int(g["N"]), int(g["q"]), eng.pitch
+    rng = np.random.default_rng(23)
+    B = 37
+    for max_val, elem, hi in ((q, 2, q), (q - 1, 2, q), (2, 1, 3), (255, 1, 256)):
+        rows = rng.integers(0, hi, size=(B, N))
+        rows[0] = hi - 1
+        rows[1] = 0
+        dt = torch.int16 if elem == 2 else torch.uint8
+        d = torch.zeros((B, P), dtype=dt, device="cuda")
+        d[:, :N] = torch.from_numpy(rows.astype(np.int16 if elem == 2 else np.uint8)).cuda()
+        bits, per, arr_len, outs = eng.pack_geometry(max_val, N)
+        packed = torch.empty((B, outs, 4), dtype=torch.int64, device="cuda")
+        eng.pack_output_dev(B, d, elem, N, P, max_val, packed)
+        eng.sync()
+        words = packed.cpu().numpy().astype(np.uint64)
+        for b in (0, 1, 2, B - 1):
+            want = o.pack_output(max_val, N, [int(x) for x in rows[b]])
+            assert (bits, outs, arr_len) == (want["maxInputBits"], want["outputSize"], want["arrLen"])
+            got = [sum(int(words[b, e, w]) << (64 * w) for w in range(4)) for e in range(outs)]
+            assert got == want["expected"], (cfg, max_val, b)
+        # and back: unpackInput(maxVal, maxOutputBits, packed) == the rows (un-trimmed, zero-extended to per * outs)
+        un = torch.full((B, per * outs + 16), -1 if elem == 2 else 255, dtype=dt, device="cuda")
+        eng.unpack_input_dev(B, packed, outs, max_val, per * bits, un, elem, un.shape[1])
+        eng.sync()
+        u = un.cpu().numpy().astype(np.int64) & (0xFFFF if elem == 2 else 0xFF)
+        assert np.array_equal(u[:, :N], rows) and not u[:, N:per * outs].any()
+        want_u = o.unpack_input(max_val, per * bits, o.pack_output(max_val, N, [int(x) for x in rows[2]])["expected"])
+        assert o.trim_polynomial(u[2, :per * outs].tolist()) == want_u["unpacked"]
+
+
 def test_empty_batch_and_errors(nb, engines):
     eng = engines("default167")
     z8 = np.zeros((0, 167), dtype=np.uint8)

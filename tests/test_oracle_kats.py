@@ -1,4 +1,5 @@
 """Pins the oracle (oracle/ntru_oracle.py, oracle/ntru_ref_port.c) against every upstream KAT of the path."""
+import math
 import random
 
 import numpy as np
@@ -147,3 +148,22 @@ def test_generate_custom_array_weights():
     assert a.count(1) == 61 and a.count(-1) == 60 and len(a) == 167
     with pytest.raises(ValueError):
         o.generate_custom_array(5, 3, 3, rng)
+
+
+def test_pack_output_matches_upstream_combine_array_formula():
+    """test/circuits.test.js:20-58: CombineArray / UnpackArray at maxVal = 8192, N = 701 -- the expectation formula of
+    the upstream test pins pack_output (for in-range data and the same bit width) and unpack_input inverts it."""
+    rng = random.Random(5)
+    max_val, N = 8192, 701
+    bits_up = int(math.log2(max_val))                      # the upstream test packs 13-bit values (values < 8192)
+    per_up = 252 // bits_up
+    arr_len = math.ceil(N / per_up) * per_up
+    in_arr = [rng.randrange(max_val) for _ in range(arr_len)]
+    want = o.combine_array(in_arr, bits_up, per_up)
+    got = o.pack_output(max_val - 1, arr_len, in_arr)      # bit length of 8191 = 13: the same packing
+    assert got["maxInputBits"] == bits_up and got["expected"] == want
+    assert o.unpack_input(max_val - 1, got["maxOutputBits"], want)["unpacked"] == o.trim_polynomial(in_arr)
+    # packOutput(q, ...) itself uses floor(log2(q) + 1) = 14 bits and at least three outputs (index.js:573-580)
+    p = o.pack_output(8192, 5, [1, 2, 3, 4, 5])
+    assert (p["maxInputBits"], p["outputSize"], p["arrLen"]) == (14, 3, 54)
+    assert p["expected"] == [1 + (2 << 14) + (3 << 28) + (4 << 42) + (5 << 56), 0, 0]
