@@ -61,6 +61,29 @@ export function accelerate(NTRUReference, ref) {
         params: [this.q, this.calculateNq(), this.p, this.calculateNp(), this.N],
       };
     }
+    // index.js:141-197: the three multiply + divide pairs run on the GPU, checks and witness assembly as upstream
+    verifyKeysInputs() {
+      for (const [k, label] of [['f', 'private key F'], ['fq', 'private key Fq'], ['fp', 'private key Fp'], ['g', 'private key G']])
+        if (!this[k]) throw new Error(`missing ${label}`);
+      if (!this.h) throw new Error('missing public key H');
+      const { q, p, N } = this, nq = this.calculateNq(), np = this.calculateNp();
+      const ex = a => expandArray(a, N, 0);
+      const o = native.verifyKeysBatch(this.#engine(), 1, N, Int8Array.from(ex(this.f)), Uint16Array.from(ex(this.fq)),
+                                       Uint8Array.from(ex(this.fp)), Int8Array.from(ex(this.g)));
+      const fmodq = this.f.map(x => x === -1 ? q - 1 : x), fmodp = this.f.map(x => x === -1 ? p - 1 : x);
+      const fqp = this.fq.map(x => x * p), g = this.g.map(x => x === -1 ? q - 1 : x);
+      const rem = a => trimPolynomial(Array.from(a));
+      if (rem(o.remainderFq).length !== 1 && o.remainderFq[0] !== 1) throw new Error('invalid fq');   // sic, index.js:159
+      if (rem(o.remainderFp).length !== 1 && o.remainderFp[0] !== 1) throw new Error('invalid fp');
+      const hRem = rem(o.remainderH);
+      if (this.h.reduce((out, cur, i) => out || hRem[i] !== cur, false)) throw new Error('invalid h');
+      const c = (params, a, b, qI, rI) => ({ params, inputs: { f: ex(a), fq: ex(b), quotientI: Array.from(qI), remainderI: Array.from(rI) } });
+      return {
+        fq: c([q, nq, N], fmodq, this.fq, o.quotientFq, o.remainderFq),
+        fp: c([p, np, N], fmodp, this.fp, o.quotientFp, o.remainderFp),
+        h: c([q, nq, N], g, fqp, o.quotientH, o.remainderH),
+      };
+    }
     // engine-native unit of work: B rows per call, typed arrays in and out (fixed length, un-trimmed)
     encryptBitsBatch(B, r, m) { return native.encryptBatch(this.#loadPublic(), B, this.N, r, m); }
     decryptBitsBatch(B, e) { return native.decryptBatch(this.#loadPrivate(), B, this.N, e); }

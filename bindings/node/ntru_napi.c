@@ -130,11 +130,34 @@ static napi_value Sum(napi_env env, napi_callback_info info) {
   return out;
 }
 
+/* verifyKeysBatch(ctx, B, N, f:Int8Array, fq:Uint16Array, fp:Uint8Array, g:Int8Array) -- index.js:141-197 for B keys */
+static napi_value VerifyKeysBatch(napi_env env, napi_callback_info info) {
+  size_t argc = 7, len; napi_value argv[7]; uint32_t B, N;
+  napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+  ntru_ctx *ctx = get_ctx(env, argv[0]);
+  napi_get_value_uint32(env, argv[1], &B);
+  napi_get_value_uint32(env, argv[2], &N);
+  void *o[6];
+  static const char *names[6] = {"quotientFq", "remainderFq", "quotientFp", "remainderFp", "quotientH", "remainderH"};
+  napi_value out, v[6];
+  for (int i = 0; i < 6; ++i) {
+    const int bytes = (i == 2 || i == 3) ? 1 : 2;
+    v[i] = make_typed(env, bytes == 1 ? napi_uint8_array : napi_uint16_array, (size_t)B * (N + 1), bytes, &o[i]);
+  }
+  CHECK(env, ntru_verify_keys_batch(ctx, B, (const int8_t *)typed_data(env, argv[3], &len), (const uint16_t *)typed_data(env, argv[4], &len),
+                                    (const uint8_t *)typed_data(env, argv[5], &len), (const int8_t *)typed_data(env, argv[6], &len),
+                                    o[0], o[1], o[2], o[3], o[4], o[5]), ctx);
+  napi_create_object(env, &out);
+  for (int i = 0; i < 6; ++i) napi_set_named_property(env, out, names[i], v[i]);
+  return out;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
       {"create", 0, Create, 0, 0, 0, napi_default, 0},           {"setPublicKey", 0, SetPublicKey, 0, 0, 0, napi_default, 0},
       {"setPrivateKey", 0, SetPrivateKey, 0, 0, 0, napi_default, 0}, {"encryptBatch", 0, EncryptBatch, 0, 0, 0, napi_default, 0},
       {"decryptBatch", 0, DecryptBatch, 0, 0, 0, napi_default, 0},   {"sum", 0, Sum, 0, 0, 0, napi_default, 0},
+      {"verifyKeysBatch", 0, VerifyKeysBatch, 0, 0, 0, napi_default, 0},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;
