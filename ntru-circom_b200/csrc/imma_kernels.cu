@@ -377,16 +377,17 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_decrypt_imma(const ImmaDecA
     for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
       uint32_t lo[4], hi[4];
       load_lo_hi(G, cbuf, k0, lo, hi);
+      // remainder2 = (lo + hi) mod 3, quotient2 = -hi = 2 hi (mod 3): one reduction each, on sums that stay below
+      // 2^16 (lo, hi <= 4 N); the additions run on packed 16-bit pairs
       uint32_t rem[2] = {0, 0}, quo[2] = {0, 0};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t l3 = mod3_16((lo[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-        const uint32_t h3 = mod3_16((hi[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-        const bool in = k0 + i < G.N;
-        const uint32_t rr = in ? mod3_16(l3 + h3) : 0u;
-        const uint32_t qq = in ? mod3_16(3u - h3) : 0u;
-        rem[i >> 2] |= rr << (8 * (i & 3));
-        quo[i >> 2] |= qq << (8 * (i & 3));
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t s2 = lo[w] + hi[w], d2 = hi[w] << 1;
+        const bool in0 = k0 + 2 * w < G.N, in1 = k0 + 2 * w + 1 < G.N;
+        const uint32_t r0 = in0 ? mod3_16(s2 & 0xffffu) : 0u, r1 = in1 ? mod3_16(s2 >> 16) : 0u;
+        const uint32_t q0 = in0 ? mod3_16(d2 & 0xffffu) : 0u, q1 = in1 ? mod3_16(d2 >> 16) : 0u;
+        rem[w >> 1] |= (r0 | (r1 << 8)) << (16 * (w & 1));
+        quo[w >> 1] |= (q0 | (q1 << 8)) << (16 * (w & 1));
       }
       const uint2 rv = make_uint2(rem[0], rem[1]);
       if (a.value) *reinterpret_cast<uint2 *>(a.value + rbase + k0) = rv;

@@ -25,7 +25,10 @@
 //         int32 accumulator receives the exact product (u8 x s8).
 // All-zero K ranges of the triangular hi matrix are skipped at 128-byte granularity.
 //
-// Warp roles (576 threads, 1 CTA per SM, persistent over row tiles):
+// Two kernels implement it: k_umma_pair (umma_pair.cuh, the default: one CTA pair per 256 rows, cta_group::2,
+// resident A operand, B ring shared by the pair, TMA-store epilogue in two warp groups) and k_umma_product below
+// (single CTA per 128 rows, kept as a cross-check).  Warp roles of k_umma_product (576 threads, 1 CTA per SM,
+// persistent over row tiles):
 //   warp 0      TMA producer (A and B slices)      warp 1      tcgen05.mma issuer, owns TMEM
 //   warps 2-9   DEC1: e -> byte-limb A slices; ENC / DEC2: epilogue   warps 10-17 epilogue (TMEM -> regs -> global)
 // Pipelines: a 4-stage shared-memory ring (full/empty mbarriers) and two 256-column TMEM accumulators
@@ -137,17 +140,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -169,10 +161,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int a_signed, int b_signed, int n) {
   return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(kTileRows >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t mod3_small(uint32_t v) {   // v < 65536
-  return v - 3u * ((v * 0xAAABu) >> 17);
 }
 
 // first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= c*NCo + 1

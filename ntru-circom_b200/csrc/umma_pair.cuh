@@ -15,7 +15,7 @@
 //   a_full[i], b_full[j]   : used in the LEADER CTA only; both CTAs' TMA loads / transform warps signal them
 //   a_empty[i], b_empty[j] : in both CTAs, signalled by tcgen05.commit multicast from the leader's MMA thread
 //   tmem_full[b]           : in both CTAs (commit multicast);  tmem_empty[b]: leader only, all epilogue warps
-// Only the leader's warp 1 issues MMAs; producer, transform and epilogue warps run in both CTAs.
+// Only the leader's MMA warp issues MMAs; producer, transform and epilogue warps run in both CTAs.
 
 #ifdef NTRU_TRACE
 // debug timeline of cluster 0 / CTA 0: each traced thread appends (tag << 40 | clock) words to its own
@@ -50,9 +50,9 @@ constexpr int kPairSlots = 13;   // 16 KB of shared memory go to the trace buffe
 constexpr int kPairSlots = 14;
 #endif
 constexpr int kPairBars = 4 * kPairSlots + 8;   // a_full/a_empty/b_full/b_empty[kPairSlots], tmem full/empty[2], m full/empty[2]
-// Warp roles: the warp scheduler favours the highest warp id of an SM sub-partition, so the two single-thread
-// roles that sit on the critical path get the highest ids: 16 = TMA producer, 17 = MMA issuer.  Warps 0-15 are
-// epilogue warps (DEC1: 0-7 transform, 8-15 epilogue); an epilogue warp reads TMEM lanes 32*(warp%4)...
+// Warp roles: 16 = B-ring TMA producer, 17 = MMA issuer, 18 = A / message producer.  Warps 0-15 are epilogue
+// warps in two groups of 8, one per TMEM buffer (DEC1: 0-7 transform, 8-15 epilogue in two groups of 4); an
+// epilogue warp reads TMEM lanes 32*(warp%4)...
 constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17, kPairAuxWarp = 18, kPairEpiWarp0Dec1 = 8;
 constexpr int kPairThreads = 19 * 32;
 #ifdef NTRU_TRACE
@@ -133,52 +133,6 @@ __device__ __forceinline__ bool elect_one() {
 __host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signed, int n) {
   return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(256 >> 4) << 24);
-}
-
-// One pipeline slice = one 128-byte K atom of one K limb of one accumulator chunk.
-struct Slice {
-  int T, hi, c, at, lk;
-  uint32_t cc;            // running chunk index (TMEM buffer = cc & 1)
-  uint32_t sb, b_par;     // B ring stage and its phase parity
-  uint32_t sa, a_par;     // A slot and its phase parity
-  uint32_t ia;            // running A-load index (streaming mode)
-  bool a_load;            // this slice (re)loads its A slot
-  bool a_release;         // the MMA frees the A slot after this slice
-  bool chunk_first, chunk_last;
-};
-
-// Calls f(slice) for every slice of this CTA pair in pipeline order; every role walks the same sequence.
-template <class F>
-__device__ __forceinline__ void pair_walk(const UmmaArgs &a, F &&f) {
-  const int parts = a.with_hi ? 2 : 1;
-  uint32_t ib = 0, ia = 0, cc = 0;
-  int titer = 0;
-  for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, ++titer) {
-    for (int part = 0; part < parts; ++part) {
-      const int hi = part == 1;
-      for (int c = 0; c < a.nchunks; ++c, ++cc) {
-        const int a0 = first_atom(a, hi, c);
-        const bool first_chunk = part == 0 && c == 0, last_chunk = part == parts - 1 && c == a.nchunks - 1;
-        for (int at = a0; at < a.atoms; ++at) {
-          for (int lk = 0; lk < a.kl; ++lk, ++ib) {
-            Slice s;
-            s.T = T; s.hi = hi; s.c = c; s.at = at; s.lk = lk; s.cc = cc;
-            s.sb = ib % a.nB; s.b_par = (ib / a.nB) & 1;
-            s.ia = ia;
-            if (a.a_resident) {
-              s.sa = at * a.kl + lk; s.a_par = titer & 1; s.a_load = first_chunk; s.a_release = last_chunk;
-            } else {
-              s.sa = ia % a.nA; s.a_par = (ia / a.nA) & 1; s.a_load = true; s.a_release = true;
-              ++ia;
-            }
-            s.chunk_first = at == a0 && lk == 0;
-            s.chunk_last = at == a.atoms - 1 && lk == a.kl - 1;
-            f(s);
-          }
-        }
-      }
-    }
-  }
 }
 
 template <int MODE>
