@@ -7,7 +7,8 @@
 // (ncu: lts throughput 65-75 % of peak, tensor pipe 34 %).
 //
 // The A operand (128 rows x K bytes per CTA) is kept RESIDENT in shared memory for the whole tile when it
-// fits (every byte-operand mode, DEC1 up to N = 640): it is loaded (TMA) or built (DEC1 transform warps)
+// fits beside a B ring of at least 4 stages (DEC2 always, ENC up to N = 768, DEC1 up to N = 512): it is loaded
+// (TMA) or built (DEC1 transform warps)
 // once per tile instead of once per accumulator chunk.  When it does not fit, A slices stream through a
 // small ring exactly like B slices.
 //

@@ -215,6 +215,56 @@ def test_pack_output_unpack_input_vs_oracle(cfg, nb, engines, golden):
         assert o.trim_polynomial(u[2, :per * outs].tolist()) == want_u["unpacked"]
 
 
+GENERAL_NQ = [(8, 4), (16, 32), (33, 64), (100, 256), (191, 512), (193, 1024), (255, 2048), (256, 2048), (257, 4096),
+              (511, 8192), (512, 2048), (513, 2048), (640, 2048), (641, 4096), (704, 8192), (705, 2048), (832, 4096),
+              (833, 2048), (1024, 8192)]
+
+
+@pytest.mark.parametrize("N,q", GENERAL_NQ)
+def test_parameter_sets_outside_baseline(N, q, nb):
+    """The engine accepts any 8 <= N <= 1024 and power-of-two q <= 8192: sizes at the edges of every tiling decision
+    (K atoms of 128, accumulator chunks, resident / streaming A operand at N = 640 / 641, IMMA buckets at 192 / 512 /
+    704 / 832, fall-back above 832, even N) with random operands, every schedule, same key and distinct keys."""
+    p = 3
+    rng = np.random.default_rng(1000 * N + q)
+    B = 70
+    h = rng.integers(0, q, size=N)
+    f = rng.integers(-1, 2, size=N)
+    fp = rng.integers(0, p, size=N)
+    r = rng.integers(0, 3, size=(B, N))
+    m = rng.integers(0, 2, size=(B, N))
+    r[0], m[0] = 2, 255 if q > 256 else 1                      # largest accumulators
+    want_e = o.encrypt_batch(h, r, m, q)
+    want_d = o.decrypt_batch(f, fp, want_e["value"], q, p)
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_public_key(h.astype(np.uint16))
+    eng.set_private_key(f.astype(np.int8), fp.astype(np.uint8))
+    paths = _paths(nb, eng)
+    assert nb.PATH_TENSOR in paths and (nb.PATH_IMMA in paths) == (N <= 832)
+    for path in paths:
+        eng.set_path(path)
+        enc = eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8))
+        for k in ENC_KEYS:
+            assert np.array_equal(enc[k], want_e[k]), (N, q, path, k)
+        dec = eng.decrypt_batch(enc["value"])
+        for k in DEC_KEYS:
+            assert np.array_equal(dec[k], want_d[k]), (N, q, path, k)
+    eng.set_path(nb.PATH_AUTO)
+    hh = rng.integers(0, q, size=(B, N)); ff = rng.integers(-1, 2, size=(B, N)); pp = rng.integers(0, p, size=(B, N))
+    want_e = o.encrypt_batch(hh, r, m, q)
+    want_d = o.decrypt_batch(ff, pp, want_e["value"], q, p)
+    enc = eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8), h=hh.astype(np.uint16))
+    dec = eng.decrypt_batch(enc["value"], f=ff.astype(np.int8), fp=pp.astype(np.uint8))
+    assert eng.last_path == (nb.PATH_IMMA if N <= 832 else nb.PATH_CUDA_CORE)
+    for k in ENC_KEYS:
+        assert np.array_equal(enc[k], want_e[k]), (N, q, "keys", k)
+    for k in DEC_KEYS:
+        assert np.array_equal(dec[k], want_d[k]), (N, q, "keys", k)
+    e = rng.integers(0, q, size=(301, N), dtype=np.uint16)
+    assert np.array_equal(eng.sum(e), o.sum_batch(e, q))
+    eng.close()
+
+
 def test_empty_batch_and_errors(nb, engines):
     eng = engines("default167")
     z8 = np.zeros((0, 167), dtype=np.uint8)

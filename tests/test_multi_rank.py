@@ -29,6 +29,41 @@ def _worker(rank, world, port, q, N, rows, out_dir):
     dist.destroy_process_group()
 
 
+class _FakeEngine:
+    """Stands in for Engine in the control-plane test: records what connect_exchange hands to the C ABI."""
+
+    def __init__(self, rank):
+        self.rank, self.created, self.connected = rank, None, None
+
+    def xchg_create(self, world, rank):
+        self.created = (world, rank)
+        return bytes([rank + 1]) * 64                      # this rank's 64-byte "IPC handle"
+
+    def xchg_connect(self, handles):
+        self.connected = handles
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ntru_circom_b200.sharding import connect_exchange
+    eng = _FakeEngine(rank)
+    connect_exchange(eng)
+    assert eng.created == (world, rank)
+    with open(os.path.join(out_dir, f"h{rank}.bin"), "wb") as fh:
+        fh.write(eng.connected)
+    dist.destroy_process_group()
+
+
+def test_exchange_handles_are_gathered_rank_major(tmp_path):
+    """connect_exchange (control plane of the peer-memory sum): every rank receives all 64-byte handles, rank-major."""
+    world, port = 2, _free_port()
+    mp.spawn(_exchange_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    want = b"".join(bytes([r + 1]) * 64 for r in range(world))
+    for r in range(world):
+        assert (tmp_path / f"h{r}.bin").read_bytes() == want
+
+
 def test_shard_bounds_cover_everything_once():
     from ntru_circom_b200.sharding import shard_bounds
     for total in (0, 1, 7, 1000, 1 << 20):
