@@ -713,7 +713,21 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
     if (pair) {
       const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
+#ifdef NTRU_TRACE
+      const int dbg = getenv("NTRU_DEBUG_EPI") ? atoi(getenv("NTRU_DEBUG_EPI")) : 0;
+#define NTRU_DBG_LAUNCH(D)                                                                                                  \
+  case D:                                                                                                                  \
+    cudaFuncSetAttribute(k_umma_pair<MODE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);          \
+    k_umma_pair<MODE, D><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]); \
+    break;
+      switch (dbg) {
+        NTRU_DBG_LAUNCH(1) NTRU_DBG_LAUNCH(2) NTRU_DBG_LAUNCH(4) NTRU_DBG_LAUNCH(8) NTRU_DBG_LAUNCH(12) NTRU_DBG_LAUNCH(16)
+        default:
+          k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+      }
+#else
       k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+#endif
     } else {
       const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
       k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);

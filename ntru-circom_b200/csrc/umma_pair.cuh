@@ -136,7 +136,11 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signe
          ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int MODE>
+// DBG (timing experiments, instantiated in NTRU_TRACE builds only; results are then wrong on purpose):
+//   1 epilogue hands the buffers back without reading them     2 TMEM reads only (no arithmetic, no stores)
+//   4 no TMEM reads (arithmetic and stores on register garbage) 8 no staging stores and no TMA stores
+//   16 staging stores and fences, but no TMA stores
+template <int MODE, int DBG = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA,
             const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapO0,
@@ -492,6 +496,15 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           if (lane == 0 && ew == 0) TRACE(2, 1, cc);
           if (MODE == ENC && !hi) mbar_wait(m_full(ms), m_par);
           if (lane == 0 && ew == 0) TRACE(2, 3, cc);
+          if (DBG & 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_cluster(lead_tempty);
+              if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));
+            }
+            continue;
+          }
           for (int ps = 0; ps < npass; ++ps) {
             const int u0 = sub * upw + ps * kPassUnits;
             const bool last_pass = ps == npass - 1;
@@ -509,10 +522,15 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               uint32_t acc1[kPassUnits][32];
 #pragma unroll
               for (int j = 0; j < kPassUnits; ++j) {
+                if (DBG & 4) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { acc[j][i] = (uint32_t)(i + lane + ps); acc1[j][i] = (uint32_t)(i ^ lane); }
+                  continue;
+                }
                 tmem_ld16(t_addr + (u0 + j) * 16, acc[j]);
                 if (MODE == ENC && a.nl == 2) tmem_ld16(t_addr + a.NCo + (u0 + j) * 16, acc1[j]);
               }
-              tmem_ld_wait();
+              if (!(DBG & 4)) tmem_ld_wait();
               if (lane == 0 && ew == 0) TRACE(2, 4, cc);
               if (MODE == ENC && a.nl == 2) {
 #pragma unroll
@@ -528,6 +546,13 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 mbar_arrive_cluster(lead_tempty);
                 if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));   // message tile is in registers
               }
+            }
+            if (DBG & 2) {
+              uint32_t x = 0;
+#pragma unroll
+              for (int j = 0; j < kPassUnits; ++j) x ^= acc[j][0] ^ acc[j][15];
+              if (x == 0x12345678u) sts128(st_row, make_uint4(x, x, x, x));
+              continue;
             }
 #pragma unroll
             for (int j = 0; j < kPassUnits; ++j) {
@@ -580,6 +605,13 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               }
             }
             if (lane == 0 && ew == 0) TRACE(2, 5, cc);
+            if (DBG & 8) {
+              uint32_t x = 0;
+#pragma unroll
+              for (int j = 0; j < kPassUnits * (MODE == DEC2 ? 4 : 8); ++j) x ^= res[j];
+              if (x == 0x12345678u) sts128(st_row, make_uint4(x, x, x, x));
+              continue;
+            }
             // the previous store must have finished reading the staging tile before it is overwritten
             if (store_pending) {
               if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -606,6 +638,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             fence_proxy_async();
             __syncwarp();
             if (lane == 0 && ew == 0) TRACE(2, 7, cc);
+            if (DBG & 16) continue;
             if (lane == 0) {
               const int col = c * a.NCo + u0 * 16;
               if (hi) {
