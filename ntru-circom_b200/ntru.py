@@ -124,6 +124,57 @@ class NTRU:
     def decryptStr(self, encrypted: Sequence[int]) -> str:
         return poly.bitsToString(poly.expandArrayToMultiple(self.decryptBits(encrypted)["value"], 8))
 
+    # ---- strings, many per call (the codec of index.js:80-86, 516-556 around the batch engine) ----
+    def encryptStrBatch(self, strings: Sequence[str], *, split: bool = False) -> np.ndarray:
+        """encryptStr for every string: 8 bits per character, MSB first (stringToBits, index.js:538-546).  Returns the
+        (B, N) ciphertext rows, fixed length (un-trimmed).  The reference has "no provision to split into words"
+        (index.js:81): a string longer than floor(N / 8) characters raises like expandArray does, unless
+        ``split=True`` -- then it is cut into blocks of floor(N / 8) characters and the result is a list of
+        (blocks_i, N) arrays, one per string (the last block zero padded)."""
+        N, cpb = self.N, self.N // 8
+        blocks, owner = [], []
+        for si, text in enumerate(strings):
+            codes = [ord(ch) for ch in text]
+            if any(c > 0xFF for c in codes):
+                raise NtruError(-1, "encryptStrBatch handles characters up to 0xFF (8 bits each, index.js:541-543)")
+            if len(codes) > cpb and not split:
+                raise IndexError("RangeError: Invalid array length")          # index.js:98 via expandArray
+            for b0 in range(0, max(len(codes), 1), cpb):
+                blocks.append(codes[b0:b0 + cpb])
+                owner.append(si)
+        ms = np.zeros((len(blocks), N), dtype=np.uint8)
+        for bi, codes in enumerate(blocks):
+            if codes:
+                ms[bi, :8 * len(codes)] = np.unpackbits(np.array(codes, dtype=np.uint8), bitorder="big")
+        value = self.encryptBitsBatch(ms, witness=False)["value"] if len(blocks) else np.zeros((0, N), dtype=np.uint16)
+        if not split:
+            return value
+        owner = np.array(owner, dtype=np.int64)
+        return [value[owner == si] for si in range(len(strings))]
+
+    def decryptStrBatch(self, es) -> List[str]:
+        """decryptStr for every row of es ((B, N) ciphertexts) -- or, for a list of (blocks_i, N) arrays as returned by
+        encryptStrBatch(split=True), one string per entry with its blocks concatenated.  Like the reference
+        (index.js:84-86, 548-556) the plaintext is trimmed, padded to a multiple of 8 and read 8 bits per character:
+        trailing NUL characters of a block are lost."""
+        if isinstance(es, (list, tuple)) and len(es) and np.asarray(es[0]).ndim == 2:
+            sizes = [np.asarray(e).shape[0] for e in es]
+            flat = self.decryptStrBatch(np.concatenate([np.asarray(e) for e in es], axis=0))
+            out, pos = [], 0
+            for n in sizes:
+                out.append("".join(flat[pos:pos + n]))
+                pos += n
+            return out
+        es = np.asarray(es)
+        if es.shape[0] == 0:
+            return []
+        plain = self.decryptBitsBatch(es, witness=False)["value"]
+        out = []
+        for row in plain:
+            bits = poly.expandArrayToMultiple(poly.trimPolynomial(row.tolist()), 8)
+            out.append(poly.bitsToString(bits))
+        return out
+
     # ---- hot path: one ciphertext (index.js:87-140) -----------------------------------------
     def sampleR(self) -> List[int]:
         """index.js:89."""

@@ -265,6 +265,29 @@ def test_parameter_sets_outside_baseline(N, q, nb):
     eng.close()
 
 
+def test_string_batches_and_multi_block_messages(nb, golden):
+    """encryptStr / decryptStr for many strings per call, against the single-string reference path
+    (index.js:80-86) and the oracle's codec; strings longer than floor(N / 8) characters split into blocks."""
+    g = golden("default167")
+    k = o.make_key("default167", 300)
+    mine = nb.NTRU(dict(o.CONFIGS["default167"]), f=list(k.f), fq=list(k.fq), fp=list(k.fp), g=list(k.g), h=list(k.h))
+    texts = ["Hello World", "", "a", "x" * 20, "NTRU on B200!", "\xe9\xff"]
+    enc = mine.encryptStrBatch(texts)
+    assert enc.shape == (len(texts), 167)
+    # the reference decrypts the empty string to one NUL character: trim -> [0] -> padded to 8 bits (index.js:84-86)
+    want = [t if t else "\x00" for t in texts]
+    assert mine.decryptStrBatch(enc) == want
+    for t, row in zip(want, enc):                                      # each row decrypts through the one-string path too
+        assert mine.decryptStr(o.trim_polynomial(row.tolist())) == t
+        assert k.decryptStr(o.trim_polynomial(row.tolist())) == t     # ... and through the oracle's class
+    with pytest.raises(IndexError):
+        mine.encryptStrBatch(["y" * 21])                               # 21 characters > floor(167 / 8): index.js:98
+    long_texts = ["The quick brown fox jumps over the lazy dog. " * 3, "short", "z" * 40]
+    blocks = mine.encryptStrBatch(long_texts, split=True)
+    assert [b.shape[0] for b in blocks] == [-(-len(t) // 20) for t in long_texts]
+    assert mine.decryptStrBatch(blocks) == long_texts
+
+
 def test_empty_batch_and_errors(nb, engines):
     eng = engines("default167")
     z8 = np.zeros((0, 167), dtype=np.uint8)
