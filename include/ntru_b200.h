@@ -130,6 +130,15 @@ int ntru_verify_keys_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const uint1
  * mod_p != 0: y bytes in [0, p), outputs bytes mod p.  Pitch ntru_pitch() elements everywhere. */
 int ntru_muldiv_dev(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quotient, void *remainder);
 
+/* loadPrivateKeyF + generatePublicKeyH for B keys at once -- index.js:30-79, 491-514.  f, g: B x N ternary (the
+ * generateCustomArray draws stay with the caller's CSPRNG).  fp = f^-1 mod (p, x^N-1), fq = f^-1 mod (q, x^N-1),
+ * h = (p fq) * g mod (q, x^N-1); rows of N entries, un-trimmed.  The extended-Euclid inversions modulo 2 and modulo p
+ * run on the host (sequential, index.js:425-459); the Newton lifting 2 -> q (index.js:497-509) and h run on the GPU.
+ * valid[b] = 1 iff f_b is invertible modulo 2 and modulo p -- then the outputs equal the reference's (the inverse is
+ * unique); otherwise the row's outputs are zero and the caller redraws f as generatePrivateKeyF does. */
+int ntru_keygen_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const int8_t *g, uint16_t *fq, uint8_t *fp, uint16_t *h,
+                      uint8_t *valid);
+
 /* packOutput / unpackInput -- index.js:572-620: coefficients <-> BN254 field elements (CombineArray / UnpackArray,
  * circuits/ntru.circom:259-306).  A field element is 32 bytes, little-endian.
  * ntru_pack_geometry is packOutput's header: maxInputBits = floor(log2(maxVal) + 1), n = floor(252 / maxInputBits),

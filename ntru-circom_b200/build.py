@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libntru_b200.so")
-SOURCES = ["api.cu", "generic_kernels.cu", "imma_kernels.cu", "umma_kernels.cu"]
+SOURCES = ["api.cu", "generic_kernels.cu", "imma_kernels.cu", "keygen.cu", "umma_kernels.cu"]
 HEADERS = ["ntru_internal.cuh", "umma_pair.cuh", os.path.join("..", "..", "include", "ntru_b200.h")]
 
 NVCC_FLAGS = [
@@ -38,7 +38,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -524,6 +524,14 @@ int ntru_verify_keys_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const uint1
   });
 }
 
+int ntru_keygen_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const int8_t *g, uint16_t *fq, uint8_t *fp, uint16_t *h,
+                      uint8_t *valid) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (B > 0 && (!f || !g || !fq || !fp || !h || !valid)) return fail(ctx, NTRU_E_PARAM, "f, g, fq, fp, h and valid are required");
+  return keygen_batch(ctx, B, f, g, fq, fp, h, valid);
+}
+
 static int bit_length(uint32_t v) {   // floor(log2(v) + 1) for v >= 1 (index.js:573, 601)
   int b = 0;
   while (v) { ++b; v >>= 1; }

@@ -184,6 +184,21 @@ class Engine:
                                                                              "remainder_fp", "quotient_h", "remainder_h")]))
         return out
 
+    def keygen_batch(self, f, g):
+        """loadPrivateKeyF + generatePublicKeyH for B keys (index.js:30-79): f, g ternary (B, N).  Returns fixed-length
+        fq, fp, h and the validity mask (f invertible modulo 2 and modulo p)."""
+        N = self.N
+        f = np.ascontiguousarray(f, dtype=np.int8)
+        B = f.shape[0]
+        f = _host(f, np.int8, (B, N))
+        g = _host(g, np.int8, (B, N))
+        fq = np.empty((B, N), dtype=np.uint16)
+        fp = np.empty((B, N), dtype=np.uint8)
+        h = np.empty((B, N), dtype=np.uint16)
+        valid = np.empty(B, dtype=np.uint8)
+        self._check(self.lib.ntru_keygen_batch(self._h, B, _ptr(f), _ptr(g), _ptr(fq), _ptr(fp), _ptr(h), _ptr(valid)))
+        return {"fq": fq, "fp": fp, "h": h, "valid": valid.astype(bool)}
+
     def muldiv_dev(self, B, x, y, mod_p, quotient=None, remainder=None):
         """multiplyPolynomials(x, y, mod) + dividePolynomials(., 1 - x^N, mod), device-resident rows."""
         self._check(self.lib.ntru_muldiv_dev(self._h, B, _ptr(x), _ptr(y), int(bool(mod_p)), _ptr(quotient), _ptr(remainder)))

@@ -104,6 +104,30 @@ class NTRU:
         if not self.fq or not self.fp:
             raise ValueError("Could not find invertible f")
 
+    def generateKeysBatch(self, B: int) -> dict:
+        """B key pairs at once: generatePrivateKeyF + generateNewPublicKeyGH (index.js:51-79) with the
+        same draws (generateCustomArray with weights (df, df - 1) for f and (dg, dg) for g) and the same retry rule
+        (redraw f while it is not invertible, at most 100 times).  The inversions modulo 2 and p run on the host inside
+        the library, the lifting to q and h on the GPU (ntru_keygen_batch).  Returns fixed-length numpy arrays."""
+        N = self.N
+        eng = self.engine()
+        f = np.zeros((B, N), dtype=np.int8)
+        g = np.array([poly.generateCustomArray(N, self.dg, self.dg, self.rand32) for _ in range(B)], dtype=np.int8).reshape(B, N)
+        out = {"fq": np.zeros((B, N), dtype=np.uint16), "fp": np.zeros((B, N), dtype=np.uint8), "h": np.zeros((B, N), dtype=np.uint16)}
+        todo = np.arange(B)
+        for _ in range(100):
+            if todo.size == 0:
+                break
+            f[todo] = np.array([poly.generateCustomArray(N, self.df, self.df - 1, self.rand32) for _ in todo], dtype=np.int8).reshape(-1, N)
+            res = eng.keygen_batch(f[todo], g[todo])
+            ok = res["valid"]
+            for k in out:
+                out[k][todo[ok]] = res[k][ok]
+            todo = todo[~ok]
+        if todo.size:
+            raise ValueError("Could not find invertible f")              # index.js:63
+        return {"f": f, "g": g, **out}
+
     def generateNewPublicKeyGH(self):
         self.g = poly.generateCustomArray(self.N, self.dg, self.dg, self.rand32)
         self.generatePublicKeyH()

@@ -7,7 +7,7 @@ csrc = os.path.join(ROOT, "ntru-circom_b200", "csrc")
 lib_path = os.path.join(ROOT, "ntru-circom_b200", "libntru_trace.so")   # *.so: git-ignored, travels with gpurun
 if not os.path.exists(lib_path) or "--build" in sys.argv:
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DNTRU_TRACE", "-Xcompiler", "-fPIC",
-                    "-shared", "-o", lib_path] + [os.path.join(csrc, f) for f in ("api.cu", "generic_kernels.cu", "imma_kernels.cu", "umma_kernels.cu")], check=True)
+                    "-shared", "-o", lib_path] + [os.path.join(csrc, f) for f in ("api.cu", "generic_kernels.cu", "imma_kernels.cu", "keygen.cu", "umma_kernels.cu")], check=True)
 import ntru_circom_b200 as nb
 from ntru_circom_b200 import _lib
 _lib.LIB_PATH = lib_path

@@ -288,6 +288,49 @@ def test_string_batches_and_multi_block_messages(nb, golden):
     assert mine.decryptStrBatch(blocks) == long_texts
 
 
+@pytest.mark.parametrize("cfg", CFGS)
+def test_keygen_batch_vs_oracle(cfg, nb, engines, golden):
+    """loadPrivateKeyF + generatePublicKeyH for a batch (host extended Euclid modulo 2 and p, GPU lifting
+    to q and h): fq, fp and h of valid oracle keys bit for bit (the inverse is unique), non-invertible f flagged."""
+    g, eng = golden(cfg), engines(cfg)
+    N, q, p = int(g["N"]), int(g["q"]), int(g["p"])
+    keys = [o.make_key(cfg, 400 + i) for i in range(6)]
+    B = len(keys) + 3
+    f = np.zeros((B, N), dtype=np.int8); gg = np.zeros((B, N), dtype=np.int8)
+    for i, k in enumerate(keys):
+        f[i], gg[i] = k.f, k.g
+    f[len(keys)] = 0                                      # zero polynomial
+    f[len(keys) + 1, :2] = 1                              # f(1) even: not invertible modulo 2
+    f[len(keys) + 2, :3] = 1                              # f(1) = 3: not invertible modulo 3
+    gg[len(keys):] = keys[0].g
+    out = eng.keygen_batch(f, gg)
+    assert out["valid"].tolist() == [True] * len(keys) + [False] * 3
+    for i, k in enumerate(keys):
+        assert out["fq"][i].tolist() == o.expand_array(k.fq, N, 0), (cfg, i, "fq")
+        assert out["fp"][i].tolist() == o.expand_array(k.fp, N, 0), (cfg, i, "fp")
+        assert out["h"][i].tolist() == o.expand_array(k.h, N, 0), (cfg, i, "h")
+    assert not out["fq"][len(keys):].any() and not out["h"][len(keys):].any() and not out["fp"][len(keys):].any()
+    # the class-level batch: every key it returns is a working key pair
+    rng = random.Random(77)
+    kk = nb.NTRU(dict(o.CONFIGS[cfg]), rand32=lambda: rng.getrandbits(32))
+    ks = kk.generateKeysBatch(5)
+    m = np.random.default_rng(1).integers(0, 2, size=(5, N)).astype(np.uint8)
+    r = o.sample_ternary_rows(5, N, int(g["dr"]), int(g["dr"]), np.random.default_rng(2)).astype(np.uint8)
+    want_e = o.encrypt_batch(ks["h"].astype(np.int64), r, m, q)
+    want_d = o.decrypt_batch(ks["f"].astype(np.int64), ks["fp"].astype(np.int64), want_e["value"], q, p)
+    dec = kk.decryptBitsBatch(kk.encryptBitsBatch(m, r, hs=ks["h"])["value"], fs=ks["f"], fps=ks["fp"])
+    assert np.array_equal(dec["value"], want_d["value"])
+    for i in range(5):                                    # f * fq = 1 (mod q, x^N - 1) and f * fp = 1 (mod p, x^N - 1)
+        c = np.convolve(ks["f"][i].astype(np.int64), ks["fq"][i].astype(np.int64))
+        cyc = c[:N].copy(); cyc[: N - 1] += c[N:]
+        assert (np.mod(cyc, q) == np.eye(1, N, 0, dtype=np.int64)[0]).all()
+        c = np.convolve(ks["f"][i].astype(np.int64), ks["fp"][i].astype(np.int64))
+        cyc = c[:N].copy(); cyc[: N - 1] += c[N:]
+        assert (np.mod(cyc, p) == np.eye(1, N, 0, dtype=np.int64)[0]).all()
+    if q % 3 == 2 and cfg != "tiny17":
+        assert np.array_equal(dec["value"], m)
+
+
 def test_empty_batch_and_errors(nb, engines):
     eng = engines("default167")
     z8 = np.zeros((0, 167), dtype=np.uint8)
