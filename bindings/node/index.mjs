@@ -88,5 +88,15 @@ export function accelerate(NTRUReference, ref) {
     encryptBitsBatch(B, r, m) { return native.encryptBatch(this.#loadPublic(), B, this.N, r, m); }
     decryptBitsBatch(B, e) { return native.decryptBatch(this.#loadPrivate(), B, this.N, e); }
     sumCiphertexts(B, e) { return trimPolynomial(Array.from(native.sum(this.#engine(), B, this.N, e))); }
+    // B key pairs: f, g drawn here like generatePrivateKeyF / generateNewPublicKeyGH do (index.js:51-71), inverses,
+    // lifting and h in the engine; rows whose f is not invertible come back with valid = 0 (redraw them)
+    generateKeysBatch(B) {
+      const f = new Int8Array(B * this.N), g = new Int8Array(B * this.N);
+      for (let b = 0; b < B; b++) {
+        f.set(generateCustomArray(this.N, this.df, this.df - 1), b * this.N);
+        g.set(generateCustomArray(this.N, this.dg, this.dg), b * this.N);
+      }
+      return { f, g, ...native.keygenBatch(this.#engine(), B, this.N, f, g) };
+    }
   };
 }

@@ -152,12 +152,32 @@ static napi_value VerifyKeysBatch(napi_env env, napi_callback_info info) {
   return out;
 }
 
+/* keygenBatch(ctx, B, N, f:Int8Array, g:Int8Array) -> {fq, fp, h, valid} -- index.js:30-79 for B keys */
+static napi_value KeygenBatch(napi_env env, napi_callback_info info) {
+  size_t argc = 5, len; napi_value argv[5]; uint32_t B, N;
+  napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+  ntru_ctx *ctx = get_ctx(env, argv[0]);
+  napi_get_value_uint32(env, argv[1], &B);
+  napi_get_value_uint32(env, argv[2], &N);
+  void *fq, *fp, *h, *valid;
+  napi_value out, v0 = make_typed(env, napi_uint16_array, (size_t)B * N, 2, &fq), v1 = make_typed(env, napi_uint8_array, (size_t)B * N, 1, &fp),
+                  v2 = make_typed(env, napi_uint16_array, (size_t)B * N, 2, &h), v3 = make_typed(env, napi_uint8_array, B, 1, &valid);
+  CHECK(env, ntru_keygen_batch(ctx, B, (const int8_t *)typed_data(env, argv[3], &len), (const int8_t *)typed_data(env, argv[4], &len),
+                               fq, fp, h, valid), ctx);
+  napi_create_object(env, &out);
+  napi_set_named_property(env, out, "fq", v0);
+  napi_set_named_property(env, out, "fp", v1);
+  napi_set_named_property(env, out, "h", v2);
+  napi_set_named_property(env, out, "valid", v3);
+  return out;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
       {"create", 0, Create, 0, 0, 0, napi_default, 0},           {"setPublicKey", 0, SetPublicKey, 0, 0, 0, napi_default, 0},
       {"setPrivateKey", 0, SetPrivateKey, 0, 0, 0, napi_default, 0}, {"encryptBatch", 0, EncryptBatch, 0, 0, 0, napi_default, 0},
       {"decryptBatch", 0, DecryptBatch, 0, 0, 0, napi_default, 0},   {"sum", 0, Sum, 0, 0, 0, napi_default, 0},
-      {"verifyKeysBatch", 0, VerifyKeysBatch, 0, 0, 0, napi_default, 0},
+      {"verifyKeysBatch", 0, VerifyKeysBatch, 0, 0, 0, napi_default, 0}, {"keygenBatch", 0, KeygenBatch, 0, 0, 0, napi_default, 0},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;
