@@ -50,7 +50,7 @@ enum {
 
 /* ntru_set_option keys */
 enum {
-  NTRU_OPT_PATH = 1,        /* 0 auto (same key: tcgen05, distinct keys: register-fragment IMMA), 1 force the fp32 CUDA-core
+  NTRU_OPT_PATH = 1,        /* 0 auto (same key: tcgen05 from 4096 rows up, IMMA below; distinct keys: IMMA), 1 force the fp32 CUDA-core
                                schedule, 2 force the tcgen05 schedule (same-key only), 3 force the register-fragment schedule */
   NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
   NTRU_OPT_TIMING = 3,      /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */

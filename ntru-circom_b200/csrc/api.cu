@@ -126,9 +126,15 @@ void set_out(HostArr &a, void *p, size_t elem, size_t width) {
   a.out = p; a.elem = elem; a.width = width; a.used = p != nullptr;
 }
 
-bool want_tensor(ntru_ctx *ctx, bool same_key, bool ready, int *rc) {
+// Below this many rows the tcgen05 schedule cannot fill the chip (one CTA pair per 256 rows, 74 pairs) and the
+// one-warp-per-ciphertext IMMA schedule finishes sooner (scripts/bench_latency.py: 1024 rows at N = 821 take 1.7 ms
+// against 0.55 ms): NTRU_OPT_PATH = 0 picks the IMMA schedule there.
+constexpr size_t kSmallBatchRows = 4096;
+
+bool want_tensor(ntru_ctx *ctx, bool same_key, bool ready, size_t B, int *rc) {
   *rc = NTRU_OK;
   if (ctx->opt_path == 1 || ctx->opt_path == 3) return false;
+  if (ctx->opt_path == 0 && B < kSmallBatchRows && ctx->tensor_ok && imma_supported(ctx)) return false;
   const bool ok = same_key && ctx->tensor_ok && ready;
   if (ctx->opt_path == 2 && !ok) {
     *rc = fail(ctx, NTRU_E_UNSUPPORTED, "tensor schedule forced but not available for this call");
@@ -154,7 +160,7 @@ int encrypt_dispatch(ntru_ctx *ctx, size_t B, const uint16_t *h_rows, const uint
   int rc;
   const bool same_key = h_rows == nullptr;
   if (same_key && !ctx->has_pub) return fail(ctx, NTRU_E_NOKEY, "public key h is not set");
-  if (want_tensor(ctx, same_key && !m_wide, ctx->km_h.ready, &rc)) {
+  if (want_tensor(ctx, same_key && !m_wide, ctx->km_h.ready, B, &rc)) {
     ctx->last_path = 2;
     return umma_encrypt(ctx, B, r, (const uint8_t *)m, value, quo, rem);
   }
@@ -176,7 +182,7 @@ int decrypt_dispatch(ntru_ctx *ctx, size_t B, const int8_t *f_rows, const uint8_
   const bool same_key = f_rows == nullptr && fp_rows == nullptr;
   if ((f_rows == nullptr) != (fp_rows == nullptr)) return fail(ctx, NTRU_E_PARAM, "f_rows and fp_rows must be given together");
   if (same_key && !ctx->has_priv) return fail(ctx, NTRU_E_NOKEY, "private key f/fp is not set");
-  if (want_tensor(ctx, same_key, ctx->km_f.ready && ctx->km_fp.ready, &rc)) {
+  if (want_tensor(ctx, same_key, ctx->km_f.ready && ctx->km_fp.ready, B, &rc)) {
     ctx->last_path = 2;
     return umma_decrypt(ctx, B, e, value, q1, r1, q2, r2);
   }

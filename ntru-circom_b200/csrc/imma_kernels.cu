@@ -503,12 +503,19 @@ ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays, int nj_bucket) {
 template <class K, class A>
 int launch_imma(ntru_ctx *ctx, K kernel, const A &args, int kind, size_t B, int regs_hint) {
   const size_t smem = (size_t)kImmaWarps * args.G.warp_bytes;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(imma)");
+  // shared-memory attribute and occupancy: once per (context, kernel, footprint), not per launch
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kImmaWarps * 32, smem);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(imma)");
-  if (per_sm < 1) per_sm = 1;
+  for (const auto &c : ctx->imma_cfg)
+    if (c.fn == (const void *)kernel && c.smem == smem) per_sm = c.per_sm;
+  // four warps need at most 43 KB (N = 832): below the 48 KB that need no opt-in.  (The opt-in attribute is per
+  // function and device, shared by every context: it must not be cached per context.)
+  if (smem > 48 * 1024) return fail(ctx, NTRU_E_UNSUPPORTED, "IMMA schedule: shared-memory footprint above 48 KB");
+  if (per_sm == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kImmaWarps * 32, smem);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(imma)");
+    if (per_sm < 1) per_sm = 1;
+    ctx->imma_cfg.push_back({(const void *)kernel, smem, per_sm});
+  }
   (void)regs_hint;
   const size_t want = (B + kImmaWarps - 1) / kImmaWarps;
   const size_t cap = (size_t)ctx->sm_count * per_sm;

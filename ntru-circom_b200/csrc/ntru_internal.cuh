@@ -71,6 +71,8 @@ struct ntru_ctx {
   int opt_path = 0;
   int umma_attr_set = 0;           // bit per kernel mode: dynamic shared memory attribute applied on this device
   bool sampler_attr_set = false;
+  struct ImmaCfg { const void *fn; size_t smem; int per_sm; };
+  std::vector<ImmaCfg> imma_cfg;   // launch configuration of the IMMA kernels already prepared on this context's device
   int tensor_variant = 0;          // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
   int last_path = 0;
   int sm_count = 148;
