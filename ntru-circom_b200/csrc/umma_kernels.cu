@@ -72,6 +72,7 @@ struct UmmaArgs {
   int npairs;             // 256-row pair tiles
   int nA, nB;             // shared-memory slots for A and stages for B
   int a_resident;         // A slots hold the whole tile (loaded once per tile)
+  int a_tma;              // DEC1, streaming A: raw e atoms arrive by TMA in an A slot pair and are transformed in place
   int nM, nS;             // message slots (ENC), store-staging slots
   int a_rel;              // commits that free an A slot: 2 (both MMA issuers) for resident A, else 1
   int two_issuers;        // second MMA issuer warp enabled (needs slices per chunk < B ring stages)
@@ -665,6 +666,9 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   } else {
     a.a_resident = 0; a.nA = 6; a.nB = avail - 6;
   }
+  // streaming DEC1: the raw e atoms (two A slots each) are prefetched by TMA, four atoms deep
+  a.a_tma = MODE == DEC1 && !a.a_resident && a.kl == 2 && ctx->tensor_variant == 0 && avail >= 11;
+  if (a.a_tma) { a.nA = 8; a.nB = avail - 8; }
   // resident A slots are read by both MMA issuer warps (alternating chunks) whenever a tile has >= 2 chunks
   a.two_issuers = 0;   // a second issuer warp was tried: the B ring is too short for two chunks in flight
   a.a_rel = (a.a_resident && a.two_issuers) ? 2 : 1;
@@ -679,6 +683,10 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   if (MODE != DEC1) {
     // byte rows straight into the UMMA layout: inner extent N (columns beyond read as zero), row pitch P
     rc = encode_2d(ctx, &tmA, const_cast<void *>(a_bytes), N, (uint64_t)a.B, P, kAtomK, kTileRows);
+    if (rc) return rc;
+  } else if (a.a_tma) {
+    // raw uint16 rows, one atom = 128 coefficients x 128 rows = 32 KB, row-major (256-byte rows) in shared memory
+    rc = encode_2d_ex(ctx, &tmA, const_cast<void *>(a.a_src), 2, P, (uint64_t)a.B, P * 2, kAtomK, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
   if (pair) {
@@ -792,6 +800,9 @@ int umma_decrypt(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uin
   a.o16_cyc = r1; a.o16_hi = q1; a.o8_cyc = (uint8_t *)ctx->d_b.ptr;
   int rc = launch_product<DEC1>(ctx, ctx->km_f, a, nullptr);
   if (rc) return rc;
+#ifdef NTRU_TRACE
+  if (getenv("NTRU_TRACE_DEC1_ONLY")) return NTRU_OK;   // leaves the DEC1 timeline in g_trace
+#endif
   UmmaArgs b = {};
   b.B = B;
   b.with_hi = q2 != nullptr;

@@ -179,6 +179,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       mbar_init(a_full(i), MODE == DEC1 ? 16 : 2);   // DEC1: 8 transform warps per CTA; else one producer per CTA
       mbar_init(a_empty(i), a.a_rel);                // tcgen05.commit (multicast) from each issuer that reads it
     }
+    if (MODE == DEC1 && a.a_tma) {
+      for (int j = 0; j < (a.nA >> 1); ++j) mbar_init(a_full(a.nA + j), 1);   // raw_full[j]: this CTA's TMA (+ bytes)
+    }
     for (int j = 0; j < a.nB; ++j) {
       mbar_init(b_full(j), 2);                       // one producer arrival per CTA (+ transaction bytes)
       mbar_init(b_empty(j), 1);
@@ -242,8 +245,35 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     }
     if (lane == 0) { TRACE(3, 12, 0); TRACE_NS(3, 13, 0); }
   } else if (warp == kPairAuxWarp) {
-    // ===================== A / message producer (both CTAs; ENC and DEC2 only) =====================
-    if (MODE != DEC1) {
+    // ===================== A / message producer (both CTAs) =====================
+    if (MODE == DEC1) {
+      if (a.a_tma) {
+        // streaming DEC1: the raw uint16 atom (128 rows x 256 bytes) lands in the A slot pair (2 pj, 2 pj + 1) that
+        // will hold its two byte limbs; the transform warps rewrite it in place.  TMA keeps nA / 2 atoms in flight,
+        // which the register prefetch of the transform warps (one atom) could not: a clock trace showed 2000-2500
+        // cycles per atom, load latency, against the 1024 cycles of MMA work an atom feeds.
+        const int parts = a.with_hi ? 2 : 1;
+        const uint32_t np = (uint32_t)a.nA >> 1;
+        uint32_t pj = 0, par = 0;
+        for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
+          const int a_row = T * 256 + (int)rank * kTileRows;
+          for (int part = 0; part < parts; ++part) {
+            for (int c = 0; c < a.nchunks; ++c) {
+              for (int at = first_atom(a, part == 1, c); at < a.atoms; ++at) {
+                mbar_wait(a_empty(2 * pj), par ^ 1);
+                mbar_wait(a_empty(2 * pj + 1), par ^ 1);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(a_full(a.nA + pj), 2u * kABytes);
+                  tma_load_2d(a_slot(2 * pj), &tmapA, at * kAtomK, a_row, a_full(a.nA + pj));
+                }
+                __syncwarp();
+                if (++pj == np) { pj = 0; par ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    } else {
       const uint32_t a_bytes = 2u * kABytes;
       const uint32_t lead_a_full = lead(a_full(0));
       const int parts = a.with_hi ? 2 : 1;
@@ -331,6 +361,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             mbar_wait(bfull0 + 8u * sb, b_par);
             if (lane == 0) TRACE(1, 2, cc);
             if (wait_a) mbar_wait(afull0 + 8u * sa, resident ? a_par : a_par_s);
+            if (lane == 0) TRACE(1, 3, cc);
             tc_fence_after();
             const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
             const uint64_t db = desc_hi | (uint64_t)(b_lo0 + sb * (kSlotBytes >> 4));
@@ -362,6 +393,54 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const int t = threadIdx.x;                           // 0..255 (warps 0-7)
     const int chunk = t & 7;                             // 16-byte chunk of the 128-byte A row
     const int r0 = t >> 3;                               // rows r0, r0+32, r0+64, r0+96
+    if (a.a_tma) {
+      // in place: raw atom (row r at byte 256 r of the slot pair) -> limb 0 in slot 2 pj, limb 1 in slot 2 pj + 1.
+      // Lanes 0-3 / 4-7 of a row read the halves of their 32 bytes in opposite order (no bank conflict).
+      const int parts = a.with_hi ? 2 : 1;
+      const uint32_t np = (uint32_t)a.nA >> 1;
+      const uint32_t lead_a_full = lead(a_full(0));
+      const uint32_t sel = (uint32_t)(chunk >> 2) & 1u;
+      uint32_t pj = 0, par = 0;
+      for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
+        for (int part = 0; part < parts; ++part) {
+          for (int c = 0; c < a.nchunks; ++c) {
+            for (int at = first_atom(a, part == 1, c); at < a.atoms; ++at) {
+              mbar_wait(a_full(a.nA + pj), par);
+              const uint32_t raw0 = a_slot(2 * pj);
+              uint4 w[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t base = raw0 + (uint32_t)(r0 + 32 * j) * 256u + (uint32_t)chunk * 32u;
+                const uint4 x = lds128(base + sel * 16u), y = lds128(base + (sel ^ 1u) * 16u);
+                w[2 * j] = sel ? y : x;
+                w[2 * j + 1] = sel ? x : y;
+              }
+              asm volatile("bar.sync 1, 256;" ::: "memory");   // every transform thread has read its part of the raw atom
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int r_in = r0 + 32 * j;
+                const uint32_t off = (uint32_t)((r_in >> 3) * 1024 + (r_in & 7) * 128 + ((chunk ^ (r_in & 7)) << 4));
+                const uint4 w0 = w[2 * j], w1 = w[2 * j + 1];
+                sts128(raw0 + off, make_uint4(__byte_perm(w0.x, w0.y, 0x6420), __byte_perm(w0.z, w0.w, 0x6420),
+                                              __byte_perm(w1.x, w1.y, 0x6420), __byte_perm(w1.z, w1.w, 0x6420)));
+                sts128(raw0 + kSlotBytes + off,
+                       make_uint4(__byte_perm((w0.x >> 6) & 0x00FC00FCu, (w0.y >> 6) & 0x00FC00FCu, 0x6420),
+                                  __byte_perm((w0.z >> 6) & 0x00FC00FCu, (w0.w >> 6) & 0x00FC00FCu, 0x6420),
+                                  __byte_perm((w1.x >> 6) & 0x00FC00FCu, (w1.y >> 6) & 0x00FC00FCu, 0x6420),
+                                  __byte_perm((w1.z >> 6) & 0x00FC00FCu, (w1.w >> 6) & 0x00FC00FCu, 0x6420)));
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive_cluster(lead_a_full + 16u * pj);
+                mbar_arrive_cluster(lead_a_full + 16u * pj + 8u);
+              }
+              if (++pj == np) { pj = 0; par ^= 1; }
+            }
+          }
+        }
+      }
+    } else {
     const uint16_t *src = reinterpret_cast<const uint16_t *>(a.a_src);
     // work list: the atoms whose A slots must be (re)built, in pipeline order
     struct Item { int T, part, c, at; uint32_t ia; int titer; bool valid; };
@@ -404,6 +483,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     cur.valid = cur.T < a.npairs;
     cur.at = 0;
     uint4 raw[8], raw_next[8];
+    int xn = 0;   // atoms built so far (trace tag)
     if (cur.valid) load_atom(cur, raw);
     while (cur.valid) {
       Item nxt = cur;
@@ -416,8 +496,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         sa0 = cur.ia % a.nA; par0 = (cur.ia / a.nA) & 1;
         sa1 = (cur.ia + 1) % a.nA; par1 = ((cur.ia + 1) / a.nA) & 1;
       }
+      if (t == 0) TRACE(4, 0, xn);
       mbar_wait(a_empty(sa0), par0 ^ 1);
       if (a.kl == 2) mbar_wait(a_empty(sa1), par1 ^ 1);
+      if (t == 0) TRACE(4, 1, xn);
       uint8_t *dst0 = smem + (size_t)sa0 * kSlotBytes;
       uint8_t *dst1 = smem + (size_t)sa1 * kSlotBytes;
 #pragma unroll
@@ -446,9 +528,12 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         mbar_arrive_cluster(lead(a_full(sa0)));
         if (a.kl == 2) mbar_arrive_cluster(lead(a_full(sa1)));
       }
+      if (t == 0) TRACE(4, 5, xn);
+      ++xn;
       cur = nxt;
 #pragma unroll
       for (int j = 0; j < 8; ++j) raw[j] = raw_next[j];
+    }
     }
   } else {
     // ===================== epilogue (both CTAs): TMEM -> registers -> shared staging -> TMA store ==========
@@ -664,7 +749,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 
 #ifdef NTRU_TRACE
   if (blockIdx.x == 0 && lane == 0) {
-    const int role = warp == kPairProducerWarp ? 3 : (warp == kPairMmaWarp ? 1 : (warp == (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0) ? 2 : 0));
+    const int role = warp == kPairProducerWarp ? 3 : (warp == kPairMmaWarp ? 1 : (warp == (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0) ? 2 : (MODE == DEC1 && warp == 0 ? 4 : 0)));
     if (role) {
       for (int i = 0; i < kTraceCap; ++i)
         g_trace[(role - 1) * kTraceCap + i] = i < trace_n[role - 1] ? trace_buf[(role - 1) * kTraceCap + i] : 0ull;

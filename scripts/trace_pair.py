@@ -51,16 +51,17 @@ recs = [x for x in recs if not (x[0] == 3 and x[1] >= 10)]
 rec = np.array(recs, dtype=np.int64)
 rec[:, 3] -= rec[:, 3].min()
 rec = rec[np.argsort(rec[:, 3], kind="stable")]
-nm = {(4,0):"MMA1 chunk start",(4,1):"MMA1 got tempty",(4,5):"MMA1 issued",(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
+nm = {(4,0):"xform loads issued",(4,1):"xform got a_empty",(4,5):"xform arrived",(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
       (2,0):"epi start",(2,1):"epi got tfull",(2,2):"epi done",(2,3):"epi got m_full",(2,4):"epi tmem loaded",(2,5):"epi math done",(2,6):"epi staged (after wait_group.read + STS)",(2,7):"epi fenced",(3,0):"prod wait b_empty",(3,1):"prod got b_empty",(3,2):"prod issued"}
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 19)
 prev = {}
 for role, e, idx, t in rec:
-    if "--mma" in sys.argv and role != 1:
+    if "--mma" in sys.argv and role not in (1, 4):
         continue
     if "--ring" in sys.argv and not (role == 3 or (role == 1 and e in (2, 4, 5))):
         continue
-    if lo <= idx <= hi:
+    xlo, xhi = int(os.environ.get("TRACE_XLO", -1)), int(os.environ.get("TRACE_XHI", -1))
+    if (role != 4 and lo <= idx <= hi) or (role == 4 and xlo <= idx <= xhi):
         d = t - prev.get(role, t)
         prev[role] = t
         print(f"{t:9d} (+{d:5d})  cc={idx:3d}  {nm.get((role,e),(role,e))}")
