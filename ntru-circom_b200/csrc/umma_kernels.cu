@@ -659,8 +659,14 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   a.npairs = (int)((a.B + 2 * kTileRows - 1) / (2 * kTileRows));
   a.nS = 2;
   a.nM = MODE == ENC ? 2 : 0;
-  const int avail = kPairSlots - a.nS - a.nM;
   const int a_slots = a.atoms * a.kl;
+  // ENC above N = 512: k_umma_pair<ENC, 0, 1> stages one unit per TMA store (one staging slot) and reads the message
+  // bytes from global memory (no message slots).  The three slots go to the B ring, and the A operand stays resident up
+  // to N = 1024: with 4 stages the ring covered ~2000 cycles of TMA latency at 900 cycles per slice (clock trace,
+  // NTRU_DEBUG_NOB timing), and streaming A doubled the L2 -> SM traffic at N = 821.
+  const bool pu1 = MODE == ENC && ctx->tensor_variant == 0 && a.atoms >= 5 && !getenv("NTRU_DEBUG_NO_PU1");
+  if (pu1) { a.nS = 1; a.nM = 0; }
+  const int avail = kPairSlots - a.nS - a.nM;
   if (a_slots + 4 <= avail) {
     a.a_resident = 1; a.nA = a_slots; a.nB = avail - a_slots;
   } else {
@@ -699,9 +705,11 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     int oelem[3], obox[3];
     CUtensorMapSwizzle oswz[3];
     if (MODE == ENC || MODE == DEC1) {
-      optr[0] = a.o16_cyc; oelem[0] = 2; obox[0] = 32; oswz[0] = CU_TENSOR_MAP_SWIZZLE_64B;
-      optr[2] = a.o16_hi; oelem[2] = 2; obox[2] = 32; oswz[2] = CU_TENSOR_MAP_SWIZZLE_64B;
-      if (MODE == ENC) { optr[1] = a.o16_cyc2; oelem[1] = 2; obox[1] = 32; oswz[1] = CU_TENSOR_MAP_SWIZZLE_64B; }
+      const int ob = pu1 ? 16 : 32;
+      const CUtensorMapSwizzle osw = pu1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+      optr[0] = a.o16_cyc; oelem[0] = 2; obox[0] = ob; oswz[0] = osw;
+      optr[2] = a.o16_hi; oelem[2] = 2; obox[2] = ob; oswz[2] = osw;
+      if (MODE == ENC) { optr[1] = a.o16_cyc2; oelem[1] = 2; obox[1] = ob; oswz[1] = osw; }
       else { optr[1] = a.o8_cyc; oelem[1] = 1; obox[1] = 32; oswz[1] = CU_TENSOR_MAP_SWIZZLE_NONE; }
     } else {
       optr[0] = a.o8_cyc; optr[1] = a.o8_cyc2; optr[2] = a.o8_hi;
@@ -731,10 +739,23 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
       switch (dbg) {
         NTRU_DBG_LAUNCH(1) NTRU_DBG_LAUNCH(2) NTRU_DBG_LAUNCH(4) NTRU_DBG_LAUNCH(8) NTRU_DBG_LAUNCH(12) NTRU_DBG_LAUNCH(16)
         default:
-          k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+          if (pu1) {
+            cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
+            k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+          } else {
+            k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+          }
       }
 #else
-      k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+      if (pu1) {
+        if (!(ctx->umma_attr_set & 8)) {
+          NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+          ctx->umma_attr_set |= 8;
+        }
+        k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+      } else {
+        k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+      }
 #endif
     } else {
       const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;

@@ -19,14 +19,14 @@
 // Only the leader's MMA warp issues MMAs; producer, transform and epilogue warps run in both CTAs.
 
 #ifdef NTRU_TRACE
-// debug timeline of cluster 0 / CTA 0: each traced thread appends (tag << 40 | clock) words to its own
-// shared-memory lane buffer (cheap: one STS), dumped to global memory at kernel end.
-constexpr int kTraceLanes = 4, kTraceCap = 448;   // MMA issuer 0, epilogue warp 0, producer, MMA issuer 1
+// debug timeline of cluster 0 / CTA 0: each traced thread appends (tag << 40 | clock) words to its own lane of a
+// global buffer (one fire-and-forget store; the shared-memory layout stays the production one).
+constexpr int kTraceLanes = 4, kTraceCap = 2048;   // MMA issuer 0, epilogue warp 0, producer, MMA issuer 1
 __device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
 #define TRACE(role, ev, idx)                                                                      \
   do {                                                                                            \
     if (blockIdx.x == 0 && trace_n[role - 1] < kTraceCap) {                                       \
-      trace_buf[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                   \
+      g_trace[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                     \
           ((unsigned long long)(((ev) << 12) | ((idx) & 0xfff)) << 40) | (clock64() & 0xffffffffffull); \
     }                                                                                             \
   } while (0)
@@ -35,7 +35,7 @@ __device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
     if (blockIdx.x == 0 && trace_n[role - 1] < kTraceCap) {                                       \
       unsigned long long _ns;                                                                     \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_ns));                                     \
-      trace_buf[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                   \
+      g_trace[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                     \
           ((unsigned long long)(((ev) << 12) | ((idx) & 0xfff)) << 40) | (_ns & 0xffffffffffull); \
     }                                                                                             \
   } while (0)
@@ -45,22 +45,14 @@ __device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
 #endif
 
 constexpr int kSlotBytes = 16384;
-#ifdef NTRU_TRACE
-constexpr int kPairSlots = 13;   // 16 KB of shared memory go to the trace buffers
-#else
 constexpr int kPairSlots = 14;
-#endif
 constexpr int kPairBars = 4 * kPairSlots + 8;   // a_full/a_empty/b_full/b_empty[kPairSlots], tmem full/empty[2], m full/empty[2]
 // Warp roles: 16 = B-ring TMA producer, 17 = MMA issuer, 18 = A / message producer.  Warps 0-15 are epilogue
 // warps in two groups of 8, one per TMEM buffer (DEC1: 0-7 transform, 8-15 epilogue in two groups of 4); an
 // epilogue warp reads TMEM lanes 32*(warp%4)...
 constexpr int kPairProducerWarp = 16, kPairMmaWarp = 17, kPairAuxWarp = 18, kPairEpiWarp0Dec1 = 8;
 constexpr int kPairThreads = 19 * 32;
-#ifdef NTRU_TRACE
-constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 1024 + 8 * kTraceLanes * kTraceCap;
-#else
 constexpr size_t kPairSmemBytes = (size_t)kPairSlots * kSlotBytes + 1024 /*align*/ + 8 * kPairBars + 64;
-#endif
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -140,7 +132,10 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signe
 //   1 epilogue hands the buffers back without reading them     2 TMEM reads only (no arithmetic, no stores)
 //   4 no TMEM reads (arithmetic and stores on register garbage) 8 no staging stores and no TMA stores
 //   16 staging stores and fences, but no TMA stores
-template <int MODE, int DBG = 0>
+//
+// PU = units (16 coefficients) a warp stages per TMA store.  ENC with PU = 1 halves the staging area (one slot instead of
+// two): at 768 < N <= 896 that slot is what lets the A operand stay resident beside a 4-stage B ring (launch_product).
+template <int MODE, int DBG = 0, int PU = (MODE == 2 ? 4 : 2)>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA,
             const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapO0,
@@ -166,7 +161,6 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   const uint32_t stage_base = smem_base + (a.nA + a.nB + a.nM) * kSlotBytes;
 
 #ifdef NTRU_TRACE
-  unsigned long long *trace_buf = reinterpret_cast<unsigned long long *>(smem + (size_t)kPairSlots * kSlotBytes + 1024);
   int trace_n[kTraceLanes] = {0, 0, 0, 0};
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,7 +292,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
               }
             }
-            if (MODE == ENC && !hi) {   // the chunk's 128 message bytes per row, for this CTA's epilogue
+            if (MODE == ENC && PU != 1 && !hi) {   // the chunk's 128 message bytes per row, for this CTA's epilogue
               const uint32_t ms = mc & 1;
               mbar_wait(m_empty(ms), ((mc >> 1) & 1) ^ 1);
               if (elect_one()) {
@@ -358,9 +352,11 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           uint32_t sa = resident ? (uint32_t)(a0 * a.kl) : sas;
           uint32_t accumulate = 0;
           for (uint32_t i = 0; i < nsl; ++i) {
-            mbar_wait(bfull0 + 8u * sb, b_par);
-            if (lane == 0) TRACE(1, 2, cc);
-            if (wait_a) mbar_wait(afull0 + 8u * sa, resident ? a_par : a_par_s);
+            // even lanes poll the B stage, odd lanes the A slot, in ONE try_wait round trip (the trace showed ~180
+            // cycles per poll of an already complete barrier, paid once per barrier and slice in the streaming modes)
+            if (wait_a) mbar_wait((lane & 1) ? afull0 + 8u * sa : bfull0 + 8u * sb, (lane & 1) ? (resident ? a_par : a_par_s) : b_par);
+            else mbar_wait(bfull0 + 8u * sb, b_par);
+            __syncwarp();
             if (lane == 0) TRACE(1, 3, cc);
             tc_fence_after();
             const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
@@ -387,7 +383,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           }
         }
       }
-    }
+  }
   } else if (MODE == DEC1 && warp < kPairEpiWarp0Dec1) {
     // ===================== DEC1 transform (both CTAs): e (uint16, global) -> byte-limb A slots =====
     const int t = threadIdx.x;                           // 0..255 (warps 0-7)
@@ -401,11 +397,14 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       const uint32_t lead_a_full = lead(a_full(0));
       const uint32_t sel = (uint32_t)(chunk >> 2) & 1u;
       uint32_t pj = 0, par = 0;
+      int xn = 0;   // atoms built so far (trace tag)
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
         for (int part = 0; part < parts; ++part) {
           for (int c = 0; c < a.nchunks; ++c) {
-            for (int at = first_atom(a, part == 1, c); at < a.atoms; ++at) {
+            for (int at = first_atom(a, part == 1, c); at < a.atoms; ++at, ++xn) {
+              if (t == 0) TRACE(4, 0, xn);
               mbar_wait(a_full(a.nA + pj), par);
+              if (t == 0) TRACE(4, 1, xn);
               const uint32_t raw0 = a_slot(2 * pj);
               uint4 w[8];
 #pragma unroll
@@ -435,6 +434,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 mbar_arrive_cluster(lead_a_full + 16u * pj);
                 mbar_arrive_cluster(lead_a_full + 16u * pj + 8u);
               }
+              if (t == 0) TRACE(4, 5, xn);
               if (++pj == np) { pj = 0; par ^= 1; }
             }
           }
@@ -547,7 +547,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     // row stores cost 32 cache lines per warp instruction).  ENC reads the message bytes from a TMA-loaded tile.
     constexpr int kGroupWarps = kEpiWarps / 2;                     // 8 (ENC, DEC2) or 4 (DEC1)
     constexpr int kSub = kGroupWarps / 4;                          // warps per TMEM lane quadrant within a group
-    constexpr int kPassUnits = MODE == DEC2 ? 4 : 2;               // units staged per TMA store (64-byte rows)
+    // ENC with PU = 1 (large N) also reads its message bytes from global memory instead of a TMA-loaded tile: no message
+    // slots, so the B ring gets them (launch_product).
+    constexpr bool kMsgGlobal = MODE == ENC && PU == 1;
+    constexpr int kPassUnits = PU;                                 // units staged per TMA store (64-byte rows; 32-byte rows for PU = 1)
     const int ew = warp - (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0);
     const int quad = warp & 3;
     const uint32_t grp = (uint32_t)(ew >> 2) & 1u;
@@ -558,9 +561,12 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const uint32_t Q2 = a.qmask | (a.qmask << 16);
     const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;   // x > q/2  <=>  bit log2(q) of x + q/2 - 1
     const int logq = 31 - __clz(a.q);
-    const uint32_t stage = stage_base + (uint32_t)ew * (MODE == DEC1 ? 4096u : 2048u);   // this warp's staging tile
-    // swizzled position of 16-byte chunk `ch` of this lane's 64-byte staging row (SWIZZLE_64B)
-    const uint32_t st_row = stage + (uint32_t)lane * 64u, st_x = (uint32_t)(lane >> 1) & 3u;
+    constexpr uint32_t kRowBytes = (MODE == DEC2 ? 16u : 32u) * PU;   // staging row: 64 bytes (SWIZZLE_64B) or 32 (SWIZZLE_32B)
+    static_assert(kRowBytes == 64 || kRowBytes == 32, "staging rows are one 64-byte or 32-byte swizzle span");
+    const uint32_t stage = stage_base + (uint32_t)ew * (MODE == DEC1 ? 4096u : 32u * kRowBytes);   // this warp's staging tile
+    // swizzled position of 16-byte chunk `ch` of this lane's staging row: ch ^ st_x
+    const uint32_t st_row = stage + (uint32_t)lane * kRowBytes;
+    const uint32_t st_x = kRowBytes == 64 ? (uint32_t)(lane >> 1) & 3u : (uint32_t)(lane >> 2) & 1u;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t m_row = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128), m_x = (uint32_t)row_in_tile & 7u;
     const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * kAccCols;
@@ -576,17 +582,27 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           if (MODE == ENC && !hi) ++mc;
           if ((cc & 1u) != grp) continue;
           if (lane == 0 && ew == 0) TRACE(2, 0, cc);
+          uint4 mg[4];                                            // kMsgGlobal: this lane's message bytes of the chunk
+          if (kMsgGlobal && !hi) {                                // (in flight while the accumulators are still being computed)
+            const size_t grow = (size_t)(out_row + lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = c * a.NCo + (sub * upw + j) * 16;
+              mg[j] = (j < upw && grow < a.B && col < a.P) ? __ldg(reinterpret_cast<const uint4 *>(a.m + grow * (size_t)a.P + col))
+                                                          : make_uint4(0, 0, 0, 0);
+            }
+          }
           mbar_wait(my_tfull, (cc >> 1) & 1);
           tc_fence_after();
           if (lane == 0 && ew == 0) TRACE(2, 1, cc);
-          if (MODE == ENC && !hi) mbar_wait(m_full(ms), m_par);
+          if (MODE == ENC && !kMsgGlobal && !hi) mbar_wait(m_full(ms), m_par);
           if (lane == 0 && ew == 0) TRACE(2, 3, cc);
           if (DBG & 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               mbar_arrive_cluster(lead_tempty);
-              if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));
+              if (MODE == ENC && !kMsgGlobal && !hi) mbar_arrive(m_empty(ms));
             }
             continue;
           }
@@ -596,7 +612,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             uint32_t res[kPassUnits * (MODE == DEC2 ? 4 : 8)];      // packed results of this pass
             uint32_t bres[kPassUnits * 4];                          // DEC1: lifted polynomial b (bytes)
             uint4 mm[kPassUnits];                                   // ENC: message bytes of the pass
-            if (MODE == ENC && !hi) {
+            if (kMsgGlobal) {
+              if (!hi) mm[0] = ps == 0 ? mg[0] : (ps == 1 ? mg[1] : (ps == 2 ? mg[2] : mg[3]));   // PU == 1: pass ps = unit ps
+            } else if (MODE == ENC && !hi) {
 #pragma unroll
               for (int j = 0; j < kPassUnits; ++j) mm[j] = lds128(m_slot(ms) + m_row + ((((uint32_t)(u0 + j)) ^ m_x) << 4));
             }
@@ -629,7 +647,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               __syncwarp();
               if (lane == 0) {
                 mbar_arrive_cluster(lead_tempty);
-                if (MODE == ENC && !hi) mbar_arrive(m_empty(ms));   // message tile is in registers
+                if (MODE == ENC && !kMsgGlobal && !hi) mbar_arrive(m_empty(ms));   // message tile is in registers
               }
             }
             if (DBG & 2) {
@@ -748,12 +766,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   }
 
 #ifdef NTRU_TRACE
-  if (blockIdx.x == 0 && lane == 0) {
+  if (blockIdx.x == 0 && lane == 0) {   // terminate the lanes this launch wrote
     const int role = warp == kPairProducerWarp ? 3 : (warp == kPairMmaWarp ? 1 : (warp == (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0) ? 2 : (MODE == DEC1 && warp == 0 ? 4 : 0)));
-    if (role) {
-      for (int i = 0; i < kTraceCap; ++i)
-        g_trace[(role - 1) * kTraceCap + i] = i < trace_n[role - 1] ? trace_buf[(role - 1) * kTraceCap + i] : 0ull;
-    }
+    if (role && trace_n[role - 1] < kTraceCap) g_trace[(role - 1) * kTraceCap + trace_n[role - 1]] = 0ull;
   }
 #endif
   tc_fence_before();

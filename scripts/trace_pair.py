@@ -25,7 +25,7 @@ r = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); eng.sample_r_dev(r
 m = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); m[:, :NN] = torch.randint(0, 2, (rows, NN), device="cuda", dtype=torch.uint8)
 val = torch.empty((rows, P), dtype=torch.int16, device="cuda"); quo = torch.empty_like(val)
 out = torch.empty((rows, P), dtype=torch.uint8, device="cuda"); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)
-LANES, CAP = 4, 448
+LANES, CAP = 4, 2048
 buf = np.zeros(LANES * CAP, dtype=np.uint64)
 dump = eng.lib.ntru_debug_trace_dump
 dump.argtypes = [ctypes.c_void_p, ctypes.c_uint]
@@ -40,7 +40,7 @@ for role in range(LANES):
     for w in buf[role * CAP:(role + 1) * CAP]:
         w = int(w)
         if w == 0:
-            continue
+            break
         tag, clk = w >> 40, w & 0xffffffffff
         recs.append((role + 1, tag >> 12, tag & 0xfff, clk))
 marks = {e: t for (role, e, idx, t) in recs if role == 3 and e in (10, 11, 12, 13)}
@@ -51,7 +51,7 @@ recs = [x for x in recs if not (x[0] == 3 and x[1] >= 10)]
 rec = np.array(recs, dtype=np.int64)
 rec[:, 3] -= rec[:, 3].min()
 rec = rec[np.argsort(rec[:, 3], kind="stable")]
-nm = {(4,0):"xform loads issued",(4,1):"xform got a_empty",(4,5):"xform arrived",(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
+nm = {(4,0):"xform loads issued / waits raw",(4,1):"xform got a_empty / raw_full",(4,5):"xform arrived",(1,0):"mma chunk start",(1,1):"mma got tempty",(1,4):"mma wait b_full",(1,2):"mma got b_full",(1,3):"mma got a_full",(1,5):"mma issued",
       (2,0):"epi start",(2,1):"epi got tfull",(2,2):"epi done",(2,3):"epi got m_full",(2,4):"epi tmem loaded",(2,5):"epi math done",(2,6):"epi staged (after wait_group.read + STS)",(2,7):"epi fenced",(3,0):"prod wait b_empty",(3,1):"prod got b_empty",(3,2):"prod issued"}
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (16, 19)
 prev = {}

@@ -217,7 +217,7 @@ def test_pack_output_unpack_input_vs_oracle(cfg, nb, engines, golden):
 
 GENERAL_NQ = [(8, 4), (16, 32), (33, 64), (100, 256), (191, 512), (193, 1024), (255, 2048), (256, 2048), (257, 4096),
               (511, 8192), (512, 2048), (513, 2048), (640, 2048), (641, 4096), (704, 8192), (705, 2048), (832, 4096),
-              (833, 2048), (1024, 8192)]
+              (833, 2048), (768, 2048), (769, 4096), (896, 8192), (897, 2048), (1024, 8192)]
 
 
 @pytest.mark.parametrize("N,q", GENERAL_NQ)
