@@ -7,12 +7,13 @@
 // (ncu: lts throughput 65-75 % of peak, tensor pipe 34 %).
 //
 // The A operand (128 rows x K bytes per CTA) is kept RESIDENT in shared memory for the whole tile when it
-// fits beside a B ring of at least 4 stages (DEC2 always, ENC up to N = 768, DEC1 up to N = 512): it is loaded
-// (TMA) or built (DEC1 transform warps)
-// once per tile instead of once per accumulator chunk.  When it does not fit, A slices stream through a
-// small ring exactly like B slices.
+// fits beside a B ring of at least 4 stages (ENC and DEC2 always, DEC1 up to N = 512): it is loaded (TMA) or built
+// (DEC1 transform warps, from registers prefetched one atom ahead) once per tile instead of once per accumulator
+// chunk.  DEC1 above N = 512 streams A: the raw uint16 atom lands by TMA in the slot pair of its two byte limbs
+// (four atoms in flight) and the transform warps split it in place (a.a_tma).  ENC above N = 512 runs the PU = 1
+// instantiation (one staging slot, message bytes from global memory): the B ring gets the three slots.
 //
-// Shared memory: 14 slots of 16 KB = nA A-slots + nB B-stages.  Barriers (same offsets in both CTAs):
+// Shared memory: 14 slots of 16 KB = nA A-slots + nB B-stages + nM message slots + nS staging slots.  Barriers (same offsets in both CTAs):
 //   a_full[i], b_full[j]   : used in the LEADER CTA only; both CTAs' TMA loads / transform warps signal them
 //   a_empty[i], b_empty[j] : in both CTAs, signalled by tcgen05.commit multicast from the leader's MMA thread
 //   tmem_full[b]           : in both CTAs (commit multicast);  tmem_empty[b]: leader only, all epilogue warps
