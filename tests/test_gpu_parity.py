@@ -52,6 +52,15 @@ def _paths(nb, eng):
     return out
 
 
+def seeded(seed):
+    """rand32 replacement for crypto.getRandomValues: NTRU decryption can fail for unlucky r (1 in 3000 at the default
+    parameters, 1 in 20 for a sum of two ciphertexts -- "this test may fail" upstream), so every test that lets the class
+    draw its own randomness pins the draws; the seeds are checked against the oracle in test_host.py."""
+    import random
+    rng = random.Random(seed)
+    return lambda: rng.getrandbits(32)
+
+
 @pytest.mark.parametrize("cfg", CFGS)
 def test_golden_vectors_both_schedules(cfg, nb, engines, golden):
     g, eng = golden(cfg), engines(cfg)
@@ -270,7 +279,8 @@ def test_string_batches_and_multi_block_messages(nb, golden):
     (index.js:80-86) and the oracle's codec; strings longer than floor(N / 8) characters split into blocks."""
     g = golden("default167")
     k = o.make_key("default167", 300)
-    mine = nb.NTRU(dict(o.CONFIGS["default167"]), f=list(k.f), fq=list(k.fq), fp=list(k.fp), g=list(k.g), h=list(k.h))
+    mine = nb.NTRU(dict(o.CONFIGS["default167"]), f=list(k.f), fq=list(k.fq), fp=list(k.fp), g=list(k.g), h=list(k.h),
+                   rand32=seeded(11))
     texts = ["Hello World", "", "a", "x" * 20, "NTRU on B200!", "\xe9\xff"]
     enc = mine.encryptStrBatch(texts)
     assert enc.shape == (len(texts), 167)
@@ -392,12 +402,12 @@ def test_class_api_matches_reference_objects(cfg, nb, golden):
 
 def test_string_roundtrip_and_wrong_key(nb):
     # test/reference.test.js:6-25
-    k = nb.NTRU()
+    k = nb.NTRU(rand32=seeded(21))
     k.generatePrivateKeyF()
     k.generateNewPublicKeyGH()
     e = k.encryptStr("Hello World")
     assert k.decryptStr(e) == "Hello World"
-    other = nb.NTRU()
+    other = nb.NTRU(rand32=seeded(22))
     other.generatePrivateKeyF()
     assert other.decryptStr(e) != "Hello World"
 
@@ -405,7 +415,7 @@ def test_string_roundtrip_and_wrong_key(nb):
 def test_large_key_string_roundtrip(nb):
     # test/reference.test.js:27-44
     d = 701 // 3
-    k = nb.NTRU({"N": 701, "q": 8192, "df": d, "dg": d, "dr": d})
+    k = nb.NTRU({"N": 701, "q": 8192, "df": d, "dg": d, "dr": d}, rand32=seeded(31))
     k.generatePrivateKeyF()
     k.generateNewPublicKeyGH()
     assert k.decryptStr(k.encryptStr("Big polys")) == "Big polys"
@@ -415,7 +425,7 @@ def test_additive_homomorphism(nb, golden):
     # test/reference.test.js:48-61 ("this test may fail" upstream: use a fixed valid key)
     g = golden("default167")
     k = nb.NTRU(dict(o.CONFIGS["default167"], f=g["f"].tolist(), fp=o.trim_polynomial(g["fp"].tolist()),
-                     h=o.trim_polynomial(g["h"].tolist())))
+                     h=o.trim_polynomial(g["h"].tolist())), rand32=seeded(1))
     e1 = k.encryptBits([1, 2, 1, 0, 1])["value"]
     e2 = k.encryptBits([0, 1, 1, 1, 0, 1, 0, 1])["value"]
     s = nb.addPolynomials(e1, e2, k.q)

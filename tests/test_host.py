@@ -132,3 +132,35 @@ def test_sampler_generator_is_reproducible():
     a = [nb.sampler_rand32(1, 2, i) for i in range(4)]
     assert a == [nb.sampler_rand32(1, 2, i) for i in range(4)]
     assert len(set(a)) == 4 and all(0 <= x < 2 ** 32 for x in a)
+
+
+def test_seeds_of_the_gpu_class_tests_decrypt_in_the_oracle(golden):
+    """tests/test_gpu_parity.py pins the draws of every test that lets ``class NTRU`` sample its own randomness
+    (NTRU decryption fails for unlucky r: ~1 in 3000 at the default parameters, ~1 in 20 for a two-ciphertext sum).
+    The GPU path is bit-exact with the oracle, so the same seeds replayed here prove those tests deterministic."""
+    g = golden("default167")
+    k = o.NTRU(dict(o.CONFIGS["default167"], f=g["f"].tolist(), fp=o.trim_polynomial(g["fp"].tolist()),
+                    h=o.trim_polynomial(g["h"].tolist())), rng=random.Random(1))
+    e1 = k.encryptBits([1, 2, 1, 0, 1])["value"]
+    e2 = k.encryptBits([0, 1, 1, 1, 0, 1, 0, 1])["value"]
+    assert k.decryptBits(o.sum_ciphertexts([e1, e2], k.q))["value"] == [1, 0, 2, 1, 1, 1, 0, 1]
+    k = o.NTRU(rng=random.Random(21))
+    k.generatePrivateKeyF()
+    k.generateNewPublicKeyGH()
+    e = k.encryptStr("Hello World")
+    assert k.decryptStr(e) == "Hello World"
+    other = o.NTRU(rng=random.Random(22))
+    other.generatePrivateKeyF()
+    assert other.decryptStr(e) != "Hello World"
+    k = o.make_key("default167", 300)
+    k.rng = random.Random(11)
+    for t in ["Hello World", "", "a", "x" * 20, "NTRU on B200!", "\xe9\xff"]:
+        assert k.decryptStr(k.encryptStr(t)) == (t if t else "\x00")
+    for t in ["The quick brown fox jumps over the lazy dog. " * 3, "short", "z" * 40]:
+        for i in range(0, len(t), 20):
+            assert k.decryptStr(k.encryptStr(t[i:i + 20])) == t[i:i + 20]
+    d = 701 // 3
+    k = o.NTRU({"N": 701, "q": 8192, "df": d, "dg": d, "dr": d}, rng=random.Random(31))
+    k.generatePrivateKeyF()
+    k.generateNewPublicKeyGH()
+    assert k.decryptStr(k.encryptStr("Big polys")) == "Big polys"
