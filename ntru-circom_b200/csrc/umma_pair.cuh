@@ -607,9 +607,22 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             }
             continue;
           }
-          for (int ps = 0; ps < npass; ++ps) {
+          // passes of this warp that hold at least one column below the pitch (the last chunk of a tile is padding
+          // beyond it: 5 of 8 units at N = 167, 677, 4 of 8 at N = 821); the others would be clipped by the TMA store
+          int npe = (a.P - (c * a.NCo + sub * upw * 16) + kPassUnits * 16 - 1) / (kPassUnits * 16);
+          npe = npe < 0 ? 0 : (npe > npass ? npass : npe);
+          if (npe == 0) {                                           // nothing to drain: hand the buffers back (in phase)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_cluster(lead_tempty);
+              if (MODE == ENC && !kMsgGlobal && !hi) mbar_arrive(m_empty(ms));
+            }
+            continue;
+          }
+          for (int ps = 0; ps < npe; ++ps) {
             const int u0 = sub * upw + ps * kPassUnits;
-            const bool last_pass = ps == npass - 1;
+            const bool last_pass = ps == npe - 1;
             uint32_t res[kPassUnits * (MODE == DEC2 ? 4 : 8)];      // packed results of this pass
             uint32_t bres[kPassUnits * 4];                          // DEC1: lifted polynomial b (bytes)
             uint4 mm[kPassUnits];                                   // ENC: message bytes of the pass
