@@ -19,7 +19,10 @@
  *     (index.js:96-103, 123-131).  Any output pointer may be NULL (not produced).
  *   - Device-buffer entry points (*_dev) take device pointers whose row pitch is
  *     ntru_pitch(ctx) ELEMENTS for every array (a multiple of 16, >= N+1), run
- *     asynchronously on the context's stream and copy nothing.
+ *     asynchronously on the context's stream and copy nothing.  Columns N..pitch-1
+ *     of every INPUT row must be zero; every output row is written with zeros there
+ *     (so an output row is the reference's expandArray(., N+1) witness field and can
+ *     be fed back as an input).
  *   - Every function returns NTRU_OK (0) or a negative NTRU_E_* code;
  *     ntru_last_error(ctx) gives the message.  There is no CPU fallback: without
  *     a CUDA device every compute entry point fails with NTRU_E_CUDA.

@@ -165,6 +165,12 @@ __global__ void __launch_bounds__(160) k_encrypt_generic(const EncArgs a) {
       if (a.value) *reinterpret_cast<uint4 *>(a.value + off) = pack8_u16(rem);
       if (a.rem) *reinterpret_cast<uint4 *>(a.rem + off) = pack8_u16(rem);
       if (a.quo) *reinterpret_cast<uint4 *>(a.quo + off) = pack8_u16(quo);
+    } else if (T * c < P) {   // pad columns beyond the last 8-coefficient block: zero, like every schedule
+      const size_t off = row * (size_t)P + T * c;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      if (a.value) *reinterpret_cast<uint4 *>(a.value + off) = z;
+      if (a.rem) *reinterpret_cast<uint4 *>(a.rem + off) = z;
+      if (a.quo) *reinterpret_cast<uint4 *>(a.quo + off) = z;
     }
     __syncthreads();
   }
@@ -216,6 +222,11 @@ __global__ void __launch_bounds__(160) k_decrypt_generic(const DecArgs a) {
       const size_t off = row * (size_t)P + T * c;
       if (a.r1) *reinterpret_cast<uint4 *>(a.r1 + off) = pack8_u16(rem);
       if (a.q1) *reinterpret_cast<uint4 *>(a.q1 + off) = pack8_u16(quo);
+    } else if (T * c < P) {
+      const size_t off = row * (size_t)P + T * c;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      if (a.r1) *reinterpret_cast<uint4 *>(a.r1 + off) = z;
+      if (a.q1) *reinterpret_cast<uint4 *>(a.q1 + off) = z;
     }
     __syncthreads();
     // product 2: c = lin(fp, b) -- window = fp, multiplier = b
@@ -241,6 +252,12 @@ __global__ void __launch_bounds__(160) k_decrypt_generic(const DecArgs a) {
       if (a.value) *reinterpret_cast<uint2 *>(a.value + off) = pack8_u8(rem);
       if (a.r2) *reinterpret_cast<uint2 *>(a.r2 + off) = pack8_u8(rem);
       if (a.q2) *reinterpret_cast<uint2 *>(a.q2 + off) = pack8_u8(quo);
+    } else if (T * c < P) {
+      const size_t off = row * (size_t)P + T * c;
+      const uint2 z = make_uint2(0, 0);
+      if (a.value) *reinterpret_cast<uint2 *>(a.value + off) = z;
+      if (a.r2) *reinterpret_cast<uint2 *>(a.r2 + off) = z;
+      if (a.q2) *reinterpret_cast<uint2 *>(a.q2 + off) = z;
     }
     __syncthreads();
   }

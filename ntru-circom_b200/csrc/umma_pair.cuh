@@ -589,8 +589,18 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int col = c * a.NCo + (sub * upw + j) * 16;
-              mg[j] = (j < upw && grow < a.B && col < a.P) ? __ldg(reinterpret_cast<const uint4 *>(a.m + grow * (size_t)a.P + col))
+              mg[j] = (j < upw && grow < a.B && col < a.N) ? __ldg(reinterpret_cast<const uint4 *>(a.m + grow * (size_t)a.P + col))
                                                           : make_uint4(0, 0, 0, 0);
+              if (col + 16 > a.N) {   // the unit that straddles N: pad bytes of the caller's row do not count (the TMA tile
+                const int keep = a.N - col;                          // of the PU = 2 path reads them as zero as well)
+                uint32_t w[4] = {mg[j].x, mg[j].y, mg[j].z, mg[j].w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const int kb = keep - 4 * t;
+                  w[t] = kb >= 4 ? w[t] : (kb <= 0 ? 0u : (w[t] & ((1u << (8 * kb)) - 1u)));
+                }
+                mg[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
             }
           }
           mbar_wait(my_tfull, (cc >> 1) & 1);

@@ -29,6 +29,11 @@ def engines(nb, golden):
             eng = nb.Engine(int(g["N"]), int(g["p"]), int(g["q"]), 0)
             eng.set_public_key(g["h"])
             eng.set_private_key(g["f"], g["fp"])
+            try:                      # tests mix torch device tensors with *_dev calls: one stream orders them
+                import torch
+                eng.set_stream(torch.cuda.current_stream().cuda_stream)
+            except ImportError:
+                pass
             cache[cfg] = eng
         return cache[cfg]
     yield get
@@ -603,3 +608,56 @@ def test_full_size_round_trip_and_checksums(nb, engines, golden):
     want = o.encrypt_batch(g["h"].astype(np.int64), r[pick, :N].cpu().numpy(), m[pick, :N].cpu().numpy(), q)
     assert np.array_equal(val[pick].cpu().numpy().view(np.uint16)[:, :N], want["value"])
     assert np.array_equal(quo[pick].cpu().numpy().view(np.uint16)[:, : N + 1], want["quotientE"])
+
+
+@pytest.mark.parametrize("cfg", ["default167", "hps509", "hps677", "hps821"])
+def test_pad_columns_of_device_rows_do_not_count(cfg, nb, engines, golden):
+    """Device-resident rows have pitch P > N.  The contract (include/ntru_b200.h) asks for zero pad columns in the inputs
+    and writes zero pad columns in every output, on every schedule.  The tcgen05 schedule is also insensitive to what a
+    caller leaves in columns N..P-1 of r, m and e: it reads them through TMA maps of extent N, against zero key-matrix
+    columns, or with an explicit mask (ENC above N = 512 reads its message bytes from global memory)."""
+    torch = pytest.importorskip("torch")
+    g, eng = golden(cfg), engines(cfg)
+    N, q, dr, P, dev = int(g["N"]), int(g["q"]), int(g["dr"]), eng.pitch, "cuda"
+    B = 74 * 256 + 77
+    gen = torch.Generator(device=dev).manual_seed(5)
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    eng.sample_r_dev(B, dr, 9, 0, r)
+    m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    m[:, :N] = torch.randint(0, 2, (B, N), generator=gen, device=dev, dtype=torch.uint8)
+
+    def run(path, r_, m_, dirty_e):
+        eng.set_path(path)
+        val = torch.full((B, P), 7, dtype=torch.int16, device=dev)
+        quo = torch.full((B, P), 7, dtype=torch.int16, device=dev)
+        torch.cuda.synchronize()                          # the engine has its own stream: order it after torch's fills ...
+        eng.encrypt_dev(B, r_, m_, value=val, quotientE=quo)
+        eng.sync()                                        # ... and torch's reads after the engine's kernels
+        e = val.clone()
+        if dirty_e:
+            e[:, N:] = 0x7FF
+        outs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(2)] + \
+               [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+        q1, r1, pv, q2 = outs
+        torch.cuda.synchronize()
+        eng.decrypt_dev(B, e, value=pv, quotient1=q1, remainder1=r1, quotient2=q2)
+        eng.sync()
+        return [val, quo] + outs
+
+    ref = None
+    for path in (nb.PATH_TENSOR, nb.PATH_IMMA, nb.PATH_CUDA_CORE):
+        clean = run(path, r, m, False)
+        for x in clean:
+            assert not x[:, N:].any(), (cfg, path)
+        if ref is None:
+            ref = clean
+        for x, y in zip(ref, clean):                      # the three schedules agree, pads included
+            assert torch.equal(x, y), (cfg, path)
+    rd, md = r.clone(), m.clone()
+    rd[:, N:] = 2
+    md[:, N:] = 0xA5
+    torch.cuda.synchronize()
+    dirty = run(nb.PATH_TENSOR, rd, md, True)
+    for x, y in zip(ref, dirty):
+        assert torch.equal(x, y), cfg
+    eng.set_path(0)
