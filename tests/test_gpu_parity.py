@@ -462,6 +462,7 @@ def test_sum_over_exchange_window_single_rank(cfg, nb, golden):
     g = golden(cfg)
     N, q = int(g["N"]), int(g["q"])
     eng = nb.Engine(N, 3, q, 0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)      # torch fills and engine kernels on one stream
     sharding.connect_exchange(eng)
     rng = np.random.default_rng(8)
     P = eng.pitch
