@@ -725,6 +725,20 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // timing experiment only: results are not written
     if (getenv("NTRU_DEBUG_NOB")) a.debug_flags |= 1;
   }
+  // The accumulator chunks cover nchunks * NCo >= N output columns; when N is a multiple of the chunk width (N = 512,
+  // 640, 768, 1024) that stops short of the row pitch, and the pad columns the kernel never sees are zeroed here so that
+  // every output row keeps the contract of include/ntru_b200.h.
+  {
+    const size_t cov = (size_t)a.nchunks * a.NCo;
+    if (cov < P) {
+      void *o16[3] = {a.o16_cyc, a.o16_cyc2, a.o16_hi};
+      void *o8[3] = {MODE == DEC2 ? a.o8_cyc : nullptr, a.o8_cyc2, a.o8_hi};
+      for (int i = 0; i < 3; ++i) {
+        if (o16[i]) NTRU_CUDA(ctx, cudaMemset2DAsync((uint16_t *)o16[i] + cov, P * 2, 0, (P - cov) * 2, a.B, ctx->stream));
+        if (o8[i]) NTRU_CUDA(ctx, cudaMemset2DAsync((uint8_t *)o8[i] + cov, P, 0, P - cov, a.B, ctx->stream));
+      }
+    }
+  }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
     if (pair) {

@@ -279,6 +279,55 @@ def test_parameter_sets_outside_baseline(N, q, nb):
     eng.close()
 
 
+@pytest.mark.parametrize("N,q", [(512, 2048), (513, 2048), (640, 4096), (641, 2048), (768, 8192), (897, 2048), (1024, 8192)])
+def test_many_tiles_per_cluster_outside_baseline(N, q, nb):
+    """Several 256-row tiles per CTA pair (ring phases, resident-slot reuse, the last partial tile) at the N where the
+    shared-memory budget of the tcgen05 kernel changes (A slots 5 ... 8, B ring 8 ... 5, streaming DEC1): device-resident
+    batch, tcgen05 schedule against the fp32 and IMMA schedules bit for bit (pad columns included), plus rows against the
+    oracle."""
+    torch = pytest.importorskip("torch")
+    p, dev = 3, "cuda"
+    rng = np.random.default_rng(77 * N + q)
+    h = rng.integers(0, q, size=N)
+    f = rng.integers(-1, 2, size=N)
+    fp = rng.integers(0, p, size=N)
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_public_key(h.astype(np.uint16))
+    eng.set_private_key(f.astype(np.int8), fp.astype(np.uint8))
+    P, B = eng.pitch, 74 * 256 * 3 + 131
+    gen = torch.Generator(device=dev).manual_seed(N)
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    r[:, :N] = torch.randint(0, 3, (B, N), generator=gen, device=dev, dtype=torch.uint8)
+    m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
+    m[:, :N] = torch.randint(0, 2, (B, N), generator=gen, device=dev, dtype=torch.uint8)
+    outs = {}
+    paths = (nb.PATH_TENSOR, nb.PATH_CUDA_CORE) + ((nb.PATH_IMMA,) if N <= 832 else ())
+    for path in paths:
+        eng.set_path(path)
+        bufs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
+               [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+        val, quo, q1, r1, pv, q2 = bufs
+        eng.encrypt_dev(B, r, m, value=val, quotientE=quo)
+        eng.decrypt_dev(B, val, value=pv, quotient1=q1, remainder1=r1, quotient2=q2)
+        eng.sync()
+        outs[path] = bufs
+    for path in paths[1:]:
+        for x, y in zip(outs[nb.PATH_TENSOR], outs[path]):   # pad columns included: every schedule writes them as zero
+            assert torch.equal(x, y), (N, q, path)
+    idx = [0, 255, 256, 74 * 256, B - 132, B - 1]
+    want_e = o.encrypt_batch(h, r[idx, :N].cpu().numpy(), m[idx, :N].cpu().numpy(), q)
+    want_d = o.decrypt_batch(f, fp, want_e["value"], q, p)
+    val, quo, q1, r1, pv, q2 = outs[nb.PATH_TENSOR]
+    assert np.array_equal(val[idx].cpu().numpy().view(np.uint16)[:, :N], want_e["value"])
+    assert np.array_equal(quo[idx].cpu().numpy().view(np.uint16)[:, : N + 1], want_e["quotientE"])
+    assert np.array_equal(r1[idx].cpu().numpy().view(np.uint16)[:, : N + 1], want_d["remainder1"])
+    assert np.array_equal(q1[idx].cpu().numpy().view(np.uint16)[:, : N + 1], want_d["quotient1"])
+    assert np.array_equal(pv[idx].cpu().numpy()[:, :N], want_d["value"])
+    assert np.array_equal(q2[idx].cpu().numpy()[:, : N + 1], want_d["quotient2"])
+    eng.close()
+
+
 def test_string_batches_and_multi_block_messages(nb, golden):
     """encryptStr / decryptStr for many strings per call, against the single-string reference path
     (index.js:80-86) and the oracle's codec; strings longer than floor(N / 8) characters split into blocks."""
