@@ -315,6 +315,14 @@ def test_many_tiles_per_cluster_outside_baseline(N, q, nb):
     for path in paths[1:]:
         for x, y in zip(outs[nb.PATH_TENSOR], outs[path]):   # pad columns included: every schedule writes them as zero
             assert torch.equal(x, y), (N, q, path)
+    # value-only mode (no hi chunks: other loop counts and ring phases), same ciphertexts and plaintexts
+    eng.set_path(nb.PATH_TENSOR)
+    val2 = torch.full((B, P), 7, dtype=torch.int16, device=dev)
+    pv2 = torch.full((B, P), 7, dtype=torch.uint8, device=dev)
+    eng.encrypt_dev(B, r, m, value=val2)
+    eng.decrypt_dev(B, val2, value=pv2)
+    eng.sync()
+    assert torch.equal(val2, outs[nb.PATH_TENSOR][0]) and torch.equal(pv2, outs[nb.PATH_TENSOR][4]), (N, q)
     idx = [0, 255, 256, 74 * 256, B - 132, B - 1]
     want_e = o.encrypt_batch(h, r[idx, :N].cpu().numpy(), m[idx, :N].cpu().numpy(), q)
     want_d = o.decrypt_batch(f, fp, want_e["value"], q, p)
@@ -711,3 +719,37 @@ def test_pad_columns_of_device_rows_do_not_count(cfg, nb, engines, golden):
     for x, y in zip(ref, dirty):
         assert torch.equal(x, y), cfg
     eng.set_path(0)
+
+
+@pytest.mark.parametrize("N,q", [(167, 128), (640, 4096), (677, 2048), (832, 4096)])
+def test_distinct_keys_device_rows_all_schedules_agree(N, q, nb):
+    """Distinct keys per row through the device-pointer entry points: the IMMA schedule against the fp32 schedule, bit
+    for bit over whole pitched rows (pad columns written as zero), with a batch that is not a multiple of any tile."""
+    torch = pytest.importorskip("torch")
+    p, dev = 3, "cuda"
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    P, B = eng.pitch, 4099
+    gen = torch.Generator(device=dev).manual_seed(N + q)
+    def rows(lo, hi, dtype):
+        t = torch.zeros((B, P), dtype=dtype, device=dev)
+        t[:, :N] = torch.randint(lo, hi, (B, N), generator=gen, device=dev).to(dtype)
+        return t
+    h, f, fp = rows(0, q, torch.int16), rows(-1, 2, torch.int8), rows(0, 3, torch.uint8)
+    r, m = rows(0, 3, torch.uint8), rows(0, 2, torch.uint8)
+    outs = {}
+    for path in (nb.PATH_IMMA, nb.PATH_CUDA_CORE):
+        eng.set_path(path)
+        bufs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
+               [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+        val, quo, q1, r1, pv, q2 = bufs
+        eng.encrypt_dev(B, r, m, value=val, quotientE=quo, h_rows=h)
+        eng.decrypt_dev(B, val, value=pv, quotient1=q1, remainder1=r1, quotient2=q2, f_rows=f, fp_rows=fp)
+        eng.sync()
+        outs[path] = bufs
+    for x, y in zip(outs[nb.PATH_IMMA], outs[nb.PATH_CUDA_CORE]):
+        assert torch.equal(x, y), (N, q)
+        assert not x[:, N:].any(), (N, q)
+    want_e = o.encrypt_batch(h[:3, :N].cpu().numpy().astype(np.int64) & 0xFFFF, r[:3, :N].cpu().numpy(), m[:3, :N].cpu().numpy(), q)
+    assert np.array_equal(outs[nb.PATH_IMMA][0][:3].cpu().numpy().view(np.uint16)[:, :N], want_e["value"])
+    eng.close()
