@@ -591,17 +591,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               const int col = c * a.NCo + (sub * upw + j) * 16;
               mg[j] = (j < upw && grow < a.B && col < a.N) ? __ldg(reinterpret_cast<const uint4 *>(a.m + grow * (size_t)a.P + col))
                                                           : make_uint4(0, 0, 0, 0);
-              if (col + 16 > a.N) {   // the unit that straddles N: pad bytes of the caller's row do not count (the TMA tile
-                const int keep = a.N - col;                          // of the PU = 2 path reads them as zero as well)
-                uint32_t w[4] = {mg[j].x, mg[j].y, mg[j].z, mg[j].w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const int kb = keep - 4 * t;
-                  w[t] = kb >= 4 ? w[t] : (kb <= 0 ? 0u : (w[t] & ((1u << (8 * kb)) - 1u)));
-                }
-                mg[j] = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            }
+            }   // (four independent loads, nothing waits for them here: the unit that straddles N is masked at its use)
           }
           mbar_wait(my_tfull, (cc >> 1) & 1);
           tc_fence_after();
@@ -637,7 +627,19 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             uint32_t bres[kPassUnits * 4];                          // DEC1: lifted polynomial b (bytes)
             uint4 mm[kPassUnits];                                   // ENC: message bytes of the pass
             if (kMsgGlobal) {
-              if (!hi) mm[0] = ps == 0 ? mg[0] : (ps == 1 ? mg[1] : (ps == 2 ? mg[2] : mg[3]));   // PU == 1: pass ps = unit ps
+              if (!hi) {
+                mm[0] = ps == 0 ? mg[0] : (ps == 1 ? mg[1] : (ps == 2 ? mg[2] : mg[3]));   // PU == 1: pass ps = unit ps
+                const int keep = a.N - (c * a.NCo + u0 * 16);   // < 16 for the unit that straddles N: the pad bytes of the
+                if (keep < 16) {                                // caller's row do not count (a TMA tile reads them as zero)
+                  uint32_t w[4] = {mm[0].x, mm[0].y, mm[0].z, mm[0].w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const int kb = keep - 4 * t;
+                    w[t] = kb >= 4 ? w[t] : (kb <= 0 ? 0u : (w[t] & ((1u << (8 * kb)) - 1u)));
+                  }
+                  mm[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
             } else if (MODE == ENC && !hi) {
 #pragma unroll
               for (int j = 0; j < kPassUnits; ++j) mm[j] = lds128(m_slot(ms) + m_row + ((((uint32_t)(u0 + j)) ^ m_x) << 4));
