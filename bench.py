@@ -182,7 +182,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- synthetic inputs, resident in HBM: r from the device sampler, m = random bits ----
     r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
-    eng.sample_r_dev(B, dr, 2026, rank * B, r)
+    eng.sample_r_dev(B, dr, rank * B, r, seed=2026)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
     m[:, :N] = torch.randint(0, 2, (B, N), generator=gen, device=dev, dtype=torch.uint8)

@@ -57,7 +57,8 @@ enum {
                                schedule, 2 force the tcgen05 schedule (same-key only), 3 force the register-fragment schedule */
   NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
   NTRU_OPT_TIMING = 3,      /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
-  NTRU_OPT_TENSOR_VARIANT = 4 /* tcgen05 schedule: 0 = CTA-pair kernel (cta_group::2, default), 1 = single-CTA kernel */
+  NTRU_OPT_TENSOR_VARIANT = 4, /* tcgen05 schedule: 0 = CTA-pair kernel (cta_group::2, default), 1 = single-CTA kernel */
+  NTRU_OPT_DR = 5           /* dr of new NTRU({..., dr}) (index.js:15): weights of the r the device draws when r == NULL */
 };
 
 /* kernel kinds reported by ntru_timing_read */
@@ -76,7 +77,8 @@ enum {
   NTRU_K_COUNT = 11
 };
 
-/* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 32768], 8 <= N <= 1024. */
+/* new NTRU({N,p,q}) -- index.js:8-28.  p must be 3, q a power of two in [4, 8192], 8 <= N <= 1024
+ * (q >= 16384 is refused with NTRU_E_PARAM: no schedule of this library is exact there). */
 int ntru_create(ntru_ctx **ctx, int N, int p, int q, int device);
 void ntru_destroy(ntru_ctx *ctx);
 const char *ntru_last_error(const ntru_ctx *ctx);
@@ -98,16 +100,29 @@ int ntru_set_public_key(ntru_ctx *ctx, const uint16_t *h);
 /* this.f, this.fp (index.js:30-36): f in {-1,0,1}, fp expanded to N entries in [0,p) */
 int ntru_set_private_key(ntru_ctx *ctx, const int8_t *f, const uint8_t *fp);
 
-/* encryptBits, B messages under the context's public key -- index.js:87-110 with r injected.
- * value = remainderE[0..N); quotientE/remainderE are the VerifyEncrypt witness (N+1 entries per row). */
+/* encryptBits, B messages under the context's public key -- index.js:87-110.
+ * value = remainderE[0..N); quotientE/remainderE are the VerifyEncrypt witness (N+1 entries per row).
+ * r (B x N, entries 0/1/2 with 2 = -1): the blinding polynomials, injected by the caller -- or NULL: the DEVICE draws
+ *   them like index.js:89 (generateCustomArray(N, dr, dr), -1 -> p-1) from its keyed ChaCha20 generator; needs
+ *   NTRU_OPT_DR.  r_out (B x N or NULL) receives the r that was used (inputs.r, index.js:97) in either case. */
 int ntru_encrypt_batch(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m,
-                       uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+                       uint16_t *value, uint16_t *quotientE, uint16_t *remainderE, uint8_t *r_out);
 /* same with messages whose coefficients do not fit a byte (m already reduced into [0,q)) -- index.js:91 */
 int ntru_encrypt_batch_wide(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint16_t *m,
-                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE, uint8_t *r_out);
 /* encryptBits with a distinct public key per row: h is B x N */
 int ntru_encrypt_batch_keys(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const uint8_t *m,
-                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE);
+                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE, uint8_t *r_out);
+
+/* The device generator behind r == NULL and ntru_sample_r_dev: ChaCha20 in counter mode (256-bit key, nonce = a
+ * 64-bit global row number that the context never reuses under one key, block counter = position in the row's
+ * keystream); the draws replace crypto.getRandomValues in the reference's Fisher-Yates shuffle (index.js:476-485)
+ * one for one.  ntru_create keys it with 256 bits from the operating system (getrandom(2)).  ntru_set_rng_key
+ * replaces the key and sets the next row number: for tests, reproducible benchmarks, or an audit replay of the r of
+ * given rows by the key holder.  ntru_rng_next_row: the row number the next device-drawn r will use. */
+#define NTRU_RNG_KEY_BYTES 32
+int ntru_set_rng_key(ntru_ctx *ctx, const uint8_t key[NTRU_RNG_KEY_BYTES], uint64_t first_row);
+uint64_t ntru_rng_next_row(const ntru_ctx *ctx);
 
 /* decryptBits, B ciphertexts under the context's private key -- index.js:111-140.
  * value = remainder2[0..N); quotient1/remainder1 (mod q) and quotient2/remainder2 (mod p) are the
@@ -171,9 +186,10 @@ int ntru_decrypt_dev(ntru_ctx *ctx, size_t B, const int8_t *f_rows, const uint8_
 int ntru_sum_partial_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial);
 /* out[k] = partial[k] mod q for k < N (and 0 up to pitch) */
 int ntru_sum_finalize_dev(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
-/* generateCustomArray(N, dr, dr).map(-1 -> p-1) for rows [row0, row0+B) -- index.js:89, 461-488:
- * the same Fisher-Yates shuffle driven by a counter-based generator (seed, row, i) instead of WebCrypto */
-int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
+/* generateCustomArray(N, dr, dr).map(-1 -> p-1) into device rows, drawn by the context's ChaCha20 generator for the
+ * global row numbers [row0, row0+B) -- index.js:89, 461-488.  The caller owns the row numbering here: never sample
+ * two different rows with the same number under one key. */
+int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r);
 
 /* ---- cross-GPU homomorphic sum (one context = one rank = one GPU of the same node) ----
  * The only exchange step of the hot path: every rank reduces its rows to N column sums mod q and all ranks need the
@@ -182,13 +198,21 @@ int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t r
  * straight into every peer's exchange window and raises a flag there; a one-CTA kernel waits for all flags and adds
  * the slots.  No collective library on the data path. */
 #define NTRU_XCHG_HANDLE_BYTES 64
-/* allocates this rank's exchange window and returns its CUDA IPC handle (to be all-gathered by the caller) */
+/* allocates this rank's exchange window and returns its CUDA IPC handle (to be all-gathered by the caller).
+ * Calling it again replaces the window: see ntru_xchg_destroy for the barrier this requires. */
 int ntru_xchg_create(ntru_ctx *ctx, int world, int rank, unsigned char handle_out[NTRU_XCHG_HANDLE_BYTES]);
 /* handles: world x NTRU_XCHG_HANDLE_BYTES, rank-major, as gathered from ntru_xchg_create on every rank */
 int ntru_xchg_connect(ntru_ctx *ctx, const unsigned char *handles);
 /* out[k] = (sum over every rank's rows of e[b][k]) mod q for k < N (0 up to pitch), on every rank; asynchronous on
- * the context's stream.  Every rank must call it the same number of times.  Without ntru_xchg_create: world = 1. */
+ * the context's stream.  Every rank must call it the same number of times (B may differ per rank and may be 0).
+ * Without ntru_xchg_create: world = 1.  If a peer does not arrive within ~4 s the kernel gives up, fills out[] with
+ * 0xFFFF (no valid residue) and the next ntru_sync / ntru_xchg_destroy on this context returns NTRU_E_CUDA. */
 int ntru_sum_allreduce_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
+/* Unmaps the peers' windows and frees this rank's.  COLLECTIVE like create / connect: every rank must have finished
+ * (ntru_sync) its last ntru_sum_allreduce_dev and the caller must pass a barrier over all ranks BEFORE any rank calls
+ * this or ntru_xchg_create again -- peers store into this window until their last call has completed.
+ * (ntru_destroy implies it, under the same rule.) */
+int ntru_xchg_destroy(ntru_ctx *ctx);
 
 void *ntru_stream(ntru_ctx *ctx);              /* cudaStream_t */
 int ntru_set_stream(ntru_ctx *ctx, void *stream);

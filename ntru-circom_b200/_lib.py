@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libntru_b200.so")
 NTRU_OK = 0
 NTRU_E_PARAM, NTRU_E_LENGTH, NTRU_E_NOKEY, NTRU_E_CUDA = -1, -2, -3, -4
 NTRU_E_NCCL, NTRU_E_NOMEM, NTRU_E_UNSUPPORTED = -5, -6, -7
-NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING, NTRU_OPT_TENSOR_VARIANT = 1, 2, 3, 4
+NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING, NTRU_OPT_TENSOR_VARIANT, NTRU_OPT_DR = 1, 2, 3, 4, 5
 KERNEL_KINDS = ["enc_tensor", "dec1_tensor", "dec2_tensor", "enc_core", "dec_core", "sum", "other", "enc_imma", "dec_imma",
                 "muldiv", "pack"]
 PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR, PATH_IMMA = 0, 1, 2, 3
@@ -35,9 +35,11 @@ SYMBOLS = {
     "ntru_timing_reset": (c_int, [_P]),
     "ntru_set_public_key": (c_int, [_P, _P]),
     "ntru_set_private_key": (c_int, [_P, _P, _P]),
-    "ntru_encrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P]),
-    "ntru_encrypt_batch_wide": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P]),
-    "ntru_encrypt_batch_keys": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
+    "ntru_encrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
+    "ntru_encrypt_batch_wide": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
+    "ntru_encrypt_batch_keys": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P]),
+    "ntru_set_rng_key": (c_int, [_P, _P, c_uint64]),
+    "ntru_rng_next_row": (c_uint64, [_P]),
     "ntru_decrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "ntru_decrypt_batch_keys": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ntru_sum": (c_int, [_P, c_size_t, _P, _P]),
@@ -51,10 +53,11 @@ SYMBOLS = {
     "ntru_decrypt_dev": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ntru_sum_partial_dev": (c_int, [_P, c_size_t, _P, _P]),
     "ntru_sum_finalize_dev": (c_int, [_P, _P, _P]),
-    "ntru_sample_r_dev": (c_int, [_P, c_size_t, c_int, c_uint64, c_uint64, _P]),
+    "ntru_sample_r_dev": (c_int, [_P, c_size_t, c_int, c_uint64, _P]),
     "ntru_xchg_create": (c_int, [_P, c_int, c_int, _P]),
     "ntru_xchg_connect": (c_int, [_P, _P]),
     "ntru_sum_allreduce_dev": (c_int, [_P, c_size_t, _P, _P]),
+    "ntru_xchg_destroy": (c_int, [_P]),
     "ntru_stream": (c_void_p, [_P]),
     "ntru_set_stream": (c_int, [_P, _P]),
     "ntru_sync": (c_int, [_P]),

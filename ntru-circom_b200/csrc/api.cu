@@ -7,6 +7,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sys/random.h>
+
 #include <new>
 #include <string>
 
@@ -235,7 +237,9 @@ int ntru_create(ntru_ctx **out, int N, int p, int q, int device) {
   *out = nullptr;
   if (p != 3) return NTRU_E_PARAM;
   if (N < 8 || N > kMaxN) return NTRU_E_PARAM;
-  if (q < 4 || q > 32768 || (q & (q - 1)) != 0) return NTRU_E_PARAM;
+  // q <= 8192: the tcgen05 schedule keeps 5 bits in its high limb and folds a lifted coefficient <= q into one byte
+  // (umma_pair.cuh), and BASELINE's largest modulus is 8192; larger moduli are refused instead of being routed silently
+  if (q < 4 || q > 8192 || (q & (q - 1)) != 0) return NTRU_E_PARAM;
   // fp32 exactness bound of the CUDA-core schedule: N * 2 * (q-1) < 2^24
   if ((long long)N * 2 * (q - 1) >= (1ll << 24)) return NTRU_E_PARAM;
   int ndev = 0;
@@ -267,6 +271,24 @@ int ntru_create(ntru_ctx **out, int N, int p, int q, int device) {
     ntru_destroy(ctx);
     return NTRU_E_CUDA;
   }
+  // key of the device CSPRNG that draws r (index.js:89 uses crypto.getRandomValues): 256 bits of OS entropy
+  {
+    size_t got = 0;
+    unsigned char *kb = reinterpret_cast<unsigned char *>(ctx->rng_key);
+    while (got < sizeof ctx->rng_key) {
+      ssize_t n = getrandom(kb + got, sizeof ctx->rng_key - got, 0);
+      if (n <= 0) break;
+      got += (size_t)n;
+    }
+    if (got < sizeof ctx->rng_key) {
+      FILE *fh = fopen("/dev/urandom", "rb");
+      if (fh) {
+        got += fread(kb + got, 1, sizeof ctx->rng_key - got, fh);
+        fclose(fh);
+      }
+    }
+    ctx->rng_keyed = got == sizeof ctx->rng_key;   // without entropy r == NULL is refused (no silent weak key)
+  }
   umma_init(ctx);
   *out = ctx;
   return NTRU_OK;
@@ -286,7 +308,7 @@ void ntru_destroy(ntru_ctx *ctx) {
     for (auto &b : ctx->slot_packed[s]) b.release();
   }
   xchg_release(ctx);
-  ctx->d_h.release(); ctx->d_f.release(); ctx->d_fp.release(); ctx->d_b.release(); ctx->d_partial.release();
+  ctx->d_h.release(); ctx->d_f.release(); ctx->d_fp.release(); ctx->d_b.release(); ctx->d_partial.release(); ctx->d_sum_scratch.release();
   ctx->km_h.mat.release(); ctx->km_f.mat.release(); ctx->km_fp.mat.release();
   for (auto &t : ctx->timed) {
     cudaEventDestroy(t.a);
@@ -312,6 +334,11 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
       return NTRU_OK;
     case NTRU_OPT_TIMING:
       ctx->timing = value != 0;
+      return NTRU_OK;
+    case NTRU_OPT_DR:
+      // index.js:462-464
+      if (value < 0 || 2 * value > ctx->N) return fail(ctx, NTRU_E_PARAM, "The total of 1s and -1s cannot exceed the array length.");
+      ctx->opt_dr = (int)value;
       return NTRU_OK;
     case NTRU_OPT_TENSOR_VARIANT:
       if (value < 0 || value > 1) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_TENSOR_VARIANT must be 0 or 1");
@@ -405,39 +432,56 @@ int ntru_set_private_key(ntru_ctx *ctx, const int8_t *f, const uint8_t *fp) {
 // ---- host-buffer entry points ---------------------------------------------------------------
 
 static int encrypt_host(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const void *m, int m_wide,
-                        uint16_t *value, uint16_t *quo, uint16_t *rem) {
+                        uint16_t *value, uint16_t *quo, uint16_t *rem, uint8_t *r_out) {
   int rc = check(ctx);
   if (rc) return rc;
-  if (!r || !m) return fail(ctx, NTRU_E_PARAM, "r and m are required");
+  if (!m) return fail(ctx, NTRU_E_PARAM, "m is required");
+  if (!r) {   // the device draws r (index.js:89): needs dr and an entropy-keyed generator
+    if (ctx->opt_dr < 0) return fail(ctx, NTRU_E_PARAM, "r is NULL and NTRU_OPT_DR (the dr of the constructor options) is not set");
+    if (!ctx->rng_keyed) return fail(ctx, NTRU_E_UNSUPPORTED, "r is NULL and the device generator has no key (no OS entropy; call ntru_set_rng_key)");
+  }
   if (B == 0) return NTRU_OK;
   const size_t N = (size_t)ctx->N;
   HostArr arr[kMaxArr];
   set_in(arr[0], h, 2, N);
-  set_in(arr[1], r, 1, N);
+  if (r) {
+    set_in(arr[1], r, 1, N);
+    if (r_out && r_out != r) memcpy(r_out, r, B * N);   // injected r is echoed (inputs.r, index.js:97)
+  } else {
+    set_out(arr[1], r_out, 1, N);
+    arr[1].used = true;                                  // device rows are needed even when r is not returned
+  }
   set_in(arr[2], m, m_wide ? 2 : 1, N);
   set_out(arr[3], value, 2, N);
   set_out(arr[4], quo, 2, N + 1);
   set_out(arr[5], rem, 2, N + 1);
+  uint64_t next_row = ctx->rng_row;
+  if (!r) ctx->rng_row += B;                             // a row number (nonce) is never used twice under one key
   return run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
+    if (!r) {
+      int rs = launch_sample_r(ctx, rows, ctx->opt_dr, next_row, (uint8_t *)dev[1]);
+      if (rs) return rs;
+      next_row += rows;
+    }
     return encrypt_dispatch(ctx, rows, (const uint16_t *)dev[0], (const uint8_t *)dev[1], dev[2], m_wide,
                             (uint16_t *)dev[3], (uint16_t *)dev[4], (uint16_t *)dev[5]);
   });
 }
 
 int ntru_encrypt_batch(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint8_t *m, uint16_t *value,
-                       uint16_t *quotientE, uint16_t *remainderE) {
-  return encrypt_host(ctx, B, nullptr, r, m, 0, value, quotientE, remainderE);
+                       uint16_t *quotientE, uint16_t *remainderE, uint8_t *r_out) {
+  return encrypt_host(ctx, B, nullptr, r, m, 0, value, quotientE, remainderE, r_out);
 }
 
 int ntru_encrypt_batch_wide(ntru_ctx *ctx, size_t B, const uint8_t *r, const uint16_t *m, uint16_t *value,
-                            uint16_t *quotientE, uint16_t *remainderE) {
-  return encrypt_host(ctx, B, nullptr, r, m, 1, value, quotientE, remainderE);
+                            uint16_t *quotientE, uint16_t *remainderE, uint8_t *r_out) {
+  return encrypt_host(ctx, B, nullptr, r, m, 1, value, quotientE, remainderE, r_out);
 }
 
 int ntru_encrypt_batch_keys(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const uint8_t *m,
-                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE) {
+                            uint16_t *value, uint16_t *quotientE, uint16_t *remainderE, uint8_t *r_out) {
   if (!h) return fail(ctx, NTRU_E_PARAM, "h is NULL");
-  return encrypt_host(ctx, B, h, r, m, 0, value, quotientE, remainderE);
+  return encrypt_host(ctx, B, h, r, m, 0, value, quotientE, remainderE, r_out);
 }
 
 static int decrypt_host(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, const uint16_t *e,
@@ -661,8 +705,6 @@ static int xchg_alloc(ntru_ctx *ctx, int world, int rank) {
   const size_t bytes = xchg_window_bytes(ctx, world);
   NTRU_CUDA(ctx, ctx->d_window.reserve(bytes));
   NTRU_CUDA(ctx, cudaMemset(ctx->d_window.ptr, 0, bytes));
-  NTRU_CUDA(ctx, cudaMemsetAsync(ctx->d_partial.ptr, 0, (size_t)ctx->P * 4, ctx->stream));
-  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->xchg_world = world;
   ctx->xchg_rank = rank;
   ctx->peer_window[rank] = ctx->d_window.ptr;
@@ -715,14 +757,27 @@ int ntru_sum_allreduce_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t 
   return launch_sum_allreduce(ctx, B, e, out);
 }
 
-int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r) {
+int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r) {
   int rc = check(ctx);
   if (rc) return rc;
   if (!r) return fail(ctx, NTRU_E_PARAM, "r is NULL");
   // index.js:462-464
   if (dr < 0 || 2 * dr > ctx->N) return fail(ctx, NTRU_E_PARAM, "The total of 1s and -1s cannot exceed the array length.");
-  return launch_sample_r(ctx, B, dr, seed, row0, r);
+  if (!ctx->rng_keyed) return fail(ctx, NTRU_E_UNSUPPORTED, "the device generator has no key (no OS entropy; call ntru_set_rng_key)");
+  return launch_sample_r(ctx, B, dr, row0, r);
 }
+
+int ntru_set_rng_key(ntru_ctx *ctx, const uint8_t key[NTRU_RNG_KEY_BYTES], uint64_t first_row) {
+  if (!ctx || !key) return NTRU_E_PARAM;
+  for (int i = 0; i < 8; ++i)
+    ctx->rng_key[i] = (uint32_t)key[4 * i] | ((uint32_t)key[4 * i + 1] << 8) | ((uint32_t)key[4 * i + 2] << 16) |
+                      ((uint32_t)key[4 * i + 3] << 24);
+  ctx->rng_row = first_row;
+  ctx->rng_keyed = true;
+  return NTRU_OK;
+}
+
+uint64_t ntru_rng_next_row(const ntru_ctx *ctx) { return ctx ? ctx->rng_row : 0; }
 
 void *ntru_stream(ntru_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
@@ -737,11 +792,30 @@ int ntru_set_stream(ntru_ctx *ctx, void *stream) {
   return NTRU_OK;
 }
 
+// error word of this rank's exchange window: set by k_sum_push when a peer's flag never arrived
+static int xchg_check(ntru_ctx *ctx) {
+  if (!ctx->d_window.ptr) return NTRU_OK;
+  uint32_t err = 0;
+  const uint32_t *word = (const uint32_t *)ctx->d_window.ptr + (size_t)2 * ctx->xchg_world * ctx->P + ctx->xchg_world;
+  NTRU_CUDA(ctx, cudaMemcpy(&err, word, sizeof err, cudaMemcpyDeviceToHost));
+  if (err) return fail(ctx, NTRU_E_CUDA, "cross-GPU sum: a peer rank did not arrive within the timeout; the result is invalid");
+  return NTRU_OK;
+}
+
 int ntru_sync(ntru_ctx *ctx) {
   int rc = check(ctx);
   if (rc) return rc;
   NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return NTRU_OK;
+  return xchg_check(ctx);
+}
+
+int ntru_xchg_destroy(ntru_ctx *ctx) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  rc = xchg_check(ctx);
+  xchg_release(ctx);
+  return rc;
 }
 
 void *ntru_host_alloc(size_t bytes) {

@@ -16,8 +16,7 @@
 //
 // Arithmetic: fp32 FMA on integer-valued operands.  Every partial sum is an integer of
 // magnitude <= N*2*(q-1) < 2^24 (N <= 1024, q <= 8192), so fp32 is exact; it runs on both
-// FMA pipes where IMAD has one.  (q = 16384/32768 would overflow 2^24: ntru_create rejects
-// them for this schedule.)
+// FMA pipes where IMAD has one.  (ntru_create refuses q > 8192 for every schedule.)
 //
 // Thread mapping: thread c owns outputs k = 8c .. 8c+7.  The i-loop runs over blocks of 8
 // multiplier coefficients; the window of 15 multiplicand values slides by 8 per block (two
@@ -266,12 +265,26 @@ __global__ void __launch_bounds__(160) k_decrypt_generic(const DecArgs a) {
 // ---- homomorphic ciphertext sum: column sums of B x N uint16 rows -------------------------------
 // Pure HBM streaming (2N bytes per ciphertext).  Thread (vx, ry) owns the 8 columns of 16-byte
 // vector vx and rows ry, ry+RY, ...; uint32 accumulation wraps mod 2^32, which is exact mod q | 2^16.
+//
+// The CTAs' column sums are combined by a two-level tree in global scratch, not by atomics: the first version
+// issued P atomicAdds per CTA onto P words = 22 cache lines, ~19 000 same-line reductions per line when 592 CTAs
+// finish together, ~60 us of serialised L2 work per call (10 M rows: 1.95 ms, 1.25 M rows: 0.296 ms => 7.4 TB/s
+// streaming + 0.06 ms fixed).  Now every CTA stores its P sums as one row of `scratch`; the last CTA of each group
+// of kSumGroup CTAs (one ticket per group) adds the group's rows into a group row, and the last group leader adds
+// the group rows: two rounds of <= 16 / <= 37 independent 16-byte loads per thread.
 constexpr int kSumRows = 4;      // rows per CTA iteration (fewer when a row has > 128 vectors)
 constexpr int kSumUnroll = 4;    // independent 16-byte loads in flight per thread
+constexpr int kSumGroup = 16;    // CTAs per first-level group of the tree
 
-__global__ void __launch_bounds__(512) k_sum_partial(const uint16_t *__restrict__ e, size_t B, int P,
-                                                      uint32_t *__restrict__ partial) {
-  extern __shared__ __align__(16) uint32_t red[];
+struct SumScratch {
+  uint32_t *rows;      // [gridDim.x][P]  per-CTA column sums
+  uint32_t *grows;     // [ngroups][P]    per-group column sums
+  uint32_t *tickets;   // [ngroups + 1]   arrival counters (groups, then the group leaders); zero between calls
+};
+
+// This CTA's column sums of rows blockIdx.x * RY + ry, stepping by gridDim.x * RY; on return the threads with
+// ry == 0 hold the eight sums of columns 8 vx .. 8 vx + 7 in s[].
+__device__ __forceinline__ void cta_column_sums(const uint16_t *__restrict__ e, size_t B, int P, uint32_t *red, uint32_t (&s)[8]) {
   const int VX = P / 8;
   const int vx = threadIdx.x, ry = threadIdx.y;
   uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
@@ -310,22 +323,108 @@ __global__ void __launch_bounds__(512) k_sum_partial(const uint16_t *__restrict_
   if (ry == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      uint32_t s = 0;
-      for (int y = 0; y < RY; ++y) s += red[((size_t)y * VX + vx) * 8 + j];
-      atomicAdd(partial + vx * 8 + j, s);
+      uint32_t t = 0;
+      for (int y = 0; y < RY; ++y) t += red[((size_t)y * VX + vx) * 8 + j];
+      s[j] = t;
     }
   }
 }
 
+// Tree over the CTAs.  Returns true in exactly one CTA per launch (the last group leader to arrive); there, thread
+// tid < P / 4 holds the grand totals of columns 4 tid .. 4 tid + 3 in tot.  The tickets are left at zero.
+__device__ __forceinline__ bool grid_column_totals(const SumScratch sc, int P, const uint32_t (&s)[8], bool *flag, uint4 &tot) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nvec = P / 4;                                  // 16-byte vectors of uint32 per row (blockDim.x * 2 <= threads)
+  const int ngroups = (gridDim.x + kSumGroup - 1) / kSumGroup;
+  const int grp = blockIdx.x / kSumGroup;
+  const int gsize = min(kSumGroup, (int)gridDim.x - grp * kSumGroup);
+  if (threadIdx.y == 0) {
+    uint4 *dst = reinterpret_cast<uint4 *>(sc.rows + (size_t)blockIdx.x * P) + 2 * threadIdx.x;
+    dst[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    dst[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();                                       // release: this CTA's row before its ticket
+    *flag = atomicAdd(sc.tickets + grp, 1u) == (uint32_t)gsize - 1;
+    __threadfence();                                       // acquire: the last arrival sees every row of the group
+  }
+  __syncthreads();
+  if (!*flag) return false;
+  __syncthreads();                                         // everyone has read *flag before thread 0 rewrites it below
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  if (tid < nvec) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(sc.rows + (size_t)grp * kSumGroup * P) + tid;
+#pragma unroll
+    for (int i = 0; i < kSumGroup; ++i) {
+      if (i < gsize) {
+        const uint4 v = __ldcg(src + (size_t)i * nvec);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    reinterpret_cast<uint4 *>(sc.grows + (size_t)grp * P)[tid] = acc;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sc.tickets[grp] = 0;                                   // ready for the next call
+    __threadfence();
+    *flag = atomicAdd(sc.tickets + ngroups, 1u) == (uint32_t)ngroups - 1;
+    __threadfence();
+  }
+  __syncthreads();
+  if (!*flag) return false;
+  tot = make_uint4(0, 0, 0, 0);
+  if (tid < nvec) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(sc.grows) + tid;
+    int g = 0;
+    for (; g + 4 <= ngroups; g += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (size_t)(g + u) * nvec);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { tot.x += v[u].x; tot.y += v[u].y; tot.z += v[u].z; tot.w += v[u].w; }
+    }
+    for (; g < ngroups; ++g) {
+      const uint4 v = __ldcg(src + (size_t)g * nvec);
+      tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+    }
+  }
+  if (tid == 0) sc.tickets[ngroups] = 0;
+  return true;
+}
+
+// partial[k] += column sums of this call's rows (one writer: the CTA that finishes the tree)
+__global__ void __launch_bounds__(512) k_sum_partial(const uint16_t *__restrict__ e, size_t B, int P, const SumScratch sc,
+                                                      uint32_t *__restrict__ partial) {
+  extern __shared__ __align__(16) uint32_t red[];
+  __shared__ bool flag;
+  uint32_t s[8];
+  cta_column_sums(e, B, P, red, s);
+  uint4 tot;
+  if (!grid_column_totals(sc, P, s, &flag, tot)) return;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < P / 4) {
+    uint4 *dst = reinterpret_cast<uint4 *>(partial) + tid;
+    uint4 v = *dst;
+    v.x += tot.x; v.y += tot.y; v.z += tot.z; v.w += tot.w;
+    *dst = v;
+  }
+}
+
 // ---- cross-GPU sum: column sums fused with the exchange over peer memory --------------------------------------
-// Window of one rank: slots[2][world][P] uint32 (parity of the call number, sender rank), flags[world], ticket, error.
-// k_sum_push   = k_sum_partial + the LAST CTA to finish (ticket) reduces nothing further: it masks the N totals,
+// Window of one rank: slots[2][world][P] uint32 (parity of the call number, sender rank), flags[world], error word.
+// k_sum_push   = the column sums above + the CTA that finishes the tree owns the exchange: it masks the N totals,
 //                stores them into slot[parity][rank] of EVERY rank's window (plain stores over NVLink for the peers),
-//                fences system-wide and raises flag[rank] = epoch in every window; it also re-zeroes partial[] and
-//                the ticket for the next call.
-//                Then the same CTA gathers: it waits until flag[r] == epoch for every r (acquire loads of its own
-//                window), adds the world slots per column, masks, writes out[].  A rank cannot run two calls ahead
-//                of a peer (it needs the peer's flag of call n to finish call n), so two slot parities are enough.
+//                fences system-wide and raises flag[rank] = epoch in every window.
+//                Then the same CTA gathers: it waits until flag[r] has REACHED epoch for every r (acquire loads of its
+//                own window; a peer may already be one call ahead and have written epoch + 1 -- its slot of this
+//                call's parity is still intact then), adds the world slots per column, masks, writes out[].  A rank
+//                cannot run two calls ahead of a peer (it needs the peer's flag of call n to finish call n), so two
+//                slot parities are enough.
+//                If a peer never arrives (~4 s), the error word of this rank's window is set, out[] is filled with
+//                0xFFFF (no valid residue) and the host reports NTRU_E_CUDA at the next ntru_sync / sum call.
 // One launch per call: HBM streaming, exchange and final sum.
 struct XchgPeers {
   uint32_t *window[ntru_ctx::kMaxRanks];   // only indexed with compile-time-unrolled, bounded loops (stays in the constant bank)
@@ -340,94 +439,55 @@ __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e, size_t B, int P, uint32_t *__restrict__ partial,
-                                                  const XchgPeers peers, uint32_t *__restrict__ ticket, int world, int rank,
-                                                  uint32_t epoch, uint32_t qmask, int N, uint16_t *__restrict__ out) {
+__global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e, size_t B, int P, const SumScratch sc,
+                                                  const XchgPeers peers, int world, int rank, uint32_t epoch, uint32_t qmask,
+                                                  int N, uint16_t *__restrict__ out) {
   extern __shared__ __align__(16) uint32_t red[];
-  __shared__ bool is_last;
-  const int VX = P / 8;
-  const int vx = threadIdx.x, ry = threadIdx.y;
-  uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
-  const int RY = blockDim.y;
-  const size_t step = (size_t)gridDim.x * RY;
-  size_t row = (size_t)blockIdx.x * RY + ry;
-  const uint4 *base = reinterpret_cast<const uint4 *>(e) + vx;
-  for (; row + (kSumUnroll - 1) * step < B; row += kSumUnroll * step) {
-    uint4 v[kSumUnroll];
-#pragma unroll
-    for (int u = 0; u < kSumUnroll; ++u) v[u] = __ldcs(base + (row + u * step) * (size_t)VX);
-#pragma unroll
-    for (int u = 0; u < kSumUnroll; ++u) {
-      lo[0] += v[u].x; hi[0] += v[u].x >> 16;
-      lo[1] += v[u].y; hi[1] += v[u].y >> 16;
-      lo[2] += v[u].z; hi[2] += v[u].z >> 16;
-      lo[3] += v[u].w; hi[3] += v[u].w >> 16;
-    }
-  }
-  for (; row < B; row += step) {
-    const uint4 v = __ldcs(base + row * (size_t)VX);
-    lo[0] += v.x; hi[0] += v.x >> 16;
-    lo[1] += v.y; hi[1] += v.y >> 16;
-    lo[2] += v.z; hi[2] += v.z >> 16;
-    lo[3] += v.w; hi[3] += v.w >> 16;
-  }
-  uint32_t *mine = red + ((size_t)ry * VX + vx) * 8;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    mine[2 * j] = lo[j] & 0xffffu;
-    mine[2 * j + 1] = hi[j];
-  }
-  __syncthreads();
-  if (ry == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t s = 0;
-      for (int y = 0; y < RY; ++y) s += red[((size_t)y * VX + vx) * 8 + j];
-      atomicAdd(partial + vx * 8 + j, s);
-    }
-  }
-  // ---- the last CTA to get here owns the exchange ----
-  __syncthreads();                                            // this CTA's atomics are issued
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-  if (tid == 0) {
-    __threadfence();                                          // release: they are visible before the ticket moves
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __threadfence();                                          // acquire: the last CTA sees every CTA's atomics
-  }
-  __syncthreads();
-  if (!is_last) return;
+  __shared__ bool flag;
+  __shared__ int timed_out;
+  uint32_t s[8];
+  cta_column_sums(e, B, P, red, s);
+  uint4 tot;
+  if (!grid_column_totals(sc, P, s, &flag, tot)) return;
+  // ---- this CTA owns the exchange ----
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) timed_out = 0;
   const size_t slot = ((size_t)(epoch & 1u) * world + rank) * P;
-  for (int k = tid; k < P; k += nthr) {
-    const uint32_t v = __ldcg(partial + k) & qmask;
-    partial[k] = 0;                                           // ready for the next call
+  if (tid < P / 4) {
+    const uint4 v = make_uint4(tot.x & qmask, tot.y & qmask, tot.z & qmask, tot.w & qmask);
 #pragma unroll
     for (int r = 0; r < ntru_ctx::kMaxRanks; ++r)
-      if (r < world) peers.window[r][slot + k] = v;           // peer stores travel over NVLink
+      if (r < world) reinterpret_cast<uint4 *>(peers.window[r] + slot)[tid] = v;   // peer stores travel over NVLink
   }
   __syncthreads();
-  if (tid == 0) *ticket = 0;
   // release at system scope, cumulative over the stores the barrier above ordered before it
 #pragma unroll
   for (int r = 0; r < ntru_ctx::kMaxRanks; ++r)
     if (r == tid && r < world) st_release_sys(peers.window[r] + (size_t)2 * world * P + rank, epoch);
   // ---- gather: wait for every rank's flag in this rank's window, add the slots ----
-  const uint32_t *window = ticket - ((size_t)2 * world * P + world);
+  uint32_t *window = peers.window[rank];
   const uint32_t *flags = window + (size_t)2 * world * P;
   if (tid < world) {
     const long long t0 = clock64();
-    while (ld_acquire_sys(flags + tid) != epoch) {
+    while ((int32_t)(ld_acquire_sys(flags + tid) - epoch) < 0) {
       if (clock64() - t0 > 8000000000ll) {                    // ~4 s: a peer never arrived; do not hang the GPU
-        atomicExch(ticket + 1, 1u);
+        atomicExch(window + (size_t)2 * world * P + world, 1u);
+        timed_out = 1;
         break;
       }
     }
   }
   __syncthreads();
+  const int nthr = blockDim.x * blockDim.y;
+  if (timed_out) {
+    for (int k = tid; k < P; k += nthr) out[k] = (uint16_t)0xFFFFu;
+    return;
+  }
   const uint32_t *slots = window + (size_t)(epoch & 1u) * world * P;
   for (int k = tid; k < P; k += nthr) {
-    uint32_t s = 0;
-    for (int r = 0; r < world; ++r) s += __ldcv(slots + (size_t)r * P + k);
-    out[k] = k < N ? (uint16_t)(s & qmask) : (uint16_t)0;
+    uint32_t t = 0;
+    for (int r = 0; r < world; ++r) t += __ldcv(slots + (size_t)r * P + k);
+    out[k] = k < N ? (uint16_t)(t & qmask) : (uint16_t)0;
   }
 }
 
@@ -439,20 +499,48 @@ __global__ void k_sum_finalize(const uint32_t *__restrict__ partial, int N, int 
 
 // ---- device sampler for r: generateCustomArray(N, dr, dr).map(-1 -> 2) -------------------------
 // Same algorithm as index.js:461-488 (dr ones, dr "minus ones", Fisher-Yates from the top with
-// j = rand32 % (i+1)); the WebCrypto draw is replaced by a counter-based generator so that any
-// shard of any batch is reproducible: rand32(seed,row,i) = splitmix64(seed + G*(row*2048+i)) >> 32.
-__device__ __host__ __forceinline__ uint32_t sampler_rand32(uint64_t seed, uint64_t row, uint32_t i) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (row * 2048ull + i);
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (uint32_t)(z >> 32);
+// j = rand32 % (i+1)); the WebCrypto draw (index.js:481-483) is replaced by a keyed counter-mode CSPRNG so that the
+// device can draw r itself (ntru_encrypt_batch with r == NULL) and any row can be replayed by the key holder:
+// ChaCha20 (D. J. Bernstein's layout: 256-bit key, 64-bit block counter, 64-bit nonce), nonce = global row number,
+// block counter = 0, 1, ... within the row; the draw for position i = N-1, N-2, ..., 1 is keystream word
+// w = N-1-i (word w % 16 of block w / 16).  The key comes from the operating system's entropy (ntru_create) or
+// from ntru_set_rng_key.  The block function is pinned on the RFC 8439 section 2.3.2 vector through its host copy
+// (tests/test_host.py), the device against the host copy (tests/test_gpu_parity.py).
+struct ChaChaKey {
+  uint32_t k[8];
+};
+
+#define NTRU_CHACHA_QR(a, b, c, d)                    \
+  a += b; d ^= a; d = __funnelshift_l(d, d, 16);      \
+  c += d; b ^= c; b = __funnelshift_l(b, b, 12);      \
+  a += b; d ^= a; d = __funnelshift_l(d, d, 8);       \
+  c += d; b ^= c; b = __funnelshift_l(b, b, 7);
+
+__device__ __forceinline__ void chacha20_block(const ChaChaKey &key, uint64_t counter, uint64_t nonce, uint32_t (&out)[16]) {
+  const uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u,
+                           key.k[0], key.k[1], key.k[2], key.k[3], key.k[4], key.k[5], key.k[6], key.k[7],
+                           (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)nonce, (uint32_t)(nonce >> 32)};
+  uint32_t x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = in[i];
+#pragma unroll 2
+  for (int round = 0; round < 10; ++round) {
+    NTRU_CHACHA_QR(x[0], x[4], x[8], x[12])
+    NTRU_CHACHA_QR(x[1], x[5], x[9], x[13])
+    NTRU_CHACHA_QR(x[2], x[6], x[10], x[14])
+    NTRU_CHACHA_QR(x[3], x[7], x[11], x[15])
+    NTRU_CHACHA_QR(x[0], x[5], x[10], x[15])
+    NTRU_CHACHA_QR(x[1], x[6], x[11], x[12])
+    NTRU_CHACHA_QR(x[2], x[7], x[8], x[13])
+    NTRU_CHACHA_QR(x[3], x[4], x[9], x[14])
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
 }
 
 constexpr int kSampleRows = 64;   // rows (threads) per CTA
 
-__global__ void __launch_bounds__(kSampleRows) k_sample_r(int N, int P, int dr, uint64_t seed, uint64_t row0,
+__global__ void __launch_bounds__(kSampleRows) k_sample_r(int N, int P, int dr, const ChaChaKey key, uint64_t row0,
                                                           size_t B, uint8_t *__restrict__ r) {
   extern __shared__ __align__(16) uint8_t arr[];
   const int stride = P + 4;                       // bytes; (P+4)/4 is odd, so rows start in distinct banks
@@ -461,11 +549,20 @@ __global__ void __launch_bounds__(kSampleRows) k_sample_r(int N, int P, int dr, 
   uint8_t *mine = arr + (size_t)threadIdx.x * stride;
   if (row < B) {
     for (int i = 0; i < P; ++i) mine[i] = i < dr ? 1 : (i < 2 * dr ? 2 : 0);
-    for (int i = N - 1; i > 0; --i) {
-      const uint32_t j = sampler_rand32(seed, row0 + row, (uint32_t)i) % (uint32_t)(i + 1);
-      const uint8_t a = mine[i], b = mine[j];
-      mine[i] = b;
-      mine[j] = a;
+    int i = N - 1;
+    for (uint64_t blk = 0; i > 0; ++blk) {
+      uint32_t ks[16];
+      chacha20_block(key, blk, row0 + row, ks);
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        if (i > 0) {
+          const uint32_t j = ks[w] % (uint32_t)(i + 1);
+          const uint8_t a = mine[i], b = mine[j];
+          mine[i] = b;
+          mine[j] = a;
+          --i;
+        }
+      }
     }
   }
   __syncthreads();
@@ -650,25 +747,49 @@ int launch_decrypt_generic(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8
   return NTRU_OK;
 }
 
-int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial) {
-  if (B == 0) return NTRU_OK;
+// launch geometry of the sum kernels + their tree scratch (rows, group rows, tickets; zeroed once, the kernels leave
+// the tickets at zero)
+static int sum_geometry(ntru_ctx *ctx, size_t B, dim3 &block, size_t &smem, unsigned &blocks, SumScratch &sc) {
   const int VX = ctx->P / 8;
   const int RY = VX * kSumRows <= 512 ? kSumRows : 512 / VX;
-  dim3 block(VX, RY);
-  const size_t smem = (size_t)VX * RY * 8 * sizeof(uint32_t);
-  size_t blocks = (B + RY - 1) / RY;
+  block = dim3(VX, RY);
+  smem = (size_t)VX * RY * 8 * sizeof(uint32_t);
+  size_t nb = (B + RY - 1) / RY;
   const size_t cap = (size_t)ctx->sm_count * 4;
-  if (blocks > cap) blocks = cap;
+  if (nb > cap) nb = cap;
+  if (nb == 0) nb = 1;                                           // an empty shard still takes part in the exchange
+  blocks = (unsigned)nb;
+  const size_t max_groups = (cap + kSumGroup - 1) / kSumGroup;
+  const size_t words = (cap + max_groups) * (size_t)ctx->P + max_groups + 1;
+  if (ctx->d_sum_scratch.bytes < words * 4) {
+    NTRU_CUDA(ctx, ctx->d_sum_scratch.reserve(words * 4));
+    NTRU_CUDA(ctx, cudaMemsetAsync(ctx->d_sum_scratch.ptr, 0, words * 4, ctx->stream));
+  }
+  sc.rows = (uint32_t *)ctx->d_sum_scratch.ptr;
+  sc.grows = sc.rows + cap * (size_t)ctx->P;
+  sc.tickets = sc.grows + max_groups * (size_t)ctx->P;
+  return NTRU_OK;
+}
+
+int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *partial) {
+  if (B == 0) return NTRU_OK;
+  dim3 block;
+  size_t smem;
+  unsigned blocks;
+  SumScratch sc;
+  int rc = sum_geometry(ctx, B, block, smem, blocks, sc);
+  if (rc) return rc;
   {
     LaunchTimer timer(ctx, NTRU_K_SUM);
-    k_sum_partial<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, partial);
+    k_sum_partial<<<blocks, block, smem, ctx->stream>>>(e, B, ctx->P, sc, partial);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
 }
 
+// window of one rank: slots[2][world][P], flags[world], error word
 size_t xchg_window_bytes(const ntru_ctx *ctx, int world) {
-  return ((size_t)2 * world * ctx->P + world + 2) * sizeof(uint32_t);
+  return ((size_t)2 * world * ctx->P + world + 1) * sizeof(uint32_t);
 }
 
 int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
@@ -676,19 +797,15 @@ int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *o
   XchgPeers peers = {};
   for (int r = 0; r < world; ++r) peers.window[r] = (uint32_t *)ctx->peer_window[r];
   const uint32_t epoch = ++ctx->xchg_epoch;
-  const int VX = ctx->P / 8;
-  const int RY = VX * kSumRows <= 512 ? kSumRows : 512 / VX;
-  dim3 block(VX, RY);
-  const size_t smem = (size_t)VX * RY * 8 * sizeof(uint32_t);
-  size_t blocks = (B + RY - 1) / RY;
-  const size_t cap = (size_t)ctx->sm_count * 4;
-  if (blocks > cap) blocks = cap;
-  if (blocks == 0) blocks = 1;                                   // an empty shard still takes part in the exchange
+  dim3 block;
+  size_t smem;
+  unsigned blocks;
+  SumScratch sc;
+  int rc = sum_geometry(ctx, B, block, smem, blocks, sc);
+  if (rc) return rc;
   {
     LaunchTimer timer(ctx, NTRU_K_SUM);
-    uint32_t *ticket = (uint32_t *)ctx->peer_window[rank] + (size_t)2 * world * ctx->P + world;
-    k_sum_push<<<(unsigned)blocks, block, smem, ctx->stream>>>(e, B, ctx->P, (uint32_t *)ctx->d_partial.ptr, peers, ticket, world, rank,
-                                                               epoch, (uint32_t)ctx->q - 1, ctx->N, out);
+    k_sum_push<<<blocks, block, smem, ctx->stream>>>(e, B, ctx->P, sc, peers, world, rank, epoch, (uint32_t)ctx->q - 1, ctx->N, out);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
@@ -703,17 +820,19 @@ int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out) {
   return NTRU_OK;
 }
 
-int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r) {
+int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r) {
   if (B == 0) return NTRU_OK;
   const size_t smem = (size_t)kSampleRows * (ctx->P + 4);
   if (!ctx->sampler_attr_set) {
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_sample_r, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ctx->sampler_attr_set = true;
   }
+  ChaChaKey key;
+  for (int i = 0; i < 8; ++i) key.k[i] = ctx->rng_key[i];
   const size_t blocks = (B + kSampleRows - 1) / kSampleRows;
   {
     LaunchTimer timer(ctx, NTRU_K_OTHER);
-    k_sample_r<<<(unsigned)blocks, kSampleRows, smem, ctx->stream>>>(ctx->N, ctx->P, dr, seed, row0, B, r);
+    k_sample_r<<<(unsigned)blocks, kSampleRows, smem, ctx->stream>>>(ctx->N, ctx->P, dr, key, row0, B, r);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;

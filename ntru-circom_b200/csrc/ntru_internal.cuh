@@ -59,11 +59,12 @@ struct ntru_ctx {
   ntru::DevBuf slot_bufs[ntru::kNumSlots][10];     // pitched device arrays of the host pipeline
   ntru::DevBuf slot_packed[ntru::kNumSlots][10];   // packed staging (what the 1-D H2D / D2H copies move)
   ntru::DevBuf d_partial;
+  ntru::DevBuf d_sum_scratch;      // tree scratch of the ciphertext sum (per-CTA rows, per-group rows, tickets)
   // cross-GPU sum: exchange window (this rank's, cudaMalloc + IPC) and the mapped windows of the peers
   static constexpr int kMaxRanks = 16;
   int xchg_world = 1, xchg_rank = 0;
   bool xchg_connected = false;
-  ntru::DevBuf d_window;           // [2 parities][world][P] uint32 slots, then [world] uint32 flags, then ticket + error word
+  ntru::DevBuf d_window;           // [2 parities][world][P] uint32 slots, then [world] uint32 flags, then the error word
   void *peer_window[kMaxRanks] = {};
   bool peer_opened[kMaxRanks] = {};
   uint32_t xchg_epoch = 0;
@@ -71,9 +72,28 @@ struct ntru_ctx {
   int opt_path = 0;
   int umma_attr_set = 0;           // bit per kernel mode: dynamic shared memory attribute applied on this device
   bool sampler_attr_set = false;
+  // device CSPRNG for r (ChaCha20, generic_kernels.cu): key words (little-endian), next unused row number (= nonce),
+  // dr of the reference's constructor options (NTRU_OPT_DR; needed when the device draws r)
+  uint32_t rng_key[8] = {};
+  bool rng_keyed = false;
+  uint64_t rng_row = 0;
+  int opt_dr = -1;
   struct ImmaCfg { const void *fn; size_t smem; int per_sm; };
   std::vector<ImmaCfg> imma_cfg;   // launch configuration of the IMMA kernels already prepared on this context's device
   int tensor_variant = 0;          // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
+  // CUtensorMaps already encoded on this context, keyed by everything cuTensorMapEncodeTiled reads: a steady-state
+  // caller (same device buffers, same batch size) pays no driver call per launch
+  struct TmapKey {
+    const void *base; uint64_t inner, rows, stride; uint32_t box_inner, box_rows; int elem, swz;
+    bool operator==(const TmapKey &o) const {
+      return base == o.base && inner == o.inner && rows == o.rows && stride == o.stride && box_inner == o.box_inner &&
+             box_rows == o.box_rows && elem == o.elem && swz == o.swz;
+    }
+  };
+  struct TmapEntry { TmapKey key; alignas(64) unsigned char map[128]; };
+  std::vector<TmapEntry> tmap_cache;
+  size_t tmap_next = 0;            // round-robin replacement once the cache holds kTmapCacheMax entries
+  static constexpr size_t kTmapCacheMax = 64;
   int last_path = 0;
   int sm_count = 148;
   bool tensor_ok = false;          // device is sm_100 and the tcgen05 schedule initialised
@@ -116,7 +136,7 @@ int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *par
 int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
 size_t xchg_window_bytes(const ntru_ctx *ctx, int world);
 int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
-int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t seed, uint64_t row0, uint8_t *r);
+int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r);
 int launch_pack_fields(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch, int bits, int n,
                        int out_elems, uint32_t *out);
 int launch_unpack_fields(ntru_ctx *ctx, size_t B, const uint32_t *data, int in_elems, int bits, int n, size_t pitch, void *out,

@@ -223,9 +223,12 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             for (int lk = 0; lk < a.kl; ++lk) {
               mbar_wait(b_empty(sb), b_par ^ 1);
               if (elect_one()) {
+#ifdef NTRU_TRACE
                 if (a.debug_flags & 1) {   // timing experiment: no B traffic at all (operands are stale shared memory)
                   if (leader) mbar_arrive(b_full(sb)); else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                } else {
+                } else
+#endif
+                {
                   if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
                   else mbar_arrive_cluster(lead_b_full + 8u * sb);
                   tma_load_2d_pair(b_slot(sb), &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);

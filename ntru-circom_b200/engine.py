@@ -118,32 +118,42 @@ class Engine:
         self._check(self.lib.ntru_set_private_key(self._h, _ptr(f), _ptr(fp)))
 
     # -- host-buffer batches (packed rows) ------------------------------------------------
-    def encrypt_batch(self, r, m, *, h=None, witness=True, out=None):
-        """r, m: (B,N).  h: None (context key) or (B,N) distinct keys.  Returns dict of numpy arrays."""
+    def encrypt_batch(self, r, m, *, h=None, witness=True, out=None, dr=None, return_r=False):
+        """r, m: (B,N).  h: None (context key) or (B,N) distinct keys.  Returns dict of numpy arrays.
+
+        r=None: the device draws r like index.js:89 (needs dr, here or through set_dr) from its keyed ChaCha20
+        generator; return_r=True adds the r that was used (inputs.r, index.js:97) under "r"."""
         N = self.N
-        r = np.ascontiguousarray(r, dtype=np.uint8)
-        B = r.shape[0]
-        r = _host(r, np.uint8, (B, N))
         m_arr = np.asarray(m)
+        B = m_arr.shape[0]
+        if r is not None:
+            r = _host(np.ascontiguousarray(r, dtype=np.uint8), np.uint8, (B, N))
+        elif dr is not None:
+            self.set_dr(dr)
         wide = m_arr.dtype.itemsize > 1 and m_arr.size and int(m_arr.max(initial=0)) > 255
         m_arr = _host(m_arr, np.uint16 if wide else np.uint8, (B, N))
         out = out or {}
         value = out.get("value", np.empty((B, N), dtype=np.uint16))
         quo = out.get("quotientE", np.empty((B, N + 1), dtype=np.uint16)) if witness else None
         rem = out.get("remainderE", np.empty((B, N + 1), dtype=np.uint16)) if witness else None
+        r_out = out.get("r", np.empty((B, N), dtype=np.uint8)) if (return_r or r is None) else None
         if h is not None:
             if wide:
                 raise NtruError(_lib.NTRU_E_UNSUPPORTED, "wide messages with per-row keys")
             h = _host(h, np.uint16, (B, N))
             rc = self.lib.ntru_encrypt_batch_keys(self._h, B, _ptr(h), _ptr(r), _ptr(m_arr), _ptr(value),
-                                                  _ptr(quo), _ptr(rem))
+                                                  _ptr(quo), _ptr(rem), _ptr(r_out))
         elif wide:
             rc = self.lib.ntru_encrypt_batch_wide(self._h, B, _ptr(r), _ptr(m_arr), _ptr(value), _ptr(quo),
-                                                  _ptr(rem))
+                                                  _ptr(rem), _ptr(r_out))
         else:
-            rc = self.lib.ntru_encrypt_batch(self._h, B, _ptr(r), _ptr(m_arr), _ptr(value), _ptr(quo), _ptr(rem))
+            rc = self.lib.ntru_encrypt_batch(self._h, B, _ptr(r), _ptr(m_arr), _ptr(value), _ptr(quo), _ptr(rem),
+                                             _ptr(r_out))
         self._check(rc)
-        return {"value": value, "quotientE": quo, "remainderE": rem}
+        res = {"value": value, "quotientE": quo, "remainderE": rem}
+        if r_out is not None:
+            res["r"] = r_out
+        return res
 
     def decrypt_batch(self, e, *, f=None, fp=None, witness=True, out=None):
         N = self.N
@@ -258,16 +268,74 @@ class Engine:
         """out[k] = column sums mod q over every rank's rows (local rows only when no exchange is connected)."""
         self._check(self.lib.ntru_sum_allreduce_dev(self._h, B, _ptr(e) if B else None, _ptr(out)))
 
-    def sample_r_dev(self, B, dr, seed, row0, r):
-        self._check(self.lib.ntru_sample_r_dev(self._h, B, int(dr), int(seed), int(row0), _ptr(r)))
+    def sample_r_dev(self, B, dr, row0, r, seed=None):
+        """generateCustomArray(N, dr, dr).map(-1 -> 2) into device rows for the global row numbers [row0, row0 + B),
+        drawn by the context's ChaCha20 generator.  seed (tests / benchmarks only): first replaces the context's
+        OS-entropy key by seed_key(seed), which makes the rows reproducible -- and predictable."""
+        if seed is not None:
+            self.set_rng_key(seed_key(seed), self.rng_next_row)
+        self._check(self.lib.ntru_sample_r_dev(self._h, B, int(dr), int(row0), _ptr(r)))
+
+    # ---- device generator for r (include/ntru_b200.h: ntru_set_rng_key) ----
+    def set_dr(self, dr: int):
+        self.set_option(_lib.NTRU_OPT_DR, int(dr))
+
+    def set_rng_key(self, key: bytes, first_row: int = 0):
+        """Replaces the OS-entropy key of the device generator (32 bytes) and sets the next row number."""
+        if len(key) != 32:
+            raise ValueError("the ChaCha20 key is 32 bytes")
+        buf = (ctypes.c_ubyte * 32).from_buffer_copy(bytes(key))
+        self._check(self.lib.ntru_set_rng_key(self._h, buf, int(first_row)))
+
+    @property
+    def rng_next_row(self) -> int:
+        return int(self.lib.ntru_rng_next_row(self._h))
+
+    def xchg_destroy(self):
+        """Collective (sync + barrier over all ranks first): frees the exchange windows; raises if a peer had timed out."""
+        self._check(self.lib.ntru_xchg_destroy(self._h))
 
 
-def sampler_rand32(seed: int, row: int, i: int) -> int:
-    """Host copy of the device sampler's counter-based generator (csrc/generic_kernels.cu:sampler_rand32)."""
-    M = (1 << 64) - 1
-    z = (seed + 0x9E3779B97F4A7C15 * (row * 2048 + i)) & M
-    z = (z + 0x9E3779B97F4A7C15) & M
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
-    z ^= z >> 31
-    return z >> 32
+# ---- host copy of the device generator (csrc/generic_kernels.cu: chacha20_block, k_sample_r) -------------------------
+# For the key holder's audit replay of device-drawn r and for the parity tests; never used to produce r in the product.
+_M32 = 0xFFFFFFFF
+
+
+def seed_key(seed: int) -> bytes:
+    """32-byte key made of a small integer seed (tests / benchmarks: reproducible, NOT secret)."""
+    return int(seed).to_bytes(32, "little")
+
+
+def chacha20_block(key: bytes, counter: int, nonce: int):
+    """ChaCha20 block function, D. J. Bernstein's layout: 32-byte key, 64-bit block counter, 64-bit nonce.
+    Returns the 16 keystream words (uint32).  RFC 8439's 32-bit counter / 96-bit nonce is the same state with
+    counter = ctr | nonce_word0 << 32 and nonce = nonce_word1 | nonce_word2 << 32."""
+    k = [int.from_bytes(key[4 * i:4 * i + 4], "little") for i in range(8)]
+    st = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574, *k,
+          counter & _M32, (counter >> 32) & _M32, nonce & _M32, (nonce >> 32) & _M32]
+    x = list(st)
+
+    def rotl(v, n):
+        return ((v << n) & _M32) | (v >> (32 - n))
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & _M32; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & _M32; x[b] = rotl(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & _M32; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & _M32; x[b] = rotl(x[b] ^ x[c], 7)
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return [(a + b) & _M32 for a, b in zip(x, st)]
+
+
+def sampler_draws(key: bytes, row: int, count: int):
+    """The first `count` 32-bit draws of global row number `row`: what the device feeds, in order, to the Fisher-Yates
+    steps i = N-1, N-2, ... of generateCustomArray (index.js:476-485)."""
+    out = []
+    blk = 0
+    while len(out) < count:
+        out.extend(chacha20_block(key, blk, row))
+        blk += 1
+    return out[:count]

@@ -250,19 +250,22 @@ class NTRU:
 
     # ---- hot path: batches (engine-native unit of work) ------------------------------------------
     def encryptBitsBatch(self, ms, rs=None, *, hs=None, witness: bool = True):
-        """ms: (B,N) messages (zero padded); rs: (B,N) in {0,1,2} or None (host CSPRNG, index.js:89);
-        hs: optional (B,N) distinct public keys.  Returns fixed-length numpy arrays (un-trimmed)."""
+        """ms: (B,N) messages (zero padded); rs: (B,N) in {0,1,2} or None: drawn like index.js:89 -- on the DEVICE by
+        the engine's entropy-keyed ChaCha20 generator, or on the host when a ``rand32`` was injected (tests);
+        hs: optional (B,N) distinct public keys.  Returns fixed-length numpy arrays (un-trimmed); "r" is included
+        whenever the call drew it (inputs.r, index.js:97)."""
         ms = np.asarray(ms)
         B = ms.shape[0]
         if ms.ndim != 2 or ms.shape[1] > self.N:
             raise IndexError("RangeError: Invalid array length")
         if ms.shape[1] < self.N:
             ms = np.pad(ms, ((0, 0), (0, self.N - ms.shape[1])))
-        if rs is None:
-            rs = np.array([self.sampleR() for _ in range(B)], dtype=np.uint8)
+        drew = rs is None
+        if drew and self.rand32 is not None:
+            rs = np.array([self.sampleR() for _ in range(B)], dtype=np.uint8).reshape(B, self.N)
         eng = self.engine() if hs is not None else self._load_public()
         return eng.encrypt_batch(rs, np.mod(ms.astype(np.int64), self.q) if ms.dtype.kind == "i" else ms,
-                                 h=hs, witness=witness)
+                                 h=hs, witness=witness, dr=self.dr if rs is None else None, return_r=drew)
 
     def decryptBitsBatch(self, es, *, fs=None, fps=None, witness: bool = True):
         es = np.asarray(es)

@@ -37,7 +37,7 @@ def setup(cfg):
 def same_key(cfg, B):
     g, eng, N, q, dr = setup(cfg)
     P = eng.pitch
-    r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, dr, 1, 0, r)
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, dr, 0, r, seed=1)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev); m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
     val = torch.empty((B, P), dtype=torch.int16, device=dev); quo = torch.empty_like(val)
     out = torch.empty((B, P), dtype=torch.uint8, device=dev); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)
@@ -79,7 +79,7 @@ def distinct_key(cfg, B, path=0, valid_keys=0):
         h[:, :N] = torch.randint(0, q, (B, N), device=dev, dtype=torch.int16)
         f[:, :N] = torch.randint(-1, 2, (B, N), device=dev, dtype=torch.int8)
         fp[:, :N] = torch.randint(0, 3, (B, N), device=dev, dtype=torch.uint8)
-    r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, dr, 1, 0, r)
+    r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, dr, 0, r, seed=1)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev); m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
     val = torch.empty((B, P), dtype=torch.int16, device=dev); quo = torch.empty_like(val)
     out = torch.empty((B, P), dtype=torch.uint8, device=dev); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)

@@ -70,7 +70,7 @@ def config4(total=1 << 20):
     lo, hi = sharding.shard_bounds(total, world, rank)
     B, P = hi - lo, eng.pitch
     r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
-    eng.sample_r_dev(B, dr, 821, lo, r)                      # counter-based: the same rows at every world size
+    eng.sample_r_dev(B, dr, lo, r, seed=821)                      # counter-based: the same rows at every world size
     gen = torch.Generator(device=dev).manual_seed(99)
     m_all = torch.randint(0, 2, (total, N), generator=gen, device=dev, dtype=torch.uint8)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev)

@@ -17,7 +17,7 @@ eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 B, P = 1 << 20, eng.pitch
 dev = "cuda"
-r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, int(g["dr"]), 1, 0, r)
+r = torch.zeros((B, P), dtype=torch.uint8, device=dev); eng.sample_r_dev(B, int(g["dr"]), 0, r, seed=1)
 m = torch.zeros((B, P), dtype=torch.uint8, device=dev); m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
 val = torch.empty((B, P), dtype=torch.int16, device=dev); quo = torch.empty_like(val)
 out = torch.empty((B, P), dtype=torch.uint8, device=dev); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)

@@ -26,7 +26,7 @@ f[:, :N] = torch.randint(-1, 2, (rows, N), device=dev, dtype=torch.int8)
 fp = torch.zeros((rows, P), dtype=torch.uint8, device=dev)
 fp[:, :N] = torch.randint(0, 3, (rows, N), device=dev, dtype=torch.uint8)
 r = torch.zeros((rows, P), dtype=torch.uint8, device=dev)
-eng.sample_r_dev(rows, dr, 1, 0, r)
+eng.sample_r_dev(rows, dr, 0, r, seed=1)
 m = torch.zeros((rows, P), dtype=torch.uint8, device=dev)
 m[:, :N] = torch.randint(0, 2, (rows, N), device=dev, dtype=torch.uint8)
 val = torch.empty((rows, P), dtype=torch.int16, device=dev)

@@ -22,7 +22,7 @@ eng.set_path(path)
 P = eng.pitch
 dev = "cuda"
 r = torch.zeros((rows, P), dtype=torch.uint8, device=dev)
-eng.sample_r_dev(rows, dr, 1, 0, r)
+eng.sample_r_dev(rows, dr, 0, r, seed=1)
 m = torch.zeros((rows, P), dtype=torch.uint8, device=dev)
 m[:, :N] = torch.randint(0, 2, (rows, N), device=dev, dtype=torch.uint8)
 val = torch.empty((rows, P), dtype=torch.int16, device=dev)

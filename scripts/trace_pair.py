@@ -21,7 +21,7 @@ eng = nb.Engine(NN, 3, QQ, 0)
 eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
 rows = int(os.environ.get('TRACE_ROWS', 74 * 256 * 6))
 P = eng.pitch
-r = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); eng.sample_r_dev(rows, int(g["dr"]), 1, 0, r)
+r = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); eng.sample_r_dev(rows, int(g["dr"]), 0, r, seed=1)
 m = torch.zeros((rows, P), dtype=torch.uint8, device="cuda"); m[:, :NN] = torch.randint(0, 2, (rows, NN), device="cuda", dtype=torch.uint8)
 val = torch.empty((rows, P), dtype=torch.int16, device="cuda"); quo = torch.empty_like(val)
 out = torch.empty((rows, P), dtype=torch.uint8, device="cuda"); q1 = torch.empty_like(val); r1 = torch.empty_like(val); q2 = torch.empty_like(out)

@@ -537,21 +537,86 @@ def test_sum_over_exchange_window_single_rank(cfg, nb, golden):
     eng.close()
 
 
-def test_device_sampler_matches_host_fisher_yates(nb, engines):
+class _Draws:
+    """rng stand-in for the oracle's generate_custom_array: hands out a fixed list of 32-bit draws."""
+
+    def __init__(self, words):
+        self.it = iter(words)
+
+    def getrandbits(self, n):
+        assert n == 32
+        return next(self.it)
+
+
+def _replay_r(nb, key, row, N, dr):
+    """r of global row number `row` as the ORACLE computes it from the generator's draws (index.js:89, 461-488)."""
+    arr = o.generate_custom_array(N, dr, dr, _Draws(nb.sampler_draws(key, row, N - 1)))
+    return [2 if x == -1 else x for x in arr]
+
+
+@pytest.mark.parametrize("cfg", ["tiny17", "default167", "hps509", "hps821"])
+def test_device_sampler_matches_oracle_fisher_yates(cfg, nb, engines, golden):
+    """The device sampler against the oracle's generate_custom_array fed with the same ChaCha20 draws (host copy of
+    the generator: pinned on the RFC 8439 vector in tests/test_host.py)."""
     torch = pytest.importorskip("torch")
-    eng = engines("hps509")
-    N, dr, B, seed, row0 = 509, 169, 70, 99, 5
+    g, eng = golden(cfg), engines(cfg)
+    N, dr, B, seed, row0 = int(g["N"]), int(g["dr"]), 70, 99, (1 << 40) + 5
     r = torch.zeros((B, eng.pitch), dtype=torch.uint8, device="cuda")
-    eng.sample_r_dev(B, dr, seed, row0, r)
+    eng.sample_r_dev(B, dr, row0, r, seed=seed)
     eng.sync()
     got = r.cpu().numpy()
     assert not got[:, N:].any()
     for b in (0, 1, 63, 64, 69):
-        it = iter(range(N - 1, 0, -1))
-        draws = iter([nb.sampler_rand32(seed, row0 + b, i) for i in range(N - 1, 0, -1)])
-        arr = nb.generateCustomArray(N, dr, dr, rand32=lambda: next(draws))
-        assert got[b, :N].tolist() == [2 if x == -1 else x for x in arr]
+        assert got[b, :N].tolist() == _replay_r(nb, nb.seed_key(seed), row0 + b, N, dr), (cfg, b)
     assert (np.count_nonzero(got == 1, axis=1) == dr).all() and (np.count_nonzero(got == 2, axis=1) == dr).all()
+    with pytest.raises(nb.NtruError, match="cannot exceed"):           # index.js:462-464
+        eng.sample_r_dev(1, N // 2 + 1, 0, r)
+
+
+@pytest.mark.parametrize("cfg", ["default167", "hps509"])
+def test_encrypt_with_device_drawn_r(cfg, nb, golden):
+    """ntru_encrypt_batch with r == NULL (index.js:89: the call draws r itself): r_out is the exact-weight ternary row
+    the oracle derives from the generator's draws for that row number, the ciphertext and witness are the oracle's for
+    that r, row numbers are never reused, and several pipeline chunks continue the numbering."""
+    g = golden(cfg)
+    N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_public_key(g["h"])
+    eng.set_private_key(g["f"], g["fp"])
+    m = np.random.default_rng(3).integers(0, 2, size=(700, N)).astype(np.uint8)
+    with pytest.raises(nb.NtruError, match="NTRU_OPT_DR"):
+        eng.encrypt_batch(None, m)
+    # 1. the context's own key (OS entropy): valid weights, decrypts, fresh r on every call
+    a = eng.encrypt_batch(None, m, dr=dr)
+    b = eng.encrypt_batch(None, m)
+    assert eng.rng_next_row == 1400
+    for x in (a, b):
+        assert (np.count_nonzero(x["r"] == 1, axis=1) == dr).all() and (np.count_nonzero(x["r"] == 2, axis=1) == dr).all()
+        assert x["r"].max() <= 2
+        assert np.array_equal(eng.decrypt_batch(x["value"], witness=False)["value"], m)
+    assert not np.array_equal(a["r"], b["r"]) and not np.array_equal(a["value"], b["value"])
+    # 2. a known key: replay through the oracle, on every schedule, with chunked pipelining (128-row chunks)
+    key = bytes(range(100, 132))
+    eng.set_option(2, 128)                                   # NTRU_OPT_CHUNK_ROWS
+    for path in _paths(nb, eng):
+        eng.set_path(path)
+        eng.set_rng_key(key, 1000)
+        enc = eng.encrypt_batch(None, m)
+        assert eng.rng_next_row == 1700
+        rows = [0, 1, 127, 128, 129, 383, 384, 699]
+        want_r = np.array([_replay_r(nb, key, 1000 + i, N, dr) for i in rows])
+        assert np.array_equal(enc["r"][rows], want_r), (cfg, path)
+        want = o.encrypt_batch(g["h"].astype(np.int64), enc["r"], m, q)
+        for k in ENC_KEYS:
+            assert np.array_equal(enc[k], want[k]), (cfg, path, k)
+        # value-only, r not returned: same ciphertexts for the same row numbers
+        eng.set_rng_key(key, 1000)
+        rc = eng.lib.ntru_encrypt_batch(eng._h, 700, None, m.ctypes.data, enc["value"].ctypes.data, None, None, None)
+        assert rc == 0 and np.array_equal(enc["value"], want["value"])
+    # 3. an injected r is echoed into r_out
+    r = o.sample_ternary_rows(5, N, dr, dr, np.random.default_rng(1)).astype(np.uint8)
+    assert np.array_equal(eng.encrypt_batch(r, m[:5], return_r=True)["r"], r)
+    eng.close()
 
 
 def test_device_resident_api_and_properties_at_scale(nb, engines, golden):
@@ -562,7 +627,7 @@ def test_device_resident_api_and_properties_at_scale(nb, engines, golden):
     dev = "cuda"
     gen = torch.Generator(device=dev).manual_seed(1)
     r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
-    eng.sample_r_dev(B, 169, 7, 0, r)
+    eng.sample_r_dev(B, 169, 0, r, seed=7)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
     m[:, :N] = torch.randint(0, 2, (B, N), generator=gen, device=dev, dtype=torch.uint8)
     val = torch.empty((B, P), dtype=torch.int16, device=dev)
@@ -634,7 +699,7 @@ def test_full_size_round_trip_and_checksums(nb, engines, golden):
     N, q, P, B = 509, 2048, eng.pitch, 1_000_000
     dev = "cuda"
     r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
-    eng.sample_r_dev(B, 169, 11, 0, r)
+    eng.sample_r_dev(B, 169, 0, r, seed=11)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
     m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
     val = torch.empty((B, P), dtype=torch.int16, device=dev)
@@ -680,7 +745,7 @@ def test_pad_columns_of_device_rows_do_not_count(cfg, nb, engines, golden):
     B = 74 * 256 + 77
     gen = torch.Generator(device=dev).manual_seed(5)
     r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
-    eng.sample_r_dev(B, dr, 9, 0, r)
+    eng.sample_r_dev(B, dr, 0, r, seed=9)
     m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
     m[:, :N] = torch.randint(0, 2, (B, N), generator=gen, device=dev, dtype=torch.uint8)
 

@@ -33,7 +33,19 @@ def test_abi_rejects_bad_parameters_without_a_gpu():
     assert lib.ntru_create(ctypes.byref(h), 167, 3, 100, 0) == _lib.NTRU_E_PARAM      # q not a power of two
     assert lib.ntru_create(ctypes.byref(h), 4, 3, 128, 0) == _lib.NTRU_E_PARAM        # N too small
     assert lib.ntru_create(ctypes.byref(h), 1024, 3, 16384, 0) == _lib.NTRU_E_PARAM   # fp32 exactness bound
+    # q > 8192 is refused outright (the tcgen05 schedule's 5-bit high limb and its one-byte lift stop at q = 8192):
+    # the two cases that used to be accepted and then decrypted wrongly on the tensor schedule
+    assert lib.ntru_create(ctypes.byref(h), 167, 3, 16384, 0) == _lib.NTRU_E_PARAM
+    assert lib.ntru_create(ctypes.byref(h), 128, 3, 32768, 0) == _lib.NTRU_E_PARAM
     assert lib.ntru_strerror(_lib.NTRU_E_NOKEY) == b"key not set"
+
+
+def test_shipped_library_reads_no_debug_environment_switches():
+    """The timing experiments (NTRU_DEBUG_*: skip loads / stores, results wrong on purpose) exist in NTRU_TRACE builds
+    only; a stray environment variable cannot change what the shipped library computes."""
+    from ntru_circom_b200 import _lib
+    blob = open(_lib.LIB_PATH, "rb").read()
+    assert b"NTRU_DEBUG_" not in blob and b"NTRU_TRACE_" not in blob
 
 
 def test_product_never_imports_the_oracle():
@@ -128,10 +140,33 @@ def test_constructor_defaults_and_errors():
         nb.generateCustomArray(5, 3, 3)
 
 
-def test_sampler_generator_is_reproducible():
-    a = [nb.sampler_rand32(1, 2, i) for i in range(4)]
-    assert a == [nb.sampler_rand32(1, 2, i) for i in range(4)]
-    assert len(set(a)) == 4 and all(0 <= x < 2 ** 32 for x in a)
+class _Draws:
+    """rng stand-in for the oracle's generate_custom_array: hands out a fixed list of 32-bit draws."""
+
+    def __init__(self, words):
+        self.it = iter(words)
+
+    def getrandbits(self, n):
+        assert n == 32
+        return next(self.it)
+
+
+def test_host_copy_of_the_device_generator_is_chacha20():
+    """The device draws r from ChaCha20 (csrc/generic_kernels.cu); its host copy is pinned on the block-function
+    vector of RFC 8439 section 2.3.2 (key 00..1f, counter 1, nonce 00:00:00:09:00:00:00:4a:00:00:00:00 -- in the
+    64-bit counter / 64-bit nonce layout used here: counter = 1 | 0x09000000 << 32, nonce = 0x4a000000)."""
+    ks = nb.chacha20_block(bytes(range(32)), 1 | (0x09000000 << 32), 0x4A000000)
+    assert ks == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3, 0xC7F4D1C7, 0x0368C033, 0x9AAA2204, 0x4E6CD4C3,
+                  0x466482D2, 0x09AA9F07, 0x05D7C214, 0xA2028BD9, 0xD19C12B5, 0xB94E16DE, 0xE883D0CB, 0x4E3C50A2]
+    # a row's draws are the keystream words of blocks 0, 1, ... under nonce = row number
+    d = nb.sampler_draws(nb.seed_key(5), 7, 40)
+    assert d[:16] == nb.chacha20_block(nb.seed_key(5), 0, 7) and d[16:32] == nb.chacha20_block(nb.seed_key(5), 1, 7)
+    assert d != nb.sampler_draws(nb.seed_key(5), 8, 40) and d != nb.sampler_draws(nb.seed_key(6), 7, 40)
+    # the product's generateCustomArray and the oracle's consume draws identically (index.js:476-485)
+    for N, dr in ((17, 3), (167, 18), (509, 169)):
+        words = nb.sampler_draws(nb.seed_key(1), 3, N - 1)
+        it = iter(words)
+        assert nb.generateCustomArray(N, dr, dr, rand32=lambda: next(it)) == o.generate_custom_array(N, dr, dr, _Draws(words))
 
 
 def test_seeds_of_the_gpu_class_tests_decrypt_in_the_oracle(golden):
