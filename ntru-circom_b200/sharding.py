@@ -53,6 +53,18 @@ def connect_exchange(engine, group=None) -> None:
     dist.barrier(group=group)
 
 
+def disconnect_exchange(engine, group=None) -> None:
+    """Collective teardown of the exchange: every rank finishes its last sum (sync), all ranks meet at a barrier --
+    peers store into a rank's window until THEIR last call has completed -- and only then the windows are unmapped
+    and freed (ntru_xchg_destroy; raises if a peer had timed out inside a sum kernel)."""
+    import torch.distributed as dist
+
+    engine.sync()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.barrier(group=group)
+    engine.xchg_destroy()
+
+
 def sum_ciphertexts_exchange(engine, e_dev, rows: int, out=None):
     """Column sums mod q of a sharded batch over the peer-memory exchange (after connect_exchange): local
     column sums, stores into every peer's window over NVLink, one-CTA gather -- all in the library's kernels."""
