@@ -57,7 +57,7 @@ enum {
                                schedule, 2 force the tcgen05 schedule (same-key only), 3 force the register-fragment schedule */
   NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
   NTRU_OPT_TIMING = 3,      /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
-  NTRU_OPT_TENSOR_VARIANT = 4, /* tcgen05 schedule: 0 = CTA-pair kernel (cta_group::2, default), 1 = single-CTA kernel */
+  /* 4 was NTRU_OPT_TENSOR_VARIANT (a single-CTA tcgen05 kernel kept as a cross-check in round 1; removed) */
   NTRU_OPT_DR = 5           /* dr of new NTRU({..., dr}) (index.js:15): weights of the r the device draws when r == NULL */
 };
 

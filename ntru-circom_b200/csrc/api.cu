@@ -340,10 +340,6 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
       if (value < 0 || 2 * value > ctx->N) return fail(ctx, NTRU_E_PARAM, "The total of 1s and -1s cannot exceed the array length.");
       ctx->opt_dr = (int)value;
       return NTRU_OK;
-    case NTRU_OPT_TENSOR_VARIANT:
-      if (value < 0 || value > 1) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_TENSOR_VARIANT must be 0 or 1");
-      ctx->tensor_variant = (int)value;
-      return NTRU_OK;
     default:
       return fail(ctx, NTRU_E_PARAM, "unknown option");
   }

@@ -34,13 +34,16 @@ struct DevBuf {
   }
 };
 
+constexpr int kMaxChunks = 8;   // accumulator chunks per product and part (ENC at N = 1024: 8 chunks of 128 outputs)
+
 // Operand matrices of the tcgen05 schedule for one fixed key polynomial (see umma_kernels.cu).
 struct KeyMatrix {
-  DevBuf mat;            // [2*ncols_pad][klen] bytes, K-major
-  alignas(64) unsigned char tmap[128];        // CUtensorMap, box = NC rows (single-CTA kernel)
-  alignas(64) unsigned char tmap_half[128];   // CUtensorMap, box = NC/2 rows (CTA-pair kernel)
+  DevBuf mat;            // [2 parts * nlimbs * covered columns][klen] bytes, K-major, tile-major per 128-byte K block
+  alignas(64) unsigned char tmap_half[2][128];   // CUtensorMaps, box = half the B rows of a chunk of width w[i]
   bool ready = false;
-  int limbs = 0, nlimbs = 0, klen = 0, nchunks = 0, chunk_cols = 0, out_cols = 0;
+  int limbs = 0, nlimbs = 0, klen = 0, nchunks = 0;
+  int col0[kMaxChunks + 1] = {};   // chunk c computes output columns [col0[c], col0[c+1])
+  int w[2] = {0, 0};               // the (at most two) distinct chunk widths: first chunk's, last chunk's
 };
 
 }  // namespace ntru
@@ -80,7 +83,6 @@ struct ntru_ctx {
   int opt_dr = -1;
   struct ImmaCfg { const void *fn; size_t smem; int per_sm; };
   std::vector<ImmaCfg> imma_cfg;   // launch configuration of the IMMA kernels already prepared on this context's device
-  int tensor_variant = 0;          // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
   // CUtensorMaps already encoded on this context, keyed by everything cuTensorMapEncodeTiled reads: a steady-state
   // caller (same device buffers, same batch size) pays no driver call per launch
   struct TmapKey {

@@ -25,14 +25,16 @@
 //         int32 accumulator receives the exact product (u8 x s8).
 // All-zero K ranges of the triangular hi matrix are skipped at 128-byte granularity.
 //
-// Two kernels implement it: k_umma_pair (umma_pair.cuh, the default: one CTA pair per 256 rows, cta_group::2,
-// resident A operand, B ring shared by the pair, TMA-store epilogue in two warp groups) and k_umma_product below
-// (single CTA per 128 rows, kept as a cross-check).  Warp roles of k_umma_product (576 threads, 1 CTA per SM,
-// persistent over row tiles):
-//   warp 0      TMA producer (A and B slices)      warp 1      tcgen05.mma issuer, owns TMEM
-//   warps 2-9   DEC1: e -> byte-limb A slices; ENC / DEC2: epilogue   warps 10-17 epilogue (TMEM -> regs -> global)
-// Pipelines: a 4-stage shared-memory ring (full/empty mbarriers) and two 256-column TMEM accumulators
-// (tmem_full/tmem_empty mbarriers) so that the epilogue of chunk j overlaps the MMAs of chunk j+1.
+// All-zero K ranges of the triangular hi matrix are skipped at 128-byte granularity, and the last K atom issues only the
+// 32-byte MMA steps that hold coefficients below N.
+//
+// The N output columns are cut into accumulator CHUNKS (at most 256 TMEM columns each, two chunks in flight).  Chunk
+// widths come from a table (UmmaArgs::col0): the widths are as equal as the epilogue's granularity allows and add up to
+// N rounded up to that granularity, not to a multiple of 256 -- at N = 821 DEC1 computes 832 columns (224 + 224 + 192 +
+// 192) where uniform 256-wide chunks computed 1024.
+//
+// The kernel is k_umma_pair (umma_pair.cuh): one CTA pair per 256 rows, cta_group::2, resident A operand, B ring shared
+// by the pair, TMA-store epilogue in two warp groups.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -48,28 +50,22 @@ namespace {
 
 enum Mode { ENC = 0, DEC1 = 1, DEC2 = 2 };
 
-constexpr int kStages = 4;
 constexpr int kTileRows = 128;
 constexpr int kAtomK = 128;                      // bytes of K per pipeline slice (one 128B swizzle atom)
 constexpr int kABytes = kTileRows * kAtomK;      // 16 KB
-constexpr int kBBytesMax = 256 * kAtomK;         // 32 KB
-constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kThreads = 576;
-constexpr int kBuilderWarp0 = 2, kEpilogueWarp0 = 10;
 constexpr int kAccCols = 256;                    // TMEM columns per accumulator buffer
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct UmmaArgs {
   int N, P, Kp, atoms;
+  int k_last;             // 32-byte MMA steps of the last K atom that hold coefficients below N (1..4)
   int kl;                 // K limbs (DEC1 with q > 256: 2)
   int nl;                 // N limbs (ENC with q > 256: 2)
-  int NC;                 // accumulator columns per chunk = MMA N = nl * NCo
-  int NCo;                // output coefficients per chunk
-  int nchunks, with_hi, q;
+  int nchunks;            // accumulator chunks per part; chunk c computes output columns [col0[c], col0[c+1])
+  int col0[kMaxChunks + 1];
+  int w0;                 // width of chunk 0: chunks of this width load B through tmapB, the others through tmapB2
+  int with_hi, q;
   uint32_t qmask;
   size_t B;
-  int ntiles;
-  // 2-CTA variant (umma_pair.cuh)
   int npairs;             // 256-row pair tiles
   int nA, nB;             // shared-memory slots for A and stages for B
   int a_resident;         // A slots hold the whole tile (loaded once per tile)
@@ -77,8 +73,8 @@ struct UmmaArgs {
   int nM, nS;             // message slots (ENC), store-staging slots
   int a_rel;              // commits that free an A slot: 2 (both MMA issuers) for resident A, else 1
   int two_issuers;        // second MMA issuer warp enabled (needs slices per chunk < B ring stages)
-  int debug_flags;        // timing experiments only (NTRU_DEBUG_NOB: bit 0 = skip the B operand loads)
-  int mat_rows;           // rows of the key matrix (2 * nchunks * NC); K block kb starts at row kb * mat_rows
+  int debug_flags;        // NTRU_TRACE builds only (NTRU_DEBUG_NOB: bit 0 = skip the B operand loads)
+  int mat_rows;           // rows of the key matrix (2 parts * nl * covered columns); K block kb starts at row kb * mat_rows
   int out_mask;           // which outputs exist: bit0 = cyc #1, bit1 = cyc #2, bit2 = hi
   const void *a_src;      // DEC1: e rows (uint16), pitch P elements
   const uint8_t *m;       // ENC: message rows
@@ -127,21 +123,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -158,387 +139,39 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// cute::UMMA::InstrDescriptor for kind::i8: c_format=S32 (2) at [4,6), a_format at [7,10), b_format at [10,13)
-// (0 = u8, 1 = s8), K-major A and B, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int a_signed, int b_signed, int n) {
-  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(kTileRows >> 4) << 24);
-}
-
-// first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= c*NCo + 1
+// first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= col0[c] + 1
 __device__ __forceinline__ int first_atom(const UmmaArgs &a, int part_hi, int c) {
   if (!part_hi) return 0;
-  const int a0 = (c * a.NCo + 1) / kAtomK;
+  const int a0 = (a.col0[c] + 1) / kAtomK;
   return a0 < a.atoms ? a0 : a.atoms - 1;
-}
-
-// Enumerates the (tile, part, chunk, atom) work items of one CTA in pipeline order.
-struct AtomIter {
-  int tile, part, c, at, parts;
-  bool valid;
-  __device__ __forceinline__ void start(const UmmaArgs &a) {
-    parts = a.with_hi ? 2 : 1;
-    tile = blockIdx.x; part = 0; c = 0;
-    valid = tile < a.ntiles;
-    at = valid ? first_atom(a, a.with_hi, 0) : 0;
-  }
-  __device__ __forceinline__ void next(const UmmaArgs &a) {
-    if (++at < a.atoms) return;
-    if (++c == a.nchunks) {
-      c = 0;
-      if (++part == parts) {
-        part = 0;
-        tile += gridDim.x;
-        if (tile >= a.ntiles) { valid = false; return; }
-      }
-    }
-    at = first_atom(a, a.with_hi && part == 0, c);
-  }
-};
-
-// One accumulator chunk of one epilogue warp: prefetch what the chunk needs from global memory, wait for the
-// MMAs, then TMEM -> registers -> reduction / fold / witness -> global.  `sub` = this warp's index among the kSub
-// warps of its TMEM lane quadrant; it owns the 16-coefficient units sub, sub + kSub, ...
-struct NoMark {
-  __device__ __forceinline__ void operator()(int) const {}
-};
-
-template <int MODE, int kSub, class WaitFn, class MarkFn = NoMark>
-__device__ __forceinline__ void epilogue_chunk(const UmmaArgs &a, int hi, int c, int sub, bool row_ok, size_t rbase,
-                                               uint32_t t_addr, WaitFn wait_acc, MarkFn mark = MarkFn()) {
-  constexpr int kUnitsPerWarp = 16 / kSub;
-  const int units = a.NCo >> 4;
-  const uint32_t Q2 = a.qmask | (a.qmask << 16);             // the modulus mask in both 16-bit lanes
-  const uint32_t lift_add = ((uint32_t)a.q >> 1) - 1;        // x > q/2  <=>  (x + q/2 - 1) >> log2(q)
-  const int logq = 31 - __clz(a.q);
-  // ENC: fetch this thread's message bytes for the whole chunk before waiting on the accumulator;
-  // bytes of coefficients >= N are cleared so that the pad of every output row is written as zero
-  uint4 mm[kUnitsPerWarp];
-  if (MODE == ENC && !hi) {
-#pragma unroll
-    for (int ui = 0; ui < kUnitsPerWarp; ++ui) {
-      const int u = sub + kSub * ui;
-      const int kk = c * a.NCo + u * 16;
-      const bool ok = row_ok && u < units && kk < a.N;
-      uint4 x = ok ? __ldg(reinterpret_cast<const uint4 *>(a.m + rbase + kk)) : make_uint4(0, 0, 0, 0);
-      const int nvalid = a.N - kk;
-      if (ok && nvalid < 16) {
-        uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int wd = 0; wd < 4; ++wd) {
-          const int nb = nvalid - 4 * wd;               // valid bytes in this word
-          xs[wd] = nb >= 4 ? xs[wd] : (nb <= 0 ? 0u : (xs[wd] & (0xffffffffu >> (8 * (4 - nb)))));
-        }
-        x = make_uint4(xs[0], xs[1], xs[2], xs[3]);
-      }
-      mm[ui] = x;
-    }
-  }
-  wait_acc();
-  tc_fence_after();
-#pragma unroll
-  for (int ui = 0; ui < kUnitsPerWarp; ++ui) {
-    const int u = sub + kSub * ui;
-    if (u >= units) break;
-    uint32_t w[32];
-    tmem_ld16(t_addr + u * 16, w);
-    if (MODE == ENC && a.nl == 2) {
-      uint32_t w1[32];
-      tmem_ld16(t_addr + a.NCo + u * 16, w1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) w[j] += w1[j] << 8;
-    } else {
-      tmem_ld_wait();
-    }
-    mark(3 + 3 * ui);   // accumulators of this unit are in registers
-    const int kk = c * a.NCo + u * 16;
-    if (!row_ok || kk >= a.P) continue;
-    if (MODE == ENC || MODE == DEC1) {
-      // two coefficients per 32-bit word, reduced mod q in both lanes at once
-      uint32_t pk[8];
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) pk[jj] = __byte_perm(w[2 * jj], w[2 * jj + 1], 0x5410);
-      if (hi) {             // -hi mod q = ((q-1-x) + 1) mod q, no carry between lanes
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) pk[jj] = ((~pk[jj] & Q2) + 0x00010001u) & Q2;
-      } else if (MODE == ENC) {
-        const uint32_t mw[4] = {mm[ui].x, mm[ui].y, mm[ui].z, mm[ui].w};
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const uint32_t mp = __byte_perm(mw[jj >> 1], 0u, (jj & 1) ? 0x4342 : 0x4140);   // bytes -> lanes
-          pk[jj] = ((pk[jj] & Q2) + mp) & Q2;
-        }
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) pk[jj] &= Q2;
-      }
-      const uint4 p0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      const uint4 p1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      mark(4 + 3 * ui);   // math done
-      uint16_t *d0 = hi ? a.o16_hi : a.o16_cyc;
-      if (d0) {
-        reinterpret_cast<uint4 *>(d0 + rbase + kk)[0] = p0;
-        reinterpret_cast<uint4 *>(d0 + rbase + kk)[1] = p1;
-      }
-      if (!hi && a.o16_cyc2) {
-        reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[0] = p0;
-        reinterpret_cast<uint4 *>(a.o16_cyc2 + rbase + kk)[1] = p1;
-      }
-      if (MODE == DEC1 && !hi && a.o8_cyc) {
-        uint32_t bq[4];
-#pragma unroll
-        for (int wd = 0; wd < 4; ++wd) {
-          uint32_t bb[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t x = w[4 * wd + j] & a.qmask;
-            const uint32_t y = x + ((x + lift_add) >> logq);          // index.js:117
-            bb[j] = y - 3u * __umulhi(y, 0x55555556u);
-          }
-          bq[wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
-        }
-        *reinterpret_cast<uint4 *>(a.o8_cyc + rbase + kk) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
-      }
-    } else {   // DEC2: mod 3 (hi: -x mod 3 = 2x mod 3)
-      uint32_t bq[4];
-#pragma unroll
-      for (int wd = 0; wd < 4; ++wd) {
-        uint32_t bb[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t y = hi ? 2u * w[4 * wd + j] : w[4 * wd + j];
-          bb[j] = y - 3u * __umulhi(y, 0x55555556u);
-        }
-        bq[wd] = __byte_perm(__byte_perm(bb[0], bb[1], 0x0040), __byte_perm(bb[2], bb[3], 0x0040), 0x5410);
-      }
-      const uint4 pk4 = make_uint4(bq[0], bq[1], bq[2], bq[3]);
-      uint8_t *d0 = hi ? a.o8_hi : a.o8_cyc;
-      if (d0) *reinterpret_cast<uint4 *>(d0 + rbase + kk) = pk4;
-      if (!hi && a.o8_cyc2) *reinterpret_cast<uint4 *>(a.o8_cyc2 + rbase + kk) = pk4;
-    }
-  }
-}
-
-// ---- the kernel --------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
-k_umma_product(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)kStages * kStageBytes);
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then the TMEM base address
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
-  const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
-  const uint32_t smem_base = smem_u32(smem);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), MODE == DEC1 ? 1 + 8 : 1);   // TMA expect_tx arrival (+ 8 transform warps)
-      mbar_init(empty_bar(s), 1);                         // tcgen05.commit
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);        // tcgen05.commit
-      mbar_init(tempty_bar(b), MODE == DEC1 ? 8 : 16);   // one arrival per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int parts = a.with_hi ? 2 : 1;          // part 0 = hi (when present), last part = cyc
-
-  if (warp == 0) {
-    // ===================== TMA producer: B slices (and A slices unless DEC1) =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      const uint32_t bytes = (uint32_t)a.NC * kAtomK + (MODE == DEC1 ? 0u : (uint32_t)kABytes);
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        for (int part = 0; part < parts; ++part) {
-          const int hi = a.with_hi && part == 0;
-          for (int c = 0; c < a.nchunks; ++c) {
-            const int a0 = first_atom(a, hi, c);
-            const int row0 = (hi * a.nchunks + c) * a.NC;
-            for (int at = a0; at < a.atoms; ++at) {
-              for (int lk = 0; lk < a.kl; ++lk, ++it) {
-                const int s = it % kStages;
-                mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(full_bar(s), bytes);
-                if (MODE != DEC1)
-                  tma_load_2d(smem_base + s * kStageBytes, &tmapA, at * kAtomK, tile * kTileRows, full_bar(s));
-                tma_load_2d(smem_base + s * kStageBytes + kABytes, &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, full_bar(s));
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(0, MODE == DEC1 ? 1 : 0, a.NC);
-      uint32_t it = 0, cc = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        for (int part = 0; part < parts; ++part) {
-          const int hi = a.with_hi && part == 0;
-          for (int c = 0; c < a.nchunks; ++c, ++cc) {
-            const int a0 = first_atom(a, hi, c);
-            const int buf = cc & 1;
-            mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * kAccCols;
-            uint32_t first = 1;
-            for (int at = a0; at < a.atoms; ++at) {
-              for (int lk = 0; lk < a.kl; ++lk, ++it) {
-                const int s = it % kStages;
-                mbar_wait(full_bar(s), (it / kStages) & 1);
-                tc_fence_after();
-                const uint64_t da = make_smem_desc(smem_base + s * kStageBytes);
-                const uint64_t db = make_smem_desc(smem_base + s * kStageBytes + kABytes);
-#pragma unroll
-                for (int k = 0; k < kAtomK / 32; ++k) {
-                  umma_i8(d_tmem, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);   // +32 bytes of K per step
-                  first = 0;
-                }
-                umma_commit(empty_bar(s));
-              }
-            }
-            umma_commit(tfull_bar(buf));
-          }
-        }
-      }
-    }
-  } else if (MODE == DEC1 && warp < kEpilogueWarp0) {
-    // ===================== DEC1 transform: e (uint16, global) -> byte-limb A slices (swizzled smem) =====
-    {
-      const int t = threadIdx.x - kBuilderWarp0 * 32;      // 0..255
-      const int chunk = t & 7;                             // 16-byte chunk of the 128-byte A row
-      const int r0 = t >> 3;                               // rows r0, r0+32, r0+64, r0+96
-      const uint16_t *src = reinterpret_cast<const uint16_t *>(a.a_src);
-      auto load_atom = [&](const AtomIter &w, uint4 (&raw)[8]) {
-        const int col = w.at * kAtomK + chunk * 16;        // first coefficient of this thread's chunk
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const size_t row = (size_t)w.tile * kTileRows + r0 + 32 * j;
-          const bool ok = w.valid && row < a.B && col < a.P;
-          const uint4 *ptr = reinterpret_cast<const uint4 *>(src + (ok ? row * (size_t)a.P + col : 0));
-          uint4 x0 = __ldg(ptr), x1 = __ldg(ptr + 1);
-          if (!ok) x0 = x1 = make_uint4(0, 0, 0, 0);
-          raw[2 * j] = x0;
-          raw[2 * j + 1] = x1;
-        }
-      };
-      AtomIter cur, nxt;
-      cur.start(a);
-      uint4 raw[8], raw_next[8];
-      if (cur.valid) load_atom(cur, raw);
-      uint32_t it = 0;
-      while (cur.valid) {
-        nxt = cur;
-        nxt.next(a);
-        load_atom(nxt, raw_next);                           // prefetch one atom ahead (zeros when !valid)
-        const int s0 = it % kStages, s1 = (it + 1) % kStages;
-        mbar_wait(empty_bar(s0), ((it / kStages) & 1) ^ 1);
-        if (a.kl == 2) mbar_wait(empty_bar(s1), (((it + 1) / kStages) & 1) ^ 1);
-        uint8_t *dst0 = smem + (size_t)s0 * kStageBytes;
-        uint8_t *dst1 = smem + (size_t)s1 * kStageBytes;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r_in = r0 + 32 * j;
-          const int off = (r_in >> 3) * 1024 + (r_in & 7) * 128 + ((chunk ^ (r_in & 7)) << 4);
-          const uint4 w0 = raw[2 * j], w1 = raw[2 * j + 1];
-          uint4 lo;
-          lo.x = __byte_perm(w0.x, w0.y, 0x6420);
-          lo.y = __byte_perm(w0.z, w0.w, 0x6420);
-          lo.z = __byte_perm(w1.x, w1.y, 0x6420);
-          lo.w = __byte_perm(w1.z, w1.w, 0x6420);
-          *reinterpret_cast<uint4 *>(dst0 + off) = lo;
-          if (a.kl == 2) {                                  // (e >> 8) << 2 in the low byte of each 16-bit field
-            uint4 hi4;
-            hi4.x = __byte_perm((w0.x >> 6) & 0x00FC00FCu, (w0.y >> 6) & 0x00FC00FCu, 0x6420);
-            hi4.y = __byte_perm((w0.z >> 6) & 0x00FC00FCu, (w0.w >> 6) & 0x00FC00FCu, 0x6420);
-            hi4.z = __byte_perm((w1.x >> 6) & 0x00FC00FCu, (w1.y >> 6) & 0x00FC00FCu, 0x6420);
-            hi4.w = __byte_perm((w1.z >> 6) & 0x00FC00FCu, (w1.w >> 6) & 0x00FC00FCu, 0x6420);
-            *reinterpret_cast<uint4 *>(dst1 + off) = hi4;
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(full_bar(s0));
-          if (a.kl == 2) mbar_arrive(full_bar(s1));
-        }
-        it += a.kl;
-        cur = nxt;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) raw[j] = raw_next[j];
-      }
-    }
-  } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    // DEC1: warps 10-17 (2 per TMEM lane quadrant); ENC / DEC2: warps 2-17 (4 per quadrant).
-    constexpr int kSub = MODE == DEC1 ? 2 : 4;                 // epilogue warps per quadrant
-    const int ew = warp - (MODE == DEC1 ? kEpilogueWarp0 : kBuilderWarp0);
-    const int quad = warp & 3;                     // TMEM lanes [32*quad, 32*quad+32) are this warp's
-    const int sub = ew >> 2;                       // this warp's units: sub, sub + kSub, ...
-    uint32_t cc = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const size_t row = (size_t)tile * kTileRows + quad * 32 + lane;
-      const bool row_ok = row < a.B;
-      const size_t rbase = row * (size_t)a.P;
-      for (int part = 0; part < parts; ++part) {
-        const int hi = a.with_hi && part == 0;
-        for (int c = 0; c < a.nchunks; ++c, ++cc) {
-          const int buf = cc & 1;
-          const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kAccCols;
-          epilogue_chunk<MODE, kSub>(a, hi, c, sub, row_ok, rbase, t_addr,
-                                     [&] { mbar_wait(tfull_bar(buf), (cc >> 1) & 1); });
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(buf));
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
-  }
 }
 
 #include "umma_pair.cuh"
 
 // ---- key matrix ---------------------------------------------------------------------------------
-// Mat[row][kb]: row = ((part * nchunks + c) * nl + ln) * NCo + j  (part 0 = cyc, 1 = hi; output k = c*NCo + j),
-//               kb  = lk * Kp + i.
-__global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, int NCo, int nchunks, const void *poly,
-                               uint8_t *mat) {
+// Mat[row][kb]: row = part * (nl * T) + nl * col0[c] + ln * w_c + j   (part 0 = cyc, 1 = hi; output k = col0[c] + j,
+//               w_c = width of chunk c, T = col0[nchunks] = covered columns),   kb = lk * Kp + i.
+struct ChunkTable {
+  int nchunks;
+  int col0[kMaxChunks + 1];
+};
+
+__global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, const ChunkTable ct, const void *poly, uint8_t *mat) {
   const int klen = kl * Kp;
-  const size_t total = (size_t)2 * nchunks * nl * NCo * klen;
+  const int T = ct.col0[ct.nchunks];
+  const size_t rows_total = (size_t)2 * nl * T;
+  const size_t total = rows_total * klen;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int kb = (int)(idx % klen);
-    int row = (int)(idx / klen);
-    const int j = row % NCo; row /= NCo;
-    const int ln = row % nl; row /= nl;
-    const int c = row % nchunks;
-    const int part = row / nchunks;
-    const int k = c * NCo + j;
+    const int row = (int)(idx / klen);
+    const int part = row / (nl * T);
+    const int rin = row % (nl * T);               // nl * col0[c] + ln * w_c + j
+    int c = 0;
+    while (c + 1 < ct.nchunks && rin >= nl * ct.col0[c + 1]) ++c;
+    const int w = ct.col0[c + 1] - ct.col0[c];
+    const int off = rin - nl * ct.col0[c];
+    const int ln = off / w, j = off % w;
+    const int k = ct.col0[c] + j;
     const int lk = kb / Kp, i = kb % Kp;
     int coef = 0;
     bool nz = k < N && i < N;
@@ -562,9 +195,8 @@ __global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, int NCo,
     else if (mode == DEC1) out = (uint8_t)(int8_t)(lk == 0 ? coef : coef * 64);
     else out = (uint8_t)coef;
     // tile-major storage: for each 128-byte K block all rows are contiguous (128-byte pitch), so that the box
-    // of one pipeline slice (NC or NC/2 rows x 128 B) is one contiguous run of global memory
-    const size_t rows_total = (size_t)2 * nchunks * nl * NCo;
-    mat[((size_t)(kb / kAtomK) * rows_total + (size_t)(idx / klen)) * kAtomK + (kb % kAtomK)] = out;
+    // of one pipeline slice (half a chunk's rows x 128 B) is one contiguous run of global memory
+    mat[((size_t)(kb / kAtomK) * rows_total + (size_t)row) * kAtomK + (kb % kAtomK)] = out;
   }
 }
 
@@ -584,23 +216,29 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Chunk table of one product.  g = the epilogue's column granularity (every warp of a TMEM lane quadrant owns a whole
+// number of store passes per chunk): ENC 64 (two-unit passes, two warps per quadrant and group), 32 with one-unit
+// passes (N > 512); DEC1 32; DEC2 128.  The covered columns T = N rounded up to g are split into
+// ceil(T / max_out) chunks whose widths differ by at most g (wider chunks first): at most two distinct widths.
+// max_out: a 256-column accumulator holds 256 / nl outputs; ENC is capped at 128 so that a chunk's message bytes are
+// one 128-byte TMA atom per row.
 void geometry(const ntru_ctx *ctx, int mode, int kl, int nl, KeyMatrix &km) {
   const int N = ctx->N;
   km.limbs = kl;
   km.nlimbs = nl;
-  // output coefficients per chunk: a 256-column accumulator holds 256 / nl; ENC is capped at 128 so that a
-  // chunk's message bytes are exactly one 128-byte TMA atom per row
-  const int max_out = mode == ENC ? 128 : 256 / nl;
-  km.nchunks = (N + max_out - 1) / max_out;
-  const int per = (N + km.nchunks - 1) / km.nchunks;
-  // the CTA-pair kernel's epilogue stages whole passes of 32 (ENC, DEC1) or 64 (DEC2) coefficients per warp:
-  // every warp of a TMEM lane quadrant must own a whole number of passes of each chunk
-  const int round = mode == ENC ? 128 : (mode == DEC1 ? 64 : 256);
-  km.out_cols = ((per + round - 1) / round) * round;
-  if (km.out_cols > max_out) km.out_cols = max_out;
-  km.chunk_cols = km.out_cols * nl;
   const int Kp = ((N + kAtomK - 1) / kAtomK) * kAtomK;
   km.klen = kl * Kp;
+  const int max_out = mode == ENC ? 128 : 256 / nl;
+  const bool pu1 = mode == ENC && Kp / kAtomK >= 5;          // launch_product's choice of the one-unit ENC instantiation
+  const int g = mode == ENC ? (pu1 ? 32 : 64) : (mode == DEC1 ? 32 : 128);
+  const int T = ((N + g - 1) / g) * g;
+  km.nchunks = (T + max_out - 1) / max_out;
+  const int base = (T / km.nchunks / g) * g;
+  const int wide = (T - base * km.nchunks) / g;              // this many chunks are g wider
+  km.col0[0] = 0;
+  for (int c = 0; c < km.nchunks; ++c) km.col0[c + 1] = km.col0[c] + base + (c < wide ? g : 0);
+  km.w[0] = km.col0[1] - km.col0[0];
+  km.w[1] = km.col0[km.nchunks] - km.col0[km.nchunks - 1];
 }
 
 int encode_2d_ex(ntru_ctx *ctx, void *out, void *base, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t stride_bytes,
@@ -641,21 +279,25 @@ int encode_2d(ntru_ctx *ctx, void *out, void *base, uint64_t inner, uint64_t row
 
 int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyMatrix &km) {
   geometry(ctx, mode, kl, nl, km);
-  const int rows = 2 * km.nchunks * km.chunk_cols;
+  const int T = km.col0[km.nchunks];
+  const int rows = 2 * nl * T;
   const int Kp = km.klen / kl;
   const size_t bytes = (size_t)rows * km.klen;
   NTRU_CUDA(ctx, km.mat.reserve(bytes));
+  ChunkTable ct;
+  ct.nchunks = km.nchunks;
+  for (int c = 0; c <= kMaxChunks; ++c) ct.col0[c] = c <= km.nchunks ? km.col0[c] : 0;
   {
     LaunchTimer timer(ctx, NTRU_K_OTHER);
-    k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, kl, nl, km.out_cols, km.nchunks, poly,
-                                                               (uint8_t *)km.mat.ptr);
+    k_build_keymat<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mode, ctx->N, Kp, kl, nl, ct, poly, (uint8_t *)km.mat.ptr);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
+  // one tensor map per distinct chunk width: the box is the half of a chunk's B rows that one CTA of the pair loads
   const uint64_t tiled_rows = (uint64_t)rows * (km.klen / kAtomK);
-  int rc = encode_2d(ctx, km.tmap, km.mat.ptr, kAtomK, tiled_rows, kAtomK, kAtomK, (uint32_t)km.chunk_cols);
-  if (rc) return rc;
-  rc = encode_2d(ctx, km.tmap_half, km.mat.ptr, kAtomK, tiled_rows, kAtomK, kAtomK, (uint32_t)km.chunk_cols / 2);
-  if (rc) return rc;
+  for (int i = 0; i < 2; ++i) {
+    int rc = encode_2d(ctx, km.tmap_half[i], km.mat.ptr, kAtomK, tiled_rows, kAtomK, kAtomK, (uint32_t)(nl * km.w[i]) / 2);
+    if (rc) return rc;
+  }
   NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   km.ready = true;
   return NTRU_OK;
@@ -664,14 +306,15 @@ int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyM
 template <int MODE>
 int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *a_bytes) {
   if (!(ctx->umma_attr_set & (1 << MODE))) {      // per context: function attributes are per device
-    NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_product<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
     ctx->umma_attr_set |= 1 << MODE;
   }
   a.N = ctx->N; a.P = ctx->P; a.kl = km.limbs; a.nl = km.nlimbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
-  a.NC = km.chunk_cols; a.NCo = km.out_cols; a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
-  a.mat_rows = 2 * a.nchunks * a.NC;
-  a.ntiles = (int)((a.B + kTileRows - 1) / kTileRows);
+  a.k_last = (ctx->N - (a.atoms - 1) * kAtomK + 31) / 32;
+  a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
+  for (int c = 0; c <= kMaxChunks; ++c) a.col0[c] = c <= km.nchunks ? km.col0[c] : km.col0[km.nchunks];
+  a.w0 = km.w[0];
+  a.mat_rows = 2 * a.nl * a.col0[a.nchunks];
   a.npairs = (int)((a.B + 2 * kTileRows - 1) / (2 * kTileRows));
   a.nS = 2;
   a.nM = MODE == ENC ? 2 : 0;
@@ -679,11 +322,9 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   // ENC above N = 512: k_umma_pair<ENC, 0, 1> stages one unit per TMA store (one staging slot) and reads the message
   // bytes from global memory (no message slots).  The three slots go to the B ring, and the A operand stays resident up
   // to N = 1024: with 4 stages the ring covered ~2000 cycles of TMA latency at 900 cycles per slice (clock trace,
-  // NTRU_DEBUG_NOB timing), and streaming A doubled the L2 -> SM traffic at N = 821.
-  bool pu1 = MODE == ENC && ctx->tensor_variant == 0 && a.atoms >= 5;
-#ifdef NTRU_TRACE   // timing experiments exist in trace builds only: the shipped library reads no environment variable
-  if (getenv("NTRU_DEBUG_NO_PU1")) pu1 = false;
-#endif
+  // NTRU_DEBUG_NOB timing), and streaming A doubled the L2 -> SM traffic at N = 821.  (geometry() makes the same choice:
+  // the chunk widths of ENC are multiples of 32 only with one-unit passes.)
+  const bool pu1 = MODE == ENC && a.atoms >= 5;
   if (pu1) { a.nS = 1; a.nM = 0; }
   const int avail = kPairSlots - a.nS - a.nM;
   if (a_slots + 4 <= avail) {
@@ -692,14 +333,14 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     a.a_resident = 0; a.nA = 6; a.nB = avail - 6;
   }
   // streaming DEC1: the raw e atoms (two A slots each) are prefetched by TMA, four atoms deep
-  a.a_tma = MODE == DEC1 && !a.a_resident && a.kl == 2 && ctx->tensor_variant == 0 && avail >= 11;
+  a.a_tma = MODE == DEC1 && !a.a_resident && a.kl == 2 && avail >= 11;
   if (a.a_tma) { a.nA = 8; a.nB = avail - 8; }
   // resident A slots are read by both MMA issuer warps (alternating chunks) whenever a tile has >= 2 chunks
   a.two_issuers = 0;   // a second issuer warp was tried: the B ring is too short for two chunks in flight
   a.a_rel = (a.a_resident && a.two_issuers) ? 2 : 1;
-  CUtensorMap tmB, tmA, tmM, tmO[3];
-  const bool pair = ctx->tensor_variant == 0;
-  memcpy(&tmB, pair ? km.tmap_half : km.tmap, sizeof tmB);
+  CUtensorMap tmB, tmB2, tmA, tmM, tmO[3];
+  memcpy(&tmB, km.tmap_half[0], sizeof tmB);
+  memcpy(&tmB2, km.tmap_half[1], sizeof tmB2);
   memset(&tmA, 0, sizeof tmA);
   memset(&tmM, 0, sizeof tmM);
   memset(tmO, 0, sizeof tmO);
@@ -714,11 +355,11 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     rc = encode_2d_ex(ctx, &tmA, const_cast<void *>(a.a_src), 2, P, (uint64_t)a.B, P * 2, kAtomK, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  if (pair) {
-    if (MODE == ENC) {
-      rc = encode_2d(ctx, &tmM, const_cast<uint8_t *>(a.m), N, (uint64_t)a.B, P, kAtomK, kTileRows);
-      if (rc) return rc;
-    }
+  if (MODE == ENC && !pu1) {
+    rc = encode_2d(ctx, &tmM, const_cast<uint8_t *>(a.m), N, (uint64_t)a.B, P, kAtomK, kTileRows);
+    if (rc) return rc;
+  }
+  {
     // outputs: per-warp tiles of 32 rows x 64 bytes (SWIZZLE_64B); DEC1's b is 32 rows x 32 bytes, unswizzled
     void *optr[3];
     int oelem[3], obox[3];
@@ -741,16 +382,16 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
       rc = encode_2d_ex(ctx, &tmO[i], optr[i], oelem[i], P, (uint64_t)a.B, P * oelem[i], (uint32_t)obox[i], 32, oswz[i]);
       if (rc) return rc;
     }
-#ifdef NTRU_TRACE
-    if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // timing experiment only: results are not written
+#ifdef NTRU_TRACE   // timing experiments exist in trace builds only: the shipped library reads no environment variable
+    if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // results are not written
     if (getenv("NTRU_DEBUG_NOB")) a.debug_flags |= 1;
 #endif
   }
-  // The accumulator chunks cover nchunks * NCo >= N output columns; when N is a multiple of the chunk width (N = 512,
-  // 640, 768, 1024) that stops short of the row pitch, and the pad columns the kernel never sees are zeroed here so that
-  // every output row keeps the contract of include/ntru_b200.h.
+  // The accumulator chunks cover col0[nchunks] >= N output columns (N rounded up to the epilogue's granularity); where
+  // that stops short of the row pitch (N a multiple of the granularity: N = 512, 640, 768, 1024, ...) the pad columns
+  // the kernel never sees are zeroed here so that every output row keeps the contract of include/ntru_b200.h.
   {
-    const size_t cov = (size_t)a.nchunks * a.NCo;
+    const size_t cov = (size_t)a.col0[a.nchunks];
     if (cov < P) {
       void *o16[3] = {a.o16_cyc, a.o16_cyc2, a.o16_hi};
       void *o8[3] = {MODE == DEC2 ? a.o8_cyc : nullptr, a.o8_cyc2, a.o8_hi};
@@ -762,40 +403,35 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   }
   {
     LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
-    if (pair) {
-      const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
+    const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
 #ifdef NTRU_TRACE
-      const int dbg = getenv("NTRU_DEBUG_EPI") ? atoi(getenv("NTRU_DEBUG_EPI")) : 0;
+    const int dbg = getenv("NTRU_DEBUG_EPI") ? atoi(getenv("NTRU_DEBUG_EPI")) : 0;
 #define NTRU_DBG_LAUNCH(D)                                                                                                  \
   case D:                                                                                                                  \
     cudaFuncSetAttribute(k_umma_pair<MODE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);          \
-    k_umma_pair<MODE, D><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]); \
+    k_umma_pair<MODE, D><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmB2, tmA, tmM, tmO[0], tmO[1], tmO[2]); \
     break;
-      switch (dbg) {
-        NTRU_DBG_LAUNCH(1) NTRU_DBG_LAUNCH(2) NTRU_DBG_LAUNCH(4) NTRU_DBG_LAUNCH(8) NTRU_DBG_LAUNCH(12) NTRU_DBG_LAUNCH(16)
-        default:
-          if (pu1) {
-            cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
-            k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
-          } else {
-            k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
-          }
-      }
-#else
-      if (pu1) {
-        if (!(ctx->umma_attr_set & 8)) {
-          NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-          ctx->umma_attr_set |= 8;
+    switch (pu1 ? 0 : dbg) {
+      NTRU_DBG_LAUNCH(1) NTRU_DBG_LAUNCH(2) NTRU_DBG_LAUNCH(4) NTRU_DBG_LAUNCH(8) NTRU_DBG_LAUNCH(12) NTRU_DBG_LAUNCH(16)
+      default:
+        if (pu1) {
+          cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
+          k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmB2, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+        } else {
+          k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmB2, tmA, tmM, tmO[0], tmO[1], tmO[2]);
         }
-        k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
-      } else {
-        k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmA, tmM, tmO[0], tmO[1], tmO[2]);
-      }
-#endif
-    } else {
-      const int grid = a.ntiles < ctx->sm_count ? a.ntiles : ctx->sm_count;
-      k_umma_product<MODE><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a, tmB, tmA);
     }
+#else
+    if (pu1) {
+      if (!(ctx->umma_attr_set & 8)) {
+        NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
+        ctx->umma_attr_set |= 8;
+      }
+      k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmB2, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+    } else {
+      k_umma_pair<MODE><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmB2, tmA, tmM, tmO[0], tmO[1], tmO[2]);
+    }
+#endif
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;
@@ -818,7 +454,7 @@ int umma_init(ntru_ctx *ctx) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return NTRU_OK;
   if (prop.major != 10) return NTRU_OK;                       // tcgen05 needs sm_100a
-  if ((size_t)prop.sharedMemPerBlockOptin < kSmemBytes || (size_t)prop.sharedMemPerBlockOptin < kPairSmemBytes) return NTRU_OK;
+  if ((size_t)prop.sharedMemPerBlockOptin < kPairSmemBytes) return NTRU_OK;
   if (!get_encode_fn()) return NTRU_OK;
   ctx->tensor_ok = true;
   return NTRU_OK;

@@ -138,7 +138,8 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signe
 // two): at 768 < N <= 896 that slot is what lets the A operand stay resident beside a 4-stage B ring (launch_product).
 template <int MODE, int DBG = 0, int PU = (MODE == 2 ? 4 : 2)>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
-k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA,
+k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapB2,
+            const __grid_constant__ CUtensorMap tmapA,
             const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapO0,
             const __grid_constant__ CUtensorMap tmapO1, const __grid_constant__ CUtensorMap tmapO2) {
   extern __shared__ uint8_t smem_raw[];
@@ -207,9 +208,8 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     // ~900 cycles per slice, so the ring never filled.  It waits on nothing but the ring itself: A-operand and
     // message loads depend on epilogue progress and live in their own warp (below), otherwise a late epilogue
     // delays the B loads of the next chunk and MMA, epilogue and loads run one after the other (clock trace).
-    const int half_rows = a.NC >> 1;
-    const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK;
     const uint32_t lead_b_full = lead(b_full(0));
+    const int part_rows = a.mat_rows >> 1;                 // key-matrix rows of one part (cyc / hi)
     const int parts = a.with_hi ? 2 : 1;
     uint32_t sb = 0, b_par = 0;
     if (lane == 0) { TRACE(3, 10, 0); TRACE_NS(3, 11, 0); }
@@ -218,7 +218,11 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         const int hi = part == 1;
         for (int c = 0; c < a.nchunks; ++c) {
           const int a0 = first_atom(a, hi, c);
-          const int row0 = (hi * a.nchunks + c) * a.NC + (int)rank * half_rows;
+          const int wc = a.col0[c + 1] - a.col0[c];
+          const int half_rows = (a.nl * wc) >> 1;            // B rows of this chunk that this CTA loads
+          const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK;
+          const CUtensorMap *bmap = wc == a.w0 ? &tmapB : &tmapB2;   // box rows = half_rows
+          const int row0 = hi * part_rows + a.nl * a.col0[c] + (int)rank * half_rows;
           for (int at = a0; at < a.atoms; ++at) {
             for (int lk = 0; lk < a.kl; ++lk) {
               mbar_wait(b_empty(sb), b_par ^ 1);
@@ -231,7 +235,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 {
                   if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
                   else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                  tma_load_2d_pair(b_slot(sb), &tmapB, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
+                  tma_load_2d_pair(b_slot(sb), bmap, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
                 }
               }
               __syncwarp();
@@ -301,7 +305,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               mbar_wait(m_empty(ms), ((mc >> 1) & 1) ^ 1);
               if (elect_one()) {
                 mbar_arrive_expect_tx(m_full(ms), kABytes);
-                tma_load_2d(m_slot(ms), &tmapM, c * a.NCo, a_row, m_full(ms));
+                tma_load_2d(m_slot(ms), &tmapM, a.col0[c], a_row, m_full(ms));
               }
               __syncwarp();
               ++mc;
@@ -325,7 +329,6 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       // (atom, K limb) in nested loops with run-time bounds and cost ~95 SASS instructions per slice on a single
       // warp (~600 cycles against the 512 cycles of tensor work a slice holds; clock trace, ncu source counters).
       // Slices of a chunk use consecutive resident A slots: sa = (first atom) * kl + i.
-      const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.NC);
       const uint64_t desc_hi = make_smem_desc(0) & ~0x3FFFull;             // everything but the start address
       const uint32_t a_lo0 = smem_base >> 4, b_lo0 = (smem_base + a.nA * kSlotBytes) >> 4;   // 16-byte units
       const int nct = (a.with_hi ? 2 : 1) * a.nchunks;                     // chunks per tile
@@ -340,6 +343,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           const int hi = j >= a.nchunks;
           const int a0 = first_atom(a, hi, hi ? j - a.nchunks : j);
           const uint32_t nsl = (uint32_t)((a.atoms - a0) * a.kl);            // slices of this chunk
+          const int cj = hi ? j - a.nchunks : j;
+          const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.nl * (a.col0[cj + 1] - a.col0[cj]));
+          const uint32_t klast = (uint32_t)a.k_last, kl_u = (uint32_t)a.kl;
           // resident A slot sa is read again later in the tile iff the next chunk reads it: chunks read ever fewer
           // atoms (cyclic chunks read all, hi chunk c reads atoms >= a0(c), a0 non-decreasing)
           const int jn = j + 1;
@@ -365,11 +371,13 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             tc_fence_after();
             const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
             const uint64_t db = desc_hi | (uint64_t)(b_lo0 + sb * (kSlotBytes >> 4));
+            // the slices of the last K atom (one per K limb) hold coefficients below N only in their first k_last 32-byte steps
+            const uint32_t nk = (nsl - i <= kl_u) ? klast : 4u;
             if (elect_one()) {
               umma_i8_pair(d_tmem, da, db, idesc, accumulate);
-              umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
-              umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
-              umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+              if (nk > 1) umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
+              if (nk > 2) umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
+              if (nk > 3) umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
               umma_commit_pair(bempty0 + 8u * sb);
               if (sa < rel_lim) umma_commit_pair(aempty0 + 8u * sa);
               if (i == nsl - 1) umma_commit_pair(tfull);
@@ -560,8 +568,6 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const uint32_t grp = (uint32_t)(ew >> 2) & 1u;
     const int sub = ew >> 3;
     const int parts = a.with_hi ? 2 : 1;
-    const int upw = (a.NCo >> 4) / kSub;                           // units per warp per chunk
-    const int npass = upw / kPassUnits;
     const uint32_t Q2 = a.qmask | (a.qmask << 16);
     const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;   // x > q/2  <=>  bit log2(q) of x + q/2 - 1
     const int logq = 31 - __clz(a.q);
@@ -585,13 +591,16 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           const uint32_t ms = mc & 1, m_par = (mc >> 1) & 1;
           if (MODE == ENC && !hi) ++mc;
           if ((cc & 1u) != grp) continue;
+          const int col0c = a.col0[c], wc = a.col0[c + 1] - col0c;
+          const int upw = (wc >> 4) / kSub;                        // units per warp in this chunk
+          const int npass = upw / kPassUnits;
           if (lane == 0 && ew == 0) TRACE(2, 0, cc);
           uint4 mg[4];                                            // kMsgGlobal: this lane's message bytes of the chunk
           if (kMsgGlobal && !hi) {                                // (in flight while the accumulators are still being computed)
             const size_t grow = (size_t)(out_row + lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int col = c * a.NCo + (sub * upw + j) * 16;
+              const int col = col0c + (sub * upw + j) * 16;
               mg[j] = (j < upw && grow < a.B && col < a.N) ? __ldg(reinterpret_cast<const uint4 *>(a.m + grow * (size_t)a.P + col))
                                                           : make_uint4(0, 0, 0, 0);
             }   // (four independent loads, nothing waits for them here: the unit that straddles N is masked at its use)
@@ -612,7 +621,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           }
           // passes of this warp that hold at least one column below the pitch (the last chunk of a tile is padding
           // beyond it: 5 of 8 units at N = 167, 677, 4 of 8 at N = 821); the others would be clipped by the TMA store
-          int npe = (a.P - (c * a.NCo + sub * upw * 16) + kPassUnits * 16 - 1) / (kPassUnits * 16);
+          int npe = (a.P - (col0c + sub * upw * 16) + kPassUnits * 16 - 1) / (kPassUnits * 16);
           npe = npe < 0 ? 0 : (npe > npass ? npass : npe);
           if (npe == 0) {                                           // nothing to drain: hand the buffers back (in phase)
             tc_fence_before();
@@ -632,7 +641,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             if (kMsgGlobal) {
               if (!hi) {
                 mm[0] = ps == 0 ? mg[0] : (ps == 1 ? mg[1] : (ps == 2 ? mg[2] : mg[3]));   // PU == 1: pass ps = unit ps
-                const int keep = a.N - (c * a.NCo + u0 * 16);   // < 16 for the unit that straddles N: the pad bytes of the
+                const int keep = a.N - (col0c + u0 * 16);   // < 16 for the unit that straddles N: the pad bytes of the
                 if (keep < 16) {                                // caller's row do not count (a TMA tile reads them as zero)
                   uint32_t w[4] = {mm[0].x, mm[0].y, mm[0].z, mm[0].w};
 #pragma unroll
@@ -660,7 +669,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                   continue;
                 }
                 tmem_ld16(t_addr + (u0 + j) * 16, acc[j]);
-                if (MODE == ENC && a.nl == 2) tmem_ld16(t_addr + a.NCo + (u0 + j) * 16, acc1[j]);
+                if (MODE == ENC && a.nl == 2) tmem_ld16(t_addr + wc + (u0 + j) * 16, acc1[j]);
               }
               if (!(DBG & 4)) tmem_ld_wait();
               if (lane == 0 && ew == 0) TRACE(2, 4, cc);
@@ -772,7 +781,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             if (lane == 0 && ew == 0) TRACE(2, 7, cc);
             if (DBG & 16) continue;
             if (lane == 0) {
-              const int col = c * a.NCo + u0 * 16;
+              const int col = col0c + u0 * 16;
               if (hi) {
                 if (a.out_mask & 4) tma_store_2d(&tmapO2, stage, col, out_row);
               } else {

@@ -28,9 +28,6 @@ def setup(cfg):
     eng = nb.Engine(N, p, q, 0)
     eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    if os.environ.get("VARIANT"):                     # tcgen05 kernel variant (NTRU_OPT_TENSOR_VARIANT)
-        from ntru_circom_b200 import _lib
-        eng.set_option(_lib.NTRU_OPT_TENSOR_VARIANT, int(os.environ["VARIANT"]))
     return g, eng, N, q, dr
 
 
@@ -51,7 +48,7 @@ def same_key(cfg, B):
         eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2)
     kt = {k: round(v[0] / v[1], 4) for k, v in eng.timing_read().items() if v[1]}
     eng.set_timing(False)
-    print(json.dumps({"config": cfg, "mode": "same-key tcgen05", "variant": int(os.environ.get("VARIANT", "0")), "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
+    print(json.dumps({"config": cfg, "mode": "same-key tcgen05", "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
                       "kernel_ms": kt,
                       "ct_per_s": B / (tot * 1e-3), "GBps_14N": 14 * N * B / (tot * 1e-3) / 1e9, "frac_hbm": 14 * N * B / (tot * 1e-3) / 1e9 / HBM,
                       "int8_TOPs_10N2": (10 if q > 256 else 6) * N * N * B / (tot * 1e-3) / 1e12, "roundtrip_equals_message": ok}))

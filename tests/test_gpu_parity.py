@@ -279,7 +279,8 @@ def test_parameter_sets_outside_baseline(N, q, nb):
     eng.close()
 
 
-@pytest.mark.parametrize("N,q", [(512, 2048), (513, 2048), (640, 4096), (641, 2048), (768, 8192), (897, 2048), (1024, 8192)])
+@pytest.mark.parametrize("N,q", [(167, 128), (509, 2048), (512, 2048), (513, 2048), (545, 2048), (640, 4096), (641, 2048), (677, 2048), (701, 8192),
+                                 (768, 8192), (821, 4096), (833, 2048), (897, 2048), (1024, 8192)])
 def test_many_tiles_per_cluster_outside_baseline(N, q, nb):
     """Several 256-row tiles per CTA pair (ring phases, resident-slot reuse, the last partial tile) at the N where the
     shared-memory budget of the tcgen05 kernel changes (A slots 5 ... 8, B ring 8 ... 5, streaming DEC1): device-resident
@@ -660,33 +661,30 @@ def test_device_resident_api_and_properties_at_scale(nb, engines, golden):
 
 
 @pytest.mark.parametrize("B", [1, 127, 128, 129, 255, 256, 257, 513])
-def test_tile_boundaries_both_tensor_kernels(B, nb, engines, golden):
-    """Row counts around the 128-row CTA tile and the 256-row CTA-pair tile, with and without witness,
-    on the CTA-pair kernel (variant 0) and the single-CTA kernel (variant 1)."""
-    g, eng = golden("hps509"), engines("hps509")
-    N, q, p = 509, 2048, 3
+@pytest.mark.parametrize("cfg", ["hps509", "hps821"])
+def test_tile_boundaries_tensor_kernel(B, cfg, nb, engines, golden):
+    """Row counts around the 128-row CTA tile and the 256-row CTA-pair tile, with and without witness, on the tcgen05
+    schedule (resident A operand at N = 509, streaming DEC1 and unequal accumulator chunks at N = 821)."""
+    g, eng = golden(cfg), engines(cfg)
+    N, q, p, dr = int(g["N"]), int(g["q"]), 3, int(g["dr"])
     rng = np.random.default_rng(B)
-    r = o.sample_ternary_rows(B, N, 169, 169, rng).astype(np.uint8)
+    r = o.sample_ternary_rows(B, N, dr, dr, rng).astype(np.uint8)
     m = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
     want_e = o.encrypt_batch(g["h"].astype(np.int64), r, m, q)
     want_d = o.decrypt_batch(g["f"].astype(np.int64), g["fp"].astype(np.int64), want_e["value"], q, p)
-    from ntru_circom_b200 import _lib
     eng.set_path(nb.PATH_TENSOR)
     try:
-        for variant in (0, 1):
-            eng.set_option(_lib.NTRU_OPT_TENSOR_VARIANT, variant)
-            for witness in (True, False):
-                enc = eng.encrypt_batch(r, m, witness=witness)
-                dec = eng.decrypt_batch(want_e["value"].astype(np.uint16), witness=witness)
-                assert np.array_equal(enc["value"], want_e["value"]), (variant, witness)
-                assert np.array_equal(dec["value"], want_d["value"]), (variant, witness)
-                if witness:
-                    for k in ENC_KEYS:
-                        assert np.array_equal(enc[k], want_e[k]), (variant, k)
-                    for k in DEC_KEYS:
-                        assert np.array_equal(dec[k], want_d[k]), (variant, k)
+        for witness in (True, False):
+            enc = eng.encrypt_batch(r, m, witness=witness)
+            dec = eng.decrypt_batch(want_e["value"].astype(np.uint16), witness=witness)
+            assert np.array_equal(enc["value"], want_e["value"]), witness
+            assert np.array_equal(dec["value"], want_d["value"]), witness
+            if witness:
+                for k in ENC_KEYS:
+                    assert np.array_equal(enc[k], want_e[k]), k
+                for k in DEC_KEYS:
+                    assert np.array_equal(dec[k], want_d[k]), k
     finally:
-        eng.set_option(_lib.NTRU_OPT_TENSOR_VARIANT, 0)
         eng.set_path(nb.PATH_AUTO)
 
 
