@@ -602,7 +602,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (CUDA events on the launch stream, inside the timed region) ----
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")))     # written by scripts/ncu_traffic.py
+        prof["int8_peak_tops"] = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"))).get("int8_peak_tops")
     except OSError:
         prof = {"bytes_per_ciphertext": {}, "int8_peak_tops": None}
     alg_bytes = {"enc_tensor": 6 * N, "dec1_tensor": 6 * N, "dec2_tensor": 2 * N, "enc_core": 6 * N, "dec_core": 8 * N,
@@ -622,7 +623,9 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GB/s"], "peak": hbm_gbs, "unit": "GB/s",
                 "frac": kernels[dom]["GB/s"] / hbm_gbs,
                 "traffic": (prof["bytes_per_ciphertext"].get(dom) or 0) * B or None,
-                "traffic_source": "ncu dram__bytes_read+write per ciphertext (profiles/r1_dram_traffic.json) x rows per launch",
+                "traffic_source": "ncu --set full at 1 000 000 rows per launch: dram__bytes_read.sum + dram__bytes_write.sum per ciphertext "
+                                  "(profiles/r2_dram_traffic.json, written by scripts/ncu_traffic.py) x rows per launch",
+                "traffic_over_algorithmic": (prof["bytes_per_ciphertext"].get(dom) or 0) / alg_bytes[dom] or None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_ciphertext": alg_bytes[dom],
                 "int8_tensor": {"achieved_TOPs": kernels[dom]["TOP/s"], "peak_TOPs": prof.get("int8_peak_tops") or 2 * bf16_tf,

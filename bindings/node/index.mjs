@@ -7,12 +7,17 @@
 import { createRequire } from 'node:module';
 const native = createRequire(import.meta.url)('./ntru_b200.node');
 
+const OPT_DR = 5;   // NTRU_OPT_DR (include/ntru_b200.h)
+
 export function accelerate(NTRUReference, ref) {
   const { trimPolynomial, expandArray, generateCustomArray } = ref;
   return class NTRU extends NTRUReference {
     #ctx = null; #pub = null; #priv = null;
     #engine() {
-      if (!this.#ctx) this.#ctx = native.create(this.N, this.p, this.q, this.device ?? 0);
+      if (!this.#ctx) {
+        this.#ctx = native.create(this.N, this.p, this.q, this.device ?? 0);
+        native.setOption(this.#ctx, OPT_DR, this.dr);   // the device draws r itself when none is injected
+      }
       return this.#ctx;
     }
     #loadPublic() {
@@ -31,16 +36,23 @@ export function accelerate(NTRUReference, ref) {
       }
       return ctx;
     }
-    // index.js:87-110; `r` is the injection seam the reference lacks
-    encryptBits(m, r = generateCustomArray(this.N, this.dr, this.dr).map(x => x === -1 ? this.p - 1 : x)) {
+    // m reduced into [0, q) like addPolynomials does (index.js:241); a byte array when every coefficient fits one,
+    // otherwise the wide (uint16) entry point -- a coefficient >= 256 must NOT wrap modulo 256
+    #message(mExp) {
+      const q = this.q;
+      const red = mExp.map(x => ((x % q) + q) % q);
+      return red.some(x => x > 255) ? Uint16Array.from(red) : Uint8Array.from(red);
+    }
+    // index.js:87-110.  Without `r` the device draws it (generateCustomArray(N, dr, dr), -1 -> p-1, index.js:89) from
+    // its entropy-keyed ChaCha20 generator; `r` is the injection seam the reference lacks.
+    encryptBits(m, r = null) {
       const ctx = this.#loadPublic();
       const mExp = expandArray(m, this.N, 0);          // RangeError when m.length > N (index.js:98)
-      const q = this.q;
-      const out = native.encryptBatch(ctx, 1, this.N, Uint8Array.from(r), Uint8Array.from(mExp, x => ((x % q) + q) % q));
+      const out = native.encryptBatch(ctx, 1, r === null ? null : Uint8Array.from(r), this.#message(mExp));
       const remainderE = Array.from(out.remainderE);
       return {
         value: trimPolynomial(remainderE),
-        inputs: { r, m: mExp, h: expandArray(this.h, this.N, 0), quotientE: Array.from(out.quotientE), remainderE },
+        inputs: { r: Array.from(out.r), m: mExp, h: expandArray(this.h, this.N, 0), quotientE: Array.from(out.quotientE), remainderE },
         params: [this.q, this.calculateNq(), this.N],
       };
     }
@@ -49,7 +61,7 @@ export function accelerate(NTRUReference, ref) {
       const ctx = this.#loadPrivate();
       const eExp = expandArray(e, this.N, 0);          // RangeError when e.length > N (index.js:126)
       const q = this.q;
-      const out = native.decryptBatch(ctx, 1, this.N, Uint16Array.from(eExp, x => ((x % q) + q) % q));
+      const out = native.decryptBatch(ctx, 1, Uint16Array.from(eExp, x => ((x % q) + q) % q));
       const remainder2 = Array.from(out.remainder2);
       return {
         value: trimPolynomial(remainder2),
@@ -68,7 +80,7 @@ export function accelerate(NTRUReference, ref) {
       if (!this.h) throw new Error('missing public key H');
       const { q, p, N } = this, nq = this.calculateNq(), np = this.calculateNp();
       const ex = a => expandArray(a, N, 0);
-      const o = native.verifyKeysBatch(this.#engine(), 1, N, Int8Array.from(ex(this.f)), Uint16Array.from(ex(this.fq)),
+      const o = native.verifyKeysBatch(this.#engine(), 1, Int8Array.from(ex(this.f)), Uint16Array.from(ex(this.fq)),
                                        Uint8Array.from(ex(this.fp)), Int8Array.from(ex(this.g)));
       const fmodq = this.f.map(x => x === -1 ? q - 1 : x), fmodp = this.f.map(x => x === -1 ? p - 1 : x);
       const fqp = this.fq.map(x => x * p), g = this.g.map(x => x === -1 ? q - 1 : x);
@@ -84,10 +96,23 @@ export function accelerate(NTRUReference, ref) {
         h: c([q, nq, N], g, fqp, o.quotientH, o.remainderH),
       };
     }
-    // engine-native unit of work: B rows per call, typed arrays in and out (fixed length, un-trimmed)
-    encryptBitsBatch(B, r, m) { return native.encryptBatch(this.#loadPublic(), B, this.N, r, m); }
-    decryptBitsBatch(B, e) { return native.decryptBatch(this.#loadPrivate(), B, this.N, e); }
-    sumCiphertexts(B, e) { return trimPolynomial(Array.from(native.sum(this.#engine(), B, this.N, e))); }
+    // engine-native unit of work: B rows per call, typed arrays in and out (fixed length, un-trimmed).
+    // r: Uint8Array(B x N) or null (device-drawn, returned as .r); m: Uint8Array, or Uint16Array for coefficients
+    // above 255; hs / fs, fps: one key per row.
+    encryptBitsBatch(B, r, m, hs = null) { return native.encryptBatch(hs ? this.#engine() : this.#loadPublic(), B, r, m, hs); }
+    decryptBitsBatch(B, e, fs = null, fps = null) { return native.decryptBatch(fs ? this.#engine() : this.#loadPrivate(), B, e, fs, fps); }
+    sumCiphertexts(B, e) { return trimPolynomial(Array.from(native.sum(this.#engine(), B, e))); }
+    // packOutput / unpackInput (index.js:572-620) for B rows at once; field elements as 8 little-endian uint32 words
+    packOutputBatch(B, maxVal, data, dataLen) { return native.packOutput(this.#engine(), B, maxVal, data, dataLen); }
+    unpackInputBatch(B, maxVal, packedBits, data, nElems, wide = true) {
+      return native.unpackInput(this.#engine(), B, maxVal, packedBits, data, nElems, wide);
+    }
+    // cross-GPU sum (one NTRU instance = one rank = one GPU; the caller moves the 64-byte handles between its worker
+    // processes and passes a barrier before xchgDestroy)
+    xchgCreate(world, rank) { return native.xchgCreate(this.#engine(), world, rank); }
+    xchgConnect(handles, world) { native.xchgConnect(this.#engine(), handles, world); }
+    xchgDestroy() { native.xchgDestroy(this.#engine()); }
+    sumCiphertextsAllRanks(B, e) { return trimPolynomial(Array.from(native.sumAllreduce(this.#engine(), B, e))); }
     // B key pairs: f, g drawn here like generatePrivateKeyF / generateNewPublicKeyGH do (index.js:51-71), inverses,
     // lifting and h in the engine; rows whose f is not invertible come back with valid = 0 (redraw them)
     generateKeysBatch(B) {
@@ -96,7 +121,8 @@ export function accelerate(NTRUReference, ref) {
         f.set(generateCustomArray(this.N, this.df, this.df - 1), b * this.N);
         g.set(generateCustomArray(this.N, this.dg, this.dg), b * this.N);
       }
-      return { f, g, ...native.keygenBatch(this.#engine(), B, this.N, f, g) };
+      return { f, g, ...native.keygenBatch(this.#engine(), B, f, g) };
     }
+    close() { if (this.#ctx) { native.destroy(this.#ctx); this.#ctx = null; this.#pub = this.#priv = null; } }
   };
 }

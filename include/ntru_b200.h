@@ -84,6 +84,8 @@ void ntru_destroy(ntru_ctx *ctx);
 const char *ntru_last_error(const ntru_ctx *ctx);
 const char *ntru_strerror(int code);
 int ntru_set_option(ntru_ctx *ctx, int key, long value);
+/* the N, p, q the context was created with (any pointer may be NULL) */
+int ntru_get_params(const ntru_ctx *ctx, int *N, int *p, int *q);
 /* device row pitch, in elements, of every *_dev array: roundup(N+1, 16) */
 int ntru_pitch(const ntru_ctx *ctx);
 /* number of CUDA kernels this context has launched so far */
@@ -172,8 +174,17 @@ int ntru_pack_output_dev(ntru_ctx *ctx, size_t B, const void *data, int elem_byt
 int ntru_unpack_input_dev(ntru_ctx *ctx, size_t B, const void *data, int n_elems, uint32_t max_val, int packed_bits,
                           void *out, int elem_bytes, size_t pitch);
 
+/* host-buffer forms of the two calls above (packed rows in, packed field elements / rows out; synchronous) */
+int ntru_pack_output(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, uint32_t max_val, void *out);
+int ntru_unpack_input(ntru_ctx *ctx, size_t B, const void *data, int n_elems, uint32_t max_val, int packed_bits, void *out,
+                      int elem_bytes);
+
 /* fold of addPolynomials(.,.,q) over B ciphertexts -- index.js:235-244, test/reference.test.js:58.  out: N entries */
 int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
+/* the same fold over the rows of EVERY rank of the exchange (ntru_xchg_create / ntru_xchg_connect below; one rank
+ * without them): this rank's B packed host rows, the total on every rank.  Every rank must call it the same number
+ * of times (B may be 0). */
+int ntru_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
 
 /* ---- device-resident variants (pitch = ntru_pitch(ctx) elements; async on ntru_stream(ctx)) ---- */
 /* h_rows == NULL: context key (same-key schedule); else one key per row */

@@ -43,6 +43,10 @@ SYMBOLS = {
     "ntru_decrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "ntru_decrypt_batch_keys": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ntru_sum": (c_int, [_P, c_size_t, _P, _P]),
+    "ntru_sum_allreduce": (c_int, [_P, c_size_t, _P, _P]),
+    "ntru_pack_output": (c_int, [_P, c_size_t, _P, c_int, c_int, ctypes.c_uint32, _P]),
+    "ntru_unpack_input": (c_int, [_P, c_size_t, _P, c_int, ctypes.c_uint32, c_int, _P, c_int]),
+    "ntru_get_params": (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "ntru_keygen_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "ntru_pack_geometry": (c_int, [ctypes.c_uint32, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "ntru_pack_output_dev": (c_int, [_P, c_size_t, _P, c_int, c_int, c_size_t, ctypes.c_uint32, _P]),

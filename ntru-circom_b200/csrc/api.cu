@@ -295,6 +295,7 @@ int ntru_create(ntru_ctx **out, int N, int p, int q, int device) {
 }
 
 static int xchg_release(ntru_ctx *ctx);
+static int xchg_check(ntru_ctx *ctx);
 
 void ntru_destroy(ntru_ctx *ctx) {
   if (!ctx) return;
@@ -751,6 +752,84 @@ int ntru_sum_allreduce_dev(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t 
   }
   if (!ctx->xchg_connected) return fail(ctx, NTRU_E_PARAM, "ntru_xchg_connect has not been called");
   return launch_sum_allreduce(ctx, B, e, out);
+}
+
+int ntru_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if ((B > 0 && !e) || !out) return fail(ctx, NTRU_E_PARAM, "e and out are required");
+  if (!ctx->d_window.ptr) {                      // no exchange set up: a world of one rank
+    rc = xchg_alloc(ctx, 1, 0);
+    if (rc) return rc;
+    ctx->xchg_connected = true;
+  }
+  if (!ctx->xchg_connected) return fail(ctx, NTRU_E_PARAM, "ntru_xchg_connect has not been called");
+  // this rank's rows stream through the pipelined chunks into d_partial, then one small kernel runs the exchange
+  NTRU_CUDA(ctx, cudaMemsetAsync(ctx->d_partial.ptr, 0, (size_t)ctx->P * 4, ctx->stream));
+  if (B > 0) {
+    HostArr arr[kMaxArr];
+    set_in(arr[0], e, 2, (size_t)ctx->N);
+    rc = run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
+      return launch_sum_partial(ctx, rows, (const uint16_t *)dev[0], (uint32_t *)ctx->d_partial.ptr);
+    });
+    if (rc) return rc;
+  }
+  NTRU_CUDA(ctx, ctx->slot_bufs[0][9].reserve((size_t)ctx->P * 2));
+  rc = launch_xchg_partial(ctx, (uint32_t *)ctx->d_partial.ptr, (uint16_t *)ctx->slot_bufs[0][9].ptr);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaMemcpyAsync(out, ctx->slot_bufs[0][9].ptr, (size_t)ctx->N * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return xchg_check(ctx);
+}
+
+int ntru_pack_output(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, uint32_t max_val, void *out) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  int bits, n, arr, outs;
+  if (ntru_pack_geometry(max_val, data_len, &bits, &n, &arr, &outs) != NTRU_OK || (elem_bytes != 1 && elem_bytes != 2))
+    return fail(ctx, NTRU_E_PARAM, "bad maxVal / dataLen / element size");
+  if (B == 0) return NTRU_OK;
+  if (!data || !out) return fail(ctx, NTRU_E_PARAM, "data and out are required");
+  const size_t in_bytes = B * (size_t)data_len * elem_bytes, out_bytes = B * (size_t)outs * 32;
+  NTRU_CUDA(ctx, ctx->slot_packed[0][8].reserve(in_bytes));
+  NTRU_CUDA(ctx, ctx->slot_packed[0][9].reserve(out_bytes));
+  NTRU_CUDA(ctx, cudaMemcpyAsync(ctx->slot_packed[0][8].ptr, data, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = ntru_pack_output_dev(ctx, B, ctx->slot_packed[0][8].ptr, elem_bytes, data_len, (size_t)data_len, max_val, ctx->slot_packed[0][9].ptr);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaMemcpyAsync(out, ctx->slot_packed[0][9].ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NTRU_OK;
+}
+
+int ntru_unpack_input(ntru_ctx *ctx, size_t B, const void *data, int n_elems, uint32_t max_val, int packed_bits, void *out,
+                      int elem_bytes) {
+  int rc = check(ctx);
+  if (rc) return rc;
+  if (max_val == 0 || n_elems < 0 || packed_bits < 1 || packed_bits > 256 || (elem_bytes != 1 && elem_bytes != 2))
+    return fail(ctx, NTRU_E_PARAM, "bad maxVal / packedBits / element size");
+  const int bits = bit_length(max_val);
+  const int n = packed_bits / bits;
+  if (n < 1) return fail(ctx, NTRU_E_PARAM, "packedBits is smaller than one coefficient");
+  if (B == 0 || n_elems == 0) return NTRU_OK;
+  if (!data || !out) return fail(ctx, NTRU_E_PARAM, "data and out are required");
+  const size_t width = (size_t)n * n_elems;
+  const size_t in_bytes = B * (size_t)n_elems * 32, out_bytes = B * width * elem_bytes;
+  NTRU_CUDA(ctx, ctx->slot_packed[0][8].reserve(in_bytes));
+  NTRU_CUDA(ctx, ctx->slot_packed[0][9].reserve(out_bytes));
+  NTRU_CUDA(ctx, cudaMemcpyAsync(ctx->slot_packed[0][8].ptr, data, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = ntru_unpack_input_dev(ctx, B, ctx->slot_packed[0][8].ptr, n_elems, max_val, packed_bits, ctx->slot_packed[0][9].ptr, elem_bytes, width);
+  if (rc) return rc;
+  NTRU_CUDA(ctx, cudaMemcpyAsync(out, ctx->slot_packed[0][9].ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NTRU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NTRU_OK;
+}
+
+int ntru_get_params(const ntru_ctx *ctx, int *N, int *p, int *q) {
+  if (!ctx) return NTRU_E_PARAM;
+  if (N) *N = ctx->N;
+  if (p) *p = ctx->p;
+  if (q) *q = ctx->q;
+  return NTRU_OK;
 }
 
 int ntru_sample_r_dev(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r) {

@@ -439,19 +439,11 @@ __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e, size_t B, int P, const SumScratch sc,
-                                                  const XchgPeers peers, int world, int rank, uint32_t epoch, uint32_t qmask,
-                                                  int N, uint16_t *__restrict__ out) {
-  extern __shared__ __align__(16) uint32_t red[];
-  __shared__ bool flag;
-  __shared__ int timed_out;
-  uint32_t s[8];
-  cta_column_sums(e, B, P, red, s);
-  uint4 tot;
-  if (!grid_column_totals(sc, P, s, &flag, tot)) return;
-  // ---- this CTA owns the exchange ----
+// The exchange itself, run by ONE CTA: thread tid < P / 4 brings the rank's totals of columns 4 tid .. 4 tid + 3.
+__device__ __forceinline__ void exchange_totals(const uint4 tot, int P, const XchgPeers &peers, int world, int rank, uint32_t epoch,
+                                                uint32_t qmask, int N, uint16_t *__restrict__ out, int *timed_out) {
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (tid == 0) timed_out = 0;
+  if (tid == 0) *timed_out = 0;
   const size_t slot = ((size_t)(epoch & 1u) * world + rank) * P;
   if (tid < P / 4) {
     const uint4 v = make_uint4(tot.x & qmask, tot.y & qmask, tot.z & qmask, tot.w & qmask);
@@ -472,14 +464,14 @@ __global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e
     while ((int32_t)(ld_acquire_sys(flags + tid) - epoch) < 0) {
       if (clock64() - t0 > 8000000000ll) {                    // ~4 s: a peer never arrived; do not hang the GPU
         atomicExch(window + (size_t)2 * world * P + world, 1u);
-        timed_out = 1;
+        *timed_out = 1;
         break;
       }
     }
   }
   __syncthreads();
   const int nthr = blockDim.x * blockDim.y;
-  if (timed_out) {
+  if (*timed_out) {
     for (int k = tid; k < P; k += nthr) out[k] = (uint16_t)0xFFFFu;
     return;
   }
@@ -489,6 +481,33 @@ __global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e
     for (int r = 0; r < world; ++r) t += __ldcv(slots + (size_t)r * P + k);
     out[k] = k < N ? (uint16_t)(t & qmask) : (uint16_t)0;
   }
+}
+
+__global__ void __launch_bounds__(512) k_sum_push(const uint16_t *__restrict__ e, size_t B, int P, const SumScratch sc,
+                                                  const XchgPeers peers, int world, int rank, uint32_t epoch, uint32_t qmask,
+                                                  int N, uint16_t *__restrict__ out) {
+  extern __shared__ __align__(16) uint32_t red[];
+  __shared__ bool flag;
+  __shared__ int timed_out;
+  uint32_t s[8];
+  cta_column_sums(e, B, P, red, s);
+  uint4 tot;
+  if (!grid_column_totals(sc, P, s, &flag, tot)) return;
+  exchange_totals(tot, P, peers, world, rank, epoch, qmask, N, out, &timed_out);   // this CTA owns the exchange
+}
+
+// the exchange alone, for column sums that were accumulated over several launches (host-buffer entry point: the
+// shard streams through the pipelined chunks into partial[], which is cleared here for the next call)
+__global__ void __launch_bounds__(512) k_xchg_partial(uint32_t *__restrict__ partial, int P, const XchgPeers peers, int world, int rank,
+                                                      uint32_t epoch, uint32_t qmask, int N, uint16_t *__restrict__ out) {
+  __shared__ int timed_out;
+  const int tid = threadIdx.x;
+  uint4 tot = make_uint4(0, 0, 0, 0);
+  if (tid < P / 4) {
+    tot = reinterpret_cast<const uint4 *>(partial)[tid];
+    reinterpret_cast<uint4 *>(partial)[tid] = make_uint4(0, 0, 0, 0);
+  }
+  exchange_totals(tot, P, peers, world, rank, epoch, qmask, N, out, &timed_out);
 }
 
 __global__ void k_sum_finalize(const uint32_t *__restrict__ partial, int N, int P, uint32_t qmask,
@@ -806,6 +825,19 @@ int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *o
   {
     LaunchTimer timer(ctx, NTRU_K_SUM);
     k_sum_push<<<blocks, block, smem, ctx->stream>>>(e, B, ctx->P, sc, peers, world, rank, epoch, (uint32_t)ctx->q - 1, ctx->N, out);
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
+int launch_xchg_partial(ntru_ctx *ctx, uint32_t *partial, uint16_t *out) {
+  const int world = ctx->xchg_world, rank = ctx->xchg_rank;
+  XchgPeers peers = {};
+  for (int r = 0; r < world; ++r) peers.window[r] = (uint32_t *)ctx->peer_window[r];
+  const uint32_t epoch = ++ctx->xchg_epoch;
+  {
+    LaunchTimer timer(ctx, NTRU_K_SUM);
+    k_xchg_partial<<<1, 512, 0, ctx->stream>>>(partial, ctx->P, peers, world, rank, epoch, (uint32_t)ctx->q - 1, ctx->N, out);
   }
   NTRU_CUDA(ctx, cudaGetLastError());
   return NTRU_OK;

@@ -83,6 +83,20 @@ __device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, 
   const uint32_t sh0 = 8u * (uint32_t)(zfirst - zb), sh1 = sh0 + 8u;
   const uint8_t *pa0 = y0 + zb, *pa1 = y1 + zb;
   const uint8_t *pb = xb + kXPad + 16 * (g - (tq >> 1)) + 8 * (tq & 1);
+  // B fragments: the Hankel block of x that (column block jn, K step s) multiplies starts at 128 jn - 32 s
+  // = 128 d - 32 s4 for jn = sg + d, s = 4 sg + s4 -- it does not depend on the step group sg.  Up to N = 512 the
+  // 4 (kDMax + 1) distinct fragments are loaded ONCE per product and stay in registers (the compiler does not merge
+  // the per-(jn, s) loads: 164 of the 308 shared-memory loads of a product at N = 677).  Above that the 56-64 extra
+  // registers cost a resident CTA per SM and the kernel gets slower (B200, N = 677: 91 against 104 M ct/s; N = 509:
+  // 167 against 161; profiles/r2_imma_bfrag_experiment.jsonl), so the large instantiations keep the loads.
+  constexpr bool kBReg = NJ <= 8;
+  uint2 bf[kBReg ? ImmaShape<NJ>::kDMax + 1 : 1][4];
+  if (kBReg) {
+#pragma unroll
+    for (int d = 0; d <= ImmaShape<NJ>::kDMax; ++d)
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) bf[d][s4] = *reinterpret_cast<const uint2 *>(pb + 128 * d - 32 * s4);
+  }
 #pragma unroll
   for (int sg = 0; sg < ImmaShape<NJ>::kSGroups; ++sg) {
 #pragma unroll
@@ -110,7 +124,7 @@ __device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, 
         for (int d = 0; d <= ImmaShape<NJ>::kDMax; ++d) {
           const int jn = sg + d;
           if (jn < NJ) {
-            const uint2 b = *reinterpret_cast<const uint2 *>(pb + 128 * jn - 32 * s);
+            const uint2 b = kBReg ? bf[kBReg ? d : 0][s4] : *reinterpret_cast<const uint2 *>(pb + 128 * jn - 32 * s);
             imma_u8s8(acc[jn][0], a[0], b.x, b.y);
             if (LIMBS == 2) imma_u8s8(acc[jn][LIMBS - 1], a[LIMBS - 1], b.x, b.y);
           }

@@ -138,6 +138,7 @@ int launch_sum_partial(ntru_ctx *ctx, size_t B, const uint16_t *e, uint32_t *par
 int launch_sum_finalize(ntru_ctx *ctx, const uint32_t *partial, uint16_t *out);
 size_t xchg_window_bytes(const ntru_ctx *ctx, int world);
 int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
+int launch_xchg_partial(ntru_ctx *ctx, uint32_t *partial, uint16_t *out);   // exchange of already accumulated column sums
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r);
 int launch_pack_fields(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch, int bits, int n,
                        int out_elems, uint32_t *out);

@@ -227,6 +227,37 @@ class Engine:
         self._check(self.lib.ntru_unpack_input_dev(self._h, B, _ptr(data), int(n_elems), int(max_val), int(packed_bits), _ptr(out),
                                                    int(elem_bytes), int(pitch)))
 
+    def pack_output(self, max_val: int, data):
+        """packOutput (index.js:572-596) for B host rows: data (B, dataLen) uint8 / uint16 -> (B, outputSize, 8) uint32
+        words of BN254 field elements (32 bytes each, little-endian)."""
+        data = np.ascontiguousarray(data)
+        if data.dtype not in (np.uint8, np.uint16):
+            raise TypeError("pack_output takes uint8 or uint16 rows")
+        B, n = data.shape
+        outs = self.pack_geometry(max_val, n)[3]
+        out = np.empty((B, outs, 8), dtype=np.uint32)
+        self._check(self.lib.ntru_pack_output(self._h, B, _ptr(data), data.dtype.itemsize, n, int(max_val), _ptr(out)))
+        return out
+
+    def unpack_input(self, max_val: int, packed_bits: int, packed, dtype=np.uint16):
+        """unpackInput (index.js:598-620) for B host rows of field elements (B, nElems, 8) uint32 -> coefficients."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        B, n_elems = packed.shape[0], packed.shape[1]
+        bits = max(1, int(max_val).bit_length())
+        out = np.empty((B, (packed_bits // bits) * n_elems), dtype=dtype)
+        self._check(self.lib.ntru_unpack_input(self._h, B, _ptr(packed), n_elems, int(max_val), int(packed_bits), _ptr(out),
+                                               out.dtype.itemsize))
+        return out
+
+    def sum_allreduce(self, e):
+        """Column sums mod q over the host rows of EVERY rank of the exchange (this rank alone without one)."""
+        e = np.ascontiguousarray(e, dtype=np.uint16)
+        B = e.shape[0]
+        e = _host(e, np.uint16, (B, self.N))
+        out = np.empty(self.N, dtype=np.uint16)
+        self._check(self.lib.ntru_sum_allreduce(self._h, B, _ptr(e) if B else None, _ptr(out)))
+        return out
+
     def sum(self, e):
         e = np.ascontiguousarray(e, dtype=np.uint16)
         B = e.shape[0]

@@ -131,4 +131,5 @@ if "c3_167" in which: distinct_key("default167", 1 << 20)
 if "c3s" in which: same_key("hps677", 1 << 20)
 if "c4" in which: same_key("hps821", 1 << 20)
 if "c5" in which: sum_rows("hrss701", 10_000_000)
+if "c5small" in which: sum_rows("hrss701", 1_250_000)
 if "c5s" in which: same_key("hrss701", 1 << 20)

@@ -83,7 +83,8 @@ for r in data:
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     rd, wr = rd * scale.get(unit_rd, 1), wr * scale.get(unit_wr, 1)
     ex = executed_macs(mode)
-    k = {"duration_us_under_ncu": num(r, "gpu__time_duration.sum"),
+    tscale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "s": 1e6, "second": 1e6}
+    k = {"duration_us_under_ncu": num(r, "gpu__time_duration.sum") * tscale.get(table[1][col["gpu__time_duration.sum"]], 1.0),
          "dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes_per_ciphertext": (rd + wr) / rows,
          "algorithmic_bytes_per_ciphertext": alg_bytes[mode], "traffic_over_algorithmic": (rd + wr) / rows / alg_bytes[mode],
          "dram_throughput_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),

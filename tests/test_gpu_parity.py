@@ -835,3 +835,29 @@ def test_cross_gpu_sum_exchange_world2_on_hardware():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "xchg_stress ok" in res.stdout
+
+
+def test_host_buffer_pack_unpack_and_sum_allreduce(nb, engines, golden):
+    """Host-buffer forms of packOutput / unpackInput (index.js:572-620) against the oracle's BigInt restatement, and the
+    host-buffer cross-GPU sum in a world of one rank against the oracle fold (several calls: the accumulator is reused)."""
+    g, eng = golden("hps509"), engines("hps509")
+    N, q = 509, 2048
+    rng = np.random.default_rng(31)
+    rows = rng.integers(0, q, size=(9, N)).astype(np.uint16)
+    rows[0] = q - 1
+    packed = eng.pack_output(q, rows)
+    for b in (0, 1, 8):
+        want = o.pack_output(q, N, [int(x) for x in rows[b]])
+        got = [sum(int(packed[b, e, w]) << (32 * w) for w in range(8)) for e in range(packed.shape[1])]
+        assert got == want["expected"] and packed.shape[1] == want["outputSize"]
+    bits, per, _, outs = eng.pack_geometry(q, N)
+    back = eng.unpack_input(q, per * bits, packed)
+    assert np.array_equal(back[:, :N], rows) and not back[:, N:].any()
+    small = rng.integers(0, 3, size=(4, N + 1)).astype(np.uint8)          # a mod-p witness row (N + 1 entries)
+    p8 = eng.pack_output(2, small)
+    want = o.pack_output(2, N + 1, [int(x) for x in small[3]])
+    assert [sum(int(p8[3, e, w]) << (32 * w) for w in range(8)) for e in range(p8.shape[1])] == want["expected"]
+    for B in (0, 1, 300, 70000):                                           # 70000 rows: three pipeline chunks
+        e = rng.integers(0, q, size=(B, N)).astype(np.uint16)
+        assert np.array_equal(eng.sum_allreduce(e), o.sum_batch(e, q) if B else np.zeros(N, dtype=np.uint16)), B
+        assert np.array_equal(eng.sum(e), o.sum_batch(e, q) if B else np.zeros(N, dtype=np.uint16)), B

@@ -40,6 +40,29 @@ def test_abi_rejects_bad_parameters_without_a_gpu():
     assert lib.ntru_strerror(_lib.NTRU_E_NOKEY) == b"key not set"
 
 
+def test_napi_shim_type_checks_and_binds_every_host_buffer_entry_point():
+    """node and node_api.h are absent from this image, so the N-API shim cannot run; it is at least compiled
+    (gcc -fsyntax-only, warnings as errors) against a stub of node_api.h with the real C-ABI header, and every
+    host-buffer entry point of include/ntru_b200.h must be called from it (the *_dev ones need device pointers, which
+    JavaScript does not have)."""
+    import subprocess
+    shim = os.path.join(ROOT, "bindings", "node", "ntru_napi.c")
+    res = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "tests", "napi_stub"),
+                          "-I", os.path.join(ROOT, "include"), shim], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    hdr = open(os.path.join(ROOT, "include", "ntru_b200.h")).read()
+    declared = set(re.findall(r"\b(ntru_[a-z0-9_]+)\s*\(", hdr))
+    src = open(shim).read()
+    host_only = {n for n in declared if not n.endswith("_dev")} - {
+        "ntru_ctx", "ntru_launch_count", "ntru_last_path", "ntru_timing_read", "ntru_timing_reset",      # bench instrumentation
+        "ntru_stream", "ntru_set_stream", "ntru_sync", "ntru_host_alloc", "ntru_host_free"}             # device-side plumbing
+    missing = sorted(n for n in host_only if not re.search(r"\b" + n + r"\s*\(", src))
+    assert not missing, missing
+    # the JS wrapper must not narrow messages to bytes (a coefficient >= 256 wrapped modulo 256 in round 1)
+    js = open(os.path.join(ROOT, "bindings", "node", "index.mjs")).read()
+    assert "Uint16Array.from(red)" in js and "Uint8Array.from(mExp" not in js
+
+
 def test_shipped_library_reads_no_debug_environment_switches():
     """The timing experiments (NTRU_DEBUG_*: skip loads / stores, results wrong on purpose) exist in NTRU_TRACE builds
     only; a stray environment variable cannot change what the shipped library computes."""
