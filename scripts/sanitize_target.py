@@ -1,9 +1,9 @@
-"""Small tcgen05-schedule run for compute-sanitizer (one tool per gpurun call):
-  compute-sanitizer --tool racecheck|initcheck|memcheck|synccheck python scripts/sanitize_target.py [N q rows]
-Several 256-row tiles per CTA pair are not needed for the hazards these tools see (shared-memory races, reads of
-uninitialised global memory, out-of-bounds accesses), so the batch is two waves of tiles plus a ragged tail; outputs are
-poisoned first and compared with the fp32 schedule afterwards, pad columns included (the round-1 report of a `value`
-array left unwritten at N = 701 is what this chases)."""
+"""Poison-and-compare stress of the tcgen05 schedule:  python scripts/sanitize_target.py [N q rows iterations]
+compute-sanitizer is CLOSED on this pool (gpurun answers "closed ... stays closed", profiles/r2_sanitizer_closed.txt), so
+the round-1 report of a `value` array left unwritten once at N = 701 (an unshipped kernel variant, inside the test
+process) is chased with the library's own means: every iteration poisons all six output arrays, runs encrypt + decrypt on
+the tcgen05 schedule in the SAME process and context, and compares every byte -- pad columns included -- with the fp32
+schedule; batch sizes alternate between a ragged few tiles and several tiles per CTA pair."""
 import sys
 
 import numpy as np
@@ -26,18 +26,30 @@ r = torch.zeros((B, P), dtype=torch.uint8, device=dev)
 r[:, :N] = torch.randint(0, 3, (B, N), device=dev, dtype=torch.uint8)
 m = torch.zeros((B, P), dtype=torch.uint8, device=dev)
 m[:, :N] = torch.randint(0, 2, (B, N), device=dev, dtype=torch.uint8)
-res = {}
-for path in (nb.PATH_TENSOR, nb.PATH_CUDA_CORE):
-    eng.set_path(path)
-    bufs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
-           [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+want = {}
+bad = 0
+for it in range(iters):
+    rows = B if it % 2 == 0 else min(B, 2 * 256 + 131)
+    if rows not in want:
+        eng.set_path(nb.PATH_CUDA_CORE)
+        ref = [torch.full((rows, P), 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
+              [torch.full((rows, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+        eng.encrypt_dev(rows, r, m, value=ref[0], quotientE=ref[1])
+        eng.decrypt_dev(rows, ref[0], value=ref[4], quotient1=ref[2], remainder1=ref[3], quotient2=ref[5])
+        eng.sync()
+        want[rows] = ref
+    eng.set_path(nb.PATH_TENSOR)
+    bufs = [torch.full((rows, P), 0x5A5A if it % 3 else 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
+           [torch.full((rows, P), 0x5A if it % 3 else 7, dtype=torch.uint8, device=dev) for _ in range(2)]
     val, quo, q1, r1, pv, q2 = bufs
-    for _ in range(2 if path == nb.PATH_TENSOR else 1):
-        eng.encrypt_dev(B, r, m, value=val, quotientE=quo)
-        eng.decrypt_dev(B, val, value=pv, quotient1=q1, remainder1=r1, quotient2=q2)
+    eng.encrypt_dev(rows, r, m, value=val, quotientE=quo)
+    eng.decrypt_dev(rows, val, value=pv, quotient1=q1, remainder1=r1, quotient2=q2)
     eng.sync()
-    res[path] = bufs
-ok = all(torch.equal(a, b) for a, b in zip(res[nb.PATH_TENSOR], res[nb.PATH_CUDA_CORE]))
-print("sanitize_target", N, q, B, "tensor == fp32 schedule (pad columns included):", ok)
+    for name, a, b in zip(("value", "quotientE", "quotient1", "remainder1", "plain", "quotient2"), bufs, want[rows]):
+        if not torch.equal(a, b):
+            bad += 1
+            print(f"iteration {it} rows {rows}: {name} differs in {int((a != b).sum())} entries", flush=True)
+print("sanitize_target", N, q, B, f"{iters} iterations, tensor == fp32 schedule (pad columns included):", bad == 0)
 eng.close()
-sys.exit(0 if ok else 1)
+sys.exit(0 if bad == 0 else 1)
