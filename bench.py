@@ -160,6 +160,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Best effort: restrict this rank to the CPUs NVML reports as local to its GPU, so that the pinned e2e buffers
+    (first touch) and the copy-issuing thread sit on the GPU's NUMA node.  Returns the CPU list or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{allowed[0]}-{allowed[-1]} ({len(allowed)} CPUs)"
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -422,6 +440,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None     # pinned host buffers land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     g = load_key()
@@ -585,6 +604,7 @@ def run_ours(args, rank, world, local_rank):
                         "d2h_GBps_per_gpu_alone": e2e["d2h_bytes_per_step"] / t_down / 1e9,
                         "how": "plain cudaMemcpyAsync of the step's arrays from/to the same pinned buffers, two streams, no kernels"}
     e2e["frac_of_pcie"] = t_both / (dt / args.e2e_steps)
+    e2e["cpu_affinity"] = numa
     del d_in, d_out
 
     # ---- the other BASELINE configs (every rank takes part: configs 4 and 5 are sharded over the ranks) ----
@@ -646,7 +666,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "extras": extras,
     }
     extras["configs"] = configs
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:                  # the CPU leg runs at N = 1 only (rank 0's host cores)
         line["cpu_baseline"] = cpu_baseline(g)
     print(json.dumps(line), flush=True)
     if world > 1:
