@@ -530,6 +530,9 @@ def run_ours(args, rank, world, local_rank):
               "value_only_GBps_7N": 7 * N * B / ((t_enc_v + t_dec_v) * 1e-3) / 1e9, "note": "per GPU, measured after the timed region"}
 
     # ---- end to end through the host-buffer ABI (pinned host memory, copies inside the timing) ----
+    # Two wire formats of the same two calls: "field_elements" -- every array as packOutput(maxVal, width, row).expected
+    # (index.js:572-596, the form CombineArray / UnpackArray take; bits packed and unpacked on the device) -- and
+    # "plain_arrays" (uint16 / uint8 coefficient rows).  Same rows, same results (checked below after unpacking).
     Be = min(args.e2e_rows, B)
     eng2 = nb.Engine(N, p, q, local_rank)
     eng2.set_public_key(g["h"])
@@ -537,54 +540,10 @@ def run_ours(args, rank, world, local_rank):
     if args.path:
         eng2.set_path(args.path)
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()   # noqa: E731
-    h_r, h_m = pin((Be, N), torch.uint8), pin((Be, N), torch.uint8)
-    h_r.copy_(r[:Be, :N].cpu())
-    h_m.copy_(m[:Be, :N].cpu())
-    h_val, h_quo = pin((Be, N), torch.int16), pin((Be, N + 1), torch.int16)
-    h_out, h_q1, h_r1 = pin((Be, N), torch.uint8), pin((Be, N + 1), torch.int16), pin((Be, N + 1), torch.int16)
-    h_q2 = pin((Be, N + 1), torch.uint8)
     lib, ctx = eng2.lib, eng2._h
+    r_host, m_host = r[:Be, :N].cpu().numpy(), m[:Be, :N].cpu().numpy()
 
-    def e2e_step():
-        rc = lib.ntru_encrypt_batch(ctx, Be, h_r.data_ptr(), h_m.data_ptr(), h_val.data_ptr(), h_quo.data_ptr(), None, None)
-        assert rc == 0, eng2.lib.ntru_last_error(ctx)
-        rc = lib.ntru_decrypt_batch(ctx, Be, h_val.data_ptr(), h_out.data_ptr(), h_q1.data_ptr(), h_r1.data_ptr(),
-                                    h_q2.data_ptr(), None)
-        assert rc == 0, eng2.lib.ntru_last_error(ctx)
-
-    e2e_step()
-    assert torch.equal(h_out, h_m)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e = {"value": world * Be * args.e2e_steps / dt, "unit": "ciphertexts/s",
-           "h2d_bytes_per_step": Be * (N + N + 2 * N), "d2h_bytes_per_step": Be * (2 * N + 2 * (N + 1) + N + 4 * (N + 1) + (N + 1)),
-           "rows_per_step": Be, "steps": args.e2e_steps, "timer": "host wall clock around the synchronous C-ABI calls"}
-    # PCIe roof of exactly these transfers: one plain cudaMemcpyAsync per array of a step (no kernels), host -> device
-    # on one stream and device -> host on another, every rank at the same time; same wall-clock timer
-    h_in, h_outs = (h_r, h_m, h_val), (pin((Be, N), torch.int16), h_quo, h_out, h_q1, h_r1, h_q2)   # value lands in its own rows:
-    d_in = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_in]
-    d_out = [torch.zeros(t.shape, dtype=t.dtype, device=dev) for t in h_outs]
-    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-
-    def pcie_step(up=True, down=True):
-        if up:
-            with torch.cuda.stream(s_up):
-                for d, h in zip(d_in, h_in):
-                    d.copy_(h, non_blocking=True)
-        if down:
-            with torch.cuda.stream(s_down):
-                for h, d in zip(h_outs, d_out):             # h_val itself is being read by the upload at the same time
-                    h.copy_(d, non_blocking=True)
-
-    def wall(fn, n=3):
+    def wall(fn, n):
         fn()
         barrier()
         t0 = time.perf_counter()
@@ -598,14 +557,79 @@ def run_ours(args, rank, world, local_rank):
             d = float(t.item())
         return d
 
-    t_both, t_up, t_down = wall(pcie_step), wall(lambda: pcie_step(True, False)), wall(lambda: pcie_step(False, True))
-    e2e["pcie_roof"] = {"s_per_step_both_directions": t_both, "ct_per_s": world * Be / t_both,
-                        "h2d_GBps_per_gpu_alone": e2e["h2d_bytes_per_step"] / t_up / 1e9,
-                        "d2h_GBps_per_gpu_alone": e2e["d2h_bytes_per_step"] / t_down / 1e9,
-                        "how": "plain cudaMemcpyAsync of the step's arrays from/to the same pinned buffers, two streams, no kernels"}
-    e2e["frac_of_pcie"] = t_both / (dt / args.e2e_steps)
+    def e2e_measure(fe: bool):
+        if fe:
+            el = lambda mod_q, width: (Be, eng2.packed_elems(mod_q, width), 8)   # noqa: E731
+            h_r, h_m = pin(el(False, N), torch.int32), pin(el(False, N), torch.int32)
+            h_r.numpy()[:] = nb.wire.pack_rows(p - 1, r_host).view(np.int32)
+            h_m.numpy()[:] = nb.wire.pack_rows(p - 1, m_host).view(np.int32)
+            h_val, h_quo = pin(el(True, N), torch.int32), pin(el(True, N + 1), torch.int32)
+            h_out, h_q1, h_r1 = pin(el(False, N), torch.int32), pin(el(True, N + 1), torch.int32), pin(el(True, N + 1), torch.int32)
+            h_q2 = pin(el(False, N + 1), torch.int32)
+            f_enc, f_dec = lib.ntru_encrypt_batch_packed, lib.ntru_decrypt_batch_packed
+        else:
+            h_r, h_m = pin((Be, N), torch.uint8), pin((Be, N), torch.uint8)
+            h_r.numpy()[:] = r_host
+            h_m.numpy()[:] = m_host
+            h_val, h_quo = pin((Be, N), torch.int16), pin((Be, N + 1), torch.int16)
+            h_out, h_q1, h_r1 = pin((Be, N), torch.uint8), pin((Be, N + 1), torch.int16), pin((Be, N + 1), torch.int16)
+            h_q2 = pin((Be, N + 1), torch.uint8)
+            f_enc, f_dec = lib.ntru_encrypt_batch, lib.ntru_decrypt_batch
+
+        def e2e_step():
+            rc = f_enc(ctx, Be, h_r.data_ptr(), h_m.data_ptr(), h_val.data_ptr(), h_quo.data_ptr(), None, None)
+            assert rc == 0, eng2.lib.ntru_last_error(ctx)
+            rc = f_dec(ctx, Be, h_val.data_ptr(), h_out.data_ptr(), h_q1.data_ptr(), h_r1.data_ptr(), h_q2.data_ptr(), None)
+            assert rc == 0, eng2.lib.ntru_last_error(ctx)
+
+        dt = wall(e2e_step, args.e2e_steps)
+        nbytes = lambda *ts: int(sum(t.numel() * t.element_size() for t in ts))   # noqa: E731
+        res = {"value": world * Be / dt, "unit": "ciphertexts/s",
+               "h2d_bytes_per_step": nbytes(h_r, h_m, h_val), "d2h_bytes_per_step": nbytes(h_val, h_quo, h_out, h_q1, h_r1, h_q2),
+               "rows_per_step": Be, "steps": args.e2e_steps, "timer": "host wall clock around the synchronous C-ABI calls"}
+        # PCIe roof of exactly these transfers: one plain cudaMemcpyAsync per array of a step (no kernels), host -> device
+        # on one stream and device -> host on another, every rank at the same time; same wall-clock timer
+        h_in, h_outs = (h_r, h_m, h_val), (pin(tuple(h_val.shape), h_val.dtype), h_quo, h_out, h_q1, h_r1, h_q2)   # value lands in its own rows
+        d_in = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in h_in]
+        d_out = [torch.zeros(t.shape, dtype=t.dtype, device=dev) for t in h_outs]
+        s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        keep = {k: v.clone() for k, v in (("value", h_val), ("quotientE", h_quo), ("plain", h_out), ("quotient1", h_q1),
+                                          ("remainder1", h_r1), ("quotient2", h_q2))}     # results, before the roof copies overwrite them
+
+        def pcie_step(up=True, down=True):
+            if up:
+                with torch.cuda.stream(s_up):
+                    for d, h in zip(d_in, h_in):
+                        d.copy_(h, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_down):
+                    for h, d in zip(h_outs, d_out):             # h_val itself is being read by the upload at the same time
+                        h.copy_(d, non_blocking=True)
+
+        t_both, t_up, t_down = wall(pcie_step, 3), wall(lambda: pcie_step(True, False), 3), wall(lambda: pcie_step(False, True), 3)
+        res["pcie_roof"] = {"s_per_step_both_directions": t_both, "ct_per_s": world * Be / t_both,
+                            "h2d_GBps_per_gpu_alone": res["h2d_bytes_per_step"] / t_up / 1e9,
+                            "d2h_GBps_per_gpu_alone": res["d2h_bytes_per_step"] / t_down / 1e9,
+                            "how": "plain cudaMemcpyAsync of the step's arrays from/to the same pinned buffers, two streams, no kernels"}
+        res["frac_of_pcie"] = t_both / dt
+        return res, keep
+
+    e2e_plain, keep_plain = e2e_measure(False)
+    e2e, keep_fe = e2e_measure(True)
+    # both wire formats carry the same results: unpack the field elements on the host and compare every array
+    assert np.array_equal(keep_plain["plain"].numpy(), m_host), "decrypt(encrypt(m)) != m (plain arrays)"
+    for k, mod_q, width in (("value", True, N), ("quotientE", True, N + 1), ("plain", False, N), ("quotient1", True, N + 1),
+                            ("remainder1", True, N + 1), ("quotient2", False, N + 1)):
+        got = nb.wire.unpack_rows(q - 1 if mod_q else p - 1, width, keep_fe[k].numpy().view(np.uint32), np.uint16 if mod_q else np.uint8)
+        want = keep_plain[k].numpy()
+        assert np.array_equal(got, want.view(np.uint16) if mod_q else want), f"field-element wire format differs from the plain arrays in {k}"
+    e2e["wire"] = ("BN254 field elements, packOutput(maxVal, width, row).expected per row (index.js:572-596): maxVal = q - 1 for value / "
+                   "quotientE / quotient1 / remainder1, p - 1 for r / m / plaintext / quotient2; ntru_encrypt_batch_packed + ntru_decrypt_batch_packed")
+    e2e["equals_plain_arrays_after_unpack"] = True
+    e2e_plain["wire"] = "uint16 / uint8 coefficient rows; ntru_encrypt_batch + ntru_decrypt_batch"
+    e2e["plain_arrays"] = e2e_plain
     e2e["cpu_affinity"] = numa
-    del d_in, d_out
+    del keep_plain, keep_fe
 
     # ---- the other BASELINE configs (every rank takes part: configs 4 and 5 are sharded over the ranks) ----
     hbm_gbs, bf16_tf, peak_src = peaks()

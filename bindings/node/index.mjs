@@ -101,6 +101,11 @@ export function accelerate(NTRUReference, ref) {
     // above 255; hs / fs, fps: one key per row.
     encryptBitsBatch(B, r, m, hs = null) { return native.encryptBatch(hs ? this.#engine() : this.#loadPublic(), B, r, m, hs); }
     decryptBitsBatch(B, e, fs = null, fps = null) { return native.decryptBatch(fs ? this.#engine() : this.#loadPrivate(), B, e, fs, fps); }
+    // the same two with every array as rows of BN254 field elements on the wire -- row = packOutput(maxVal, width,
+    // coefficients).expected as 8 little-endian uint32 words per element, maxVal = q - 1 for the arrays modulo q and
+    // p - 1 for r, m and the arrays modulo p: what CombineArray / UnpackArray take, and two thirds of the bytes
+    encryptBitsBatchPacked(B, r, m) { return native.encryptBatchPacked(this.#loadPublic(), B, r, m); }
+    decryptBitsBatchPacked(B, e) { return native.decryptBatchPacked(this.#loadPrivate(), B, e); }
     sumCiphertexts(B, e) { return trimPolynomial(Array.from(native.sum(this.#engine(), B, e))); }
     // packOutput / unpackInput (index.js:572-620) for B rows at once; field elements as 8 little-endian uint32 words
     packOutputBatch(B, maxVal, data, dataLen) { return native.packOutput(this.#engine(), B, maxVal, data, dataLen); }

@@ -19,6 +19,8 @@
  *                                                   a Uint16Array m takes the wide path (index.js:91); h: one key per row
  *   decryptBatch(handle, B, e: Uint16Array[, f: Int8Array, fp: Uint8Array])
  *        -> {value, quotient1, remainder1, quotient2, remainder2}
+ *   encryptBatchPacked(handle, B, r: Uint32Array | null, m: Uint32Array) / decryptBatchPacked(handle, B, e: Uint32Array):
+ *        the same with every array as rows of BN254 field elements (packOutput form), B x packedElems x 8 words
  *   verifyKeysBatch(handle, B, f, fq, fp, g)   keygenBatch(handle, B, f, g)
  *   packOutput(handle, B, maxVal, data: Uint8Array | Uint16Array, dataLen) -> Uint32Array(B x outputSize x 8)
  *   unpackInput(handle, B, maxVal, packedBits, data: Uint32Array, nElems, wide: bool) -> Uint8Array | Uint16Array
@@ -330,6 +332,65 @@ static napi_value DecryptBatch(napi_env env, napi_callback_info info) {
   return out;
 }
 
+/* ---- the same two calls with BN254 field elements on the wire (packOutput form, index.js:572-596) ---------------------
+ * encryptBatchPacked(handle, B, r: Uint32Array | null, m: Uint32Array) -> {value, quotientE, remainderE, r}
+ * decryptBatchPacked(handle, B, e: Uint32Array) -> {value, quotient1, remainder1, quotient2, remainder2}
+ * every array: B x packedElems x 8 little-endian 32-bit words per row (BigInt = sum of word[i] << 32 i). */
+static napi_value EncryptBatchPacked(napi_env env, napi_callback_info info) {
+  ARGS(4);
+  ntru_ctx *ctx = get_ctx(env, argv[0]);
+  size_t N;
+  uint32_t B;
+  if (!ctx || !ctx_N(ctx, &N) || !get_u32(env, argv[1], &B, "B: row count")) return NULL;
+  const size_t small = (size_t)B * (size_t)ntru_packed_elems(ctx, 0, (int)N) * 8, val = (size_t)B * (size_t)ntru_packed_elems(ctx, 1, (int)N) * 8,
+               wit = (size_t)B * (size_t)ntru_packed_elems(ctx, 1, (int)N + 1) * 8;
+  const void *r = NULL;
+  if (!is_nullish(env, argv[2])) {
+    r = typed_arg(env, argv[2], napi_uint32_array, small, "r: Uint32Array(B x packedElems x 8) or null");
+    if (!r) return NULL;
+  }
+  const void *m = typed_arg(env, argv[3], napi_uint32_array, small, "m: Uint32Array(B x packedElems x 8)");
+  if (!m) return NULL;
+  void *value, *quo, *rem, *r_out;
+  napi_value v0 = make_typed(env, napi_uint32_array, val, 4, &value), v1 = make_typed(env, napi_uint32_array, wit, 4, &quo),
+             v2 = make_typed(env, napi_uint32_array, wit, 4, &rem), v3 = make_typed(env, napi_uint32_array, small, 4, &r_out);
+  if (!value || !quo || !rem || !r_out) return NULL;
+  NTRU_TRY(env, ctx, ntru_encrypt_batch_packed(ctx, B, r, m, value, quo, rem, r_out));
+  napi_value out;
+  NAPI_TRY(env, napi_create_object(env, &out));
+  SET(out, "value", v0);
+  SET(out, "quotientE", v1);
+  SET(out, "remainderE", v2);
+  SET(out, "r", v3);
+  return out;
+}
+
+static napi_value DecryptBatchPacked(napi_env env, napi_callback_info info) {
+  ARGS(3);
+  ntru_ctx *ctx = get_ctx(env, argv[0]);
+  size_t N;
+  uint32_t B;
+  if (!ctx || !ctx_N(ctx, &N) || !get_u32(env, argv[1], &B, "B: row count")) return NULL;
+  const size_t e_len = (size_t)B * (size_t)ntru_packed_elems(ctx, 1, (int)N) * 8, wq = (size_t)B * (size_t)ntru_packed_elems(ctx, 1, (int)N + 1) * 8,
+               vs = (size_t)B * (size_t)ntru_packed_elems(ctx, 0, (int)N) * 8, ws = (size_t)B * (size_t)ntru_packed_elems(ctx, 0, (int)N + 1) * 8;
+  const void *e = typed_arg(env, argv[2], napi_uint32_array, e_len, "e: Uint32Array(B x packedElems x 8)");
+  if (!e) return NULL;
+  void *value, *q1, *r1, *q2, *r2;
+  napi_value v0 = make_typed(env, napi_uint32_array, vs, 4, &value), v1 = make_typed(env, napi_uint32_array, wq, 4, &q1),
+             v2 = make_typed(env, napi_uint32_array, wq, 4, &r1), v3 = make_typed(env, napi_uint32_array, ws, 4, &q2),
+             v4 = make_typed(env, napi_uint32_array, ws, 4, &r2);
+  if (!value || !q1 || !r1 || !q2 || !r2) return NULL;
+  NTRU_TRY(env, ctx, ntru_decrypt_batch_packed(ctx, B, e, value, q1, r1, q2, r2));
+  napi_value out;
+  NAPI_TRY(env, napi_create_object(env, &out));
+  SET(out, "value", v0);
+  SET(out, "quotient1", v1);
+  SET(out, "remainder1", v2);
+  SET(out, "quotient2", v3);
+  SET(out, "remainder2", v4);
+  return out;
+}
+
 /* verifyKeysBatch(handle, B, f: Int8Array, fq: Uint16Array, fp: Uint8Array, g: Int8Array) -- index.js:141-197 for B keys */
 static napi_value VerifyKeysBatch(napi_env env, napi_callback_info info) {
   ARGS(6);
@@ -521,7 +582,8 @@ static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
       FN("create", Create), FN("destroy", Destroy), FN("params", Params), FN("setOption", SetOption), FN("setRngKey", SetRngKey),
       FN("rngNextRow", RngNextRow), FN("setPublicKey", SetPublicKey), FN("setPrivateKey", SetPrivateKey),
-      FN("encryptBatch", EncryptBatch), FN("decryptBatch", DecryptBatch), FN("verifyKeysBatch", VerifyKeysBatch),
+      FN("encryptBatch", EncryptBatch), FN("decryptBatch", DecryptBatch), FN("encryptBatchPacked", EncryptBatchPacked),
+      FN("decryptBatchPacked", DecryptBatchPacked), FN("verifyKeysBatch", VerifyKeysBatch),
       FN("keygenBatch", KeygenBatch), FN("packGeometry", PackGeometry), FN("packOutput", PackOutput), FN("unpackInput", UnpackInput),
       FN("sum", Sum), FN("xchgCreate", XchgCreate), FN("xchgConnect", XchgConnect), FN("xchgDestroy", XchgDestroy),
       FN("sumAllreduce", SumAllreduce),

@@ -58,7 +58,12 @@ enum {
   NTRU_OPT_CHUNK_ROWS = 2,  /* rows per pipelined chunk of the host-buffer entry points (default 32768) */
   NTRU_OPT_TIMING = 3,      /* 1: bracket every kernel launch with CUDA events on its stream (ntru_timing_read) */
   /* 4 was NTRU_OPT_TENSOR_VARIANT (a single-CTA tcgen05 kernel kept as a cross-check in round 1; removed) */
-  NTRU_OPT_DR = 5           /* dr of new NTRU({..., dr}) (index.js:15): weights of the r the device draws when r == NULL */
+  NTRU_OPT_DR = 5,          /* dr of new NTRU({..., dr}) (index.js:15): weights of the r the device draws when r == NULL */
+  NTRU_OPT_DEC1_FORM = 6    /* tcgen05 schedule, first decrypt product at 256 < q <= 2048: 2 = fp16 tiles (a uint16 coefficient
+                               below 2048 is its own fp16 encoding: no operand transform, sixteen epilogue warps), 1 = the
+                               two-byte-limb int8 form used at every other q, 0 (default) = whichever measured faster on B200:
+                               fp16 above N = 512 (DEC1 at N = 677: 1.49 against 1.65 ms), byte limbs up to it (0.85 against
+                               0.89 ms at N = 509).  Both forms are exact; each is the other's cross-check in the tests. */
 };
 
 /* kernel kinds reported by ntru_timing_read */
@@ -178,6 +183,21 @@ int ntru_unpack_input_dev(ntru_ctx *ctx, size_t B, const void *data, int n_elems
 int ntru_pack_output(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, uint32_t max_val, void *out);
 int ntru_unpack_input(ntru_ctx *ctx, size_t B, const void *data, int n_elems, uint32_t max_val, int packed_bits, void *out,
                       int elem_bytes);
+
+/* encryptBits / decryptBits with every array crossing the host link as BN254 field elements, the form the circuits'
+ * CombineArray / UnpackArray take (circuits/ntru.circom:259-306): row b of an array of `width` coefficients is
+ * packOutput(maxVal, width, row).expected (index.js:572-596) -- ntru_packed_elems(ctx, mod_q, width) elements of 32
+ * bytes, little-endian -- with maxVal = q - 1 for the arrays modulo q (value / e, quotientE, remainderE, quotient1,
+ * remainder1) and maxVal = p - 1 for the small ones (r with 2 = -1, m, decrypt's value, quotient2, remainder2).
+ * Widths as in the calls above (N, or N + 1 for the witness arrays).  Inputs must hold zeros beyond `width` (packOutput
+ * pads with zeros).  The bits are packed / unpacked on the device: at N = 509, q = 2048 a ciphertext with its full
+ * witness crosses the link in 3392 bytes device -> host instead of 5097, 1088 instead of 2036 host -> device.
+ * r == NULL, r_out, NULL outputs: as in ntru_encrypt_batch / ntru_decrypt_batch. */
+int ntru_packed_elems(const ntru_ctx *ctx, int mod_q, int width);
+int ntru_encrypt_batch_packed(ntru_ctx *ctx, size_t B, const void *r, const void *m, void *value, void *quotientE,
+                              void *remainderE, void *r_out);
+int ntru_decrypt_batch_packed(ntru_ctx *ctx, size_t B, const void *e, void *value, void *quotient1, void *remainder1,
+                              void *quotient2, void *remainder2);
 
 /* fold of addPolynomials(.,.,q) over B ciphertexts -- index.js:235-244, test/reference.test.js:58.  out: N entries */
 int ntru_sum(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libntru_b200.so")
 NTRU_OK = 0
 NTRU_E_PARAM, NTRU_E_LENGTH, NTRU_E_NOKEY, NTRU_E_CUDA = -1, -2, -3, -4
 NTRU_E_NCCL, NTRU_E_NOMEM, NTRU_E_UNSUPPORTED = -5, -6, -7
-NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING, NTRU_OPT_DR = 1, 2, 3, 5
+NTRU_OPT_PATH, NTRU_OPT_CHUNK_ROWS, NTRU_OPT_TIMING, NTRU_OPT_DR, NTRU_OPT_DEC1_FORM = 1, 2, 3, 5, 6
 KERNEL_KINDS = ["enc_tensor", "dec1_tensor", "dec2_tensor", "enc_core", "dec_core", "sum", "other", "enc_imma", "dec_imma",
                 "muldiv", "pack"]
 PATH_AUTO, PATH_CUDA_CORE, PATH_TENSOR, PATH_IMMA = 0, 1, 2, 3
@@ -42,6 +42,9 @@ SYMBOLS = {
     "ntru_rng_next_row": (c_uint64, [_P]),
     "ntru_decrypt_batch": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "ntru_decrypt_batch_keys": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ntru_packed_elems": (c_int, [_P, c_int, c_int]),
+    "ntru_encrypt_batch_packed": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
+    "ntru_decrypt_batch_packed": (c_int, [_P, c_size_t, _P, _P, _P, _P, _P, _P]),
     "ntru_sum": (c_int, [_P, c_size_t, _P, _P]),
     "ntru_sum_allreduce": (c_int, [_P, c_size_t, _P, _P]),
     "ntru_pack_output": (c_int, [_P, c_size_t, _P, c_int, c_int, ctypes.c_uint32, _P]),

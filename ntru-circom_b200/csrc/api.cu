@@ -60,6 +60,10 @@ struct HostArr {
   size_t elem = 1;            // bytes per element
   size_t width = 0;           // packed elements per row on the host
   bool used = false;
+  // field-element wire format (ntru_*_batch_packed): the host row is fe_elems BN254 field elements of 32 bytes,
+  // packOutput(maxVal, width, row).expected -- fe_n coefficients of fe_bits bits each per element; 0 = plain rows
+  int fe_bits = 0, fe_n = 0, fe_elems = 0;
+  size_t host_row_bytes() const { return fe_bits ? (size_t)fe_elems * 32 : width * elem; }
 };
 
 constexpr int kMaxArr = 10;
@@ -75,7 +79,7 @@ int run_pipeline(ntru_ctx *ctx, size_t B, HostArr (&arr)[kMaxArr], Launch launch
     for (int a = 0; a < kMaxArr; ++a)
       if (arr[a].used) {
         NTRU_CUDA(ctx, ctx->slot_bufs[s][a].reserve(rows_alloc * P * arr[a].elem));
-        NTRU_CUDA(ctx, ctx->slot_packed[s][a].reserve(rows_alloc * arr[a].width * arr[a].elem));
+        NTRU_CUDA(ctx, ctx->slot_packed[s][a].reserve(rows_alloc * arr[a].host_row_bytes()));
       }
   size_t ci = 0;
   for (size_t row0 = 0; row0 < B; row0 += chunk, ++ci) {
@@ -87,7 +91,7 @@ int run_pipeline(ntru_ctx *ctx, size_t B, HostArr (&arr)[kMaxArr], Launch launch
     if (ci >= (size_t)kNumSlots) NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[s], 0));
     for (int a = 0; a < kMaxArr; ++a) {
       if (!arr[a].used || !arr[a].in) continue;
-      const size_t wb = arr[a].width * arr[a].elem;
+      const size_t wb = arr[a].host_row_bytes();
       NTRU_CUDA(ctx, cudaMemcpyAsync(ctx->slot_packed[s][a].ptr, (const char *)arr[a].in + row0 * wb, rows * wb,
                                      cudaMemcpyHostToDevice, ctx->s_in));
     }
@@ -96,21 +100,27 @@ int run_pipeline(ntru_ctx *ctx, size_t B, HostArr (&arr)[kMaxArr], Launch launch
     if (ci >= (size_t)kNumSlots) NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[s], 0));
     for (int a = 0; a < kMaxArr; ++a) {
       if (!arr[a].used || !arr[a].in) continue;
-      int rc = launch_repitch(ctx, ctx->slot_packed[s][a].ptr, dev[a], rows, (int)arr[a].width, (int)arr[a].elem, true);
+      int rc = arr[a].fe_bits
+                   ? launch_wire_unpack(ctx, rows, (const uint32_t *)ctx->slot_packed[s][a].ptr, arr[a].fe_elems, arr[a].fe_bits,
+                                        arr[a].fe_n, (int)arr[a].width, dev[a], (int)arr[a].elem)
+                   : launch_repitch(ctx, ctx->slot_packed[s][a].ptr, dev[a], rows, (int)arr[a].width, (int)arr[a].elem, true);
       if (rc != NTRU_OK) return rc;
     }
     int rc = launch(rows, dev);
     if (rc != NTRU_OK) return rc;
     for (int a = 0; a < kMaxArr; ++a) {
       if (!arr[a].used || !arr[a].out) continue;
-      rc = launch_repitch(ctx, dev[a], ctx->slot_packed[s][a].ptr, rows, (int)arr[a].width, (int)arr[a].elem, false);
+      rc = arr[a].fe_bits
+               ? launch_pack_fields(ctx, rows, dev[a], (int)arr[a].elem, (int)arr[a].width, (size_t)ctx->P, arr[a].fe_bits, arr[a].fe_n,
+                                    arr[a].fe_elems, (uint32_t *)ctx->slot_packed[s][a].ptr)
+               : launch_repitch(ctx, dev[a], ctx->slot_packed[s][a].ptr, rows, (int)arr[a].width, (int)arr[a].elem, false);
       if (rc != NTRU_OK) return rc;
     }
     NTRU_CUDA(ctx, cudaEventRecord(ctx->ev_comp[s], ctx->stream));
     NTRU_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[s], 0));
     for (int a = 0; a < kMaxArr; ++a) {
       if (!arr[a].used || !arr[a].out) continue;
-      const size_t wb = arr[a].width * arr[a].elem;
+      const size_t wb = arr[a].host_row_bytes();
       NTRU_CUDA(ctx, cudaMemcpyAsync((char *)arr[a].out + row0 * wb, ctx->slot_packed[s][a].ptr, rows * wb,
                                      cudaMemcpyDeviceToHost, ctx->s_out));
     }
@@ -126,6 +136,26 @@ void set_in(HostArr &a, const void *p, size_t elem, size_t width) {
 }
 void set_out(HostArr &a, void *p, size_t elem, size_t width) {
   a.out = p; a.elem = elem; a.width = width; a.used = p != nullptr;
+}
+
+int bit_length(uint32_t v) {   // floor(log2(v) + 1) for v >= 1 (index.js:573, 601)
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b;
+}
+// the array crosses the host link as packOutput(max_val, width, row).expected (index.js:572-596)
+void set_fe(HostArr &a, uint32_t max_val) {
+  if (!a.used) return;
+  a.fe_bits = bit_length(max_val);
+  a.fe_n = 252 / a.fe_bits;
+  int outs = ((int)a.width + a.fe_n - 1) / a.fe_n;
+  a.fe_elems = outs < 3 ? 3 : outs;
+}
+
+int packed_elems(uint32_t max_val, int width) {
+  const int n = 252 / bit_length(max_val);
+  const int outs = (width + n - 1) / n;
+  return outs < 3 ? 3 : outs;
 }
 
 // Below this many rows the tcgen05 schedule cannot fill the chip (one CTA pair per 256 rows, 74 pairs) and the
@@ -336,6 +366,11 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
     case NTRU_OPT_TIMING:
       ctx->timing = value != 0;
       return NTRU_OK;
+    case NTRU_OPT_DEC1_FORM:
+      if (value < 0 || value > 2) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_DEC1_FORM must be 0, 1 or 2");
+      ctx->opt_dec1_form = (int)value;
+      if (ctx->has_priv && ctx->tensor_ok) return umma_prepare_private(ctx);   // rebuild the operand matrix of f in the other form
+      return NTRU_OK;
     case NTRU_OPT_DR:
       // index.js:462-464
       if (value < 0 || 2 * value > ctx->N) return fail(ctx, NTRU_E_PARAM, "The total of 1s and -1s cannot exceed the array length.");
@@ -429,7 +464,7 @@ int ntru_set_private_key(ntru_ctx *ctx, const int8_t *f, const uint8_t *fp) {
 // ---- host-buffer entry points ---------------------------------------------------------------
 
 static int encrypt_host(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_t *r, const void *m, int m_wide,
-                        uint16_t *value, uint16_t *quo, uint16_t *rem, uint8_t *r_out) {
+                        uint16_t *value, uint16_t *quo, uint16_t *rem, uint8_t *r_out, bool fe = false) {
   int rc = check(ctx);
   if (rc) return rc;
   if (!m) return fail(ctx, NTRU_E_PARAM, "m is required");
@@ -443,7 +478,8 @@ static int encrypt_host(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_
   set_in(arr[0], h, 2, N);
   if (r) {
     set_in(arr[1], r, 1, N);
-    if (r_out && r_out != r) memcpy(r_out, r, B * N);   // injected r is echoed (inputs.r, index.js:97)
+    if (r_out && r_out != r)                             // injected r is echoed (inputs.r, index.js:97)
+      memcpy(r_out, r, fe ? B * (size_t)packed_elems(ctx->p - 1, (int)N) * 32 : B * N);
   } else {
     set_out(arr[1], r_out, 1, N);
     arr[1].used = true;                                  // device rows are needed even when r is not returned
@@ -452,6 +488,10 @@ static int encrypt_host(ntru_ctx *ctx, size_t B, const uint16_t *h, const uint8_
   set_out(arr[3], value, 2, N);
   set_out(arr[4], quo, 2, N + 1);
   set_out(arr[5], rem, 2, N + 1);
+  if (fe) {
+    set_fe(arr[1], (uint32_t)ctx->p - 1); set_fe(arr[2], (uint32_t)ctx->p - 1);
+    for (int a = 3; a <= 5; ++a) set_fe(arr[a], (uint32_t)ctx->q - 1);
+  }
   uint64_t next_row = ctx->rng_row;
   if (!r) ctx->rng_row += B;                             // a row number (nonce) is never used twice under one key
   return run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
@@ -482,7 +522,7 @@ int ntru_encrypt_batch_keys(ntru_ctx *ctx, size_t B, const uint16_t *h, const ui
 }
 
 static int decrypt_host(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t *fp, const uint16_t *e,
-                        uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2) {
+                        uint8_t *value, uint16_t *q1, uint16_t *r1, uint8_t *q2, uint8_t *r2, bool fe = false) {
   int rc = check(ctx);
   if (rc) return rc;
   if (!e) return fail(ctx, NTRU_E_PARAM, "e is required");
@@ -497,6 +537,10 @@ static int decrypt_host(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t 
   set_out(arr[5], r1, 2, N + 1);
   set_out(arr[6], q2, 1, N + 1);
   set_out(arr[7], r2, 1, N + 1);
+  if (fe) {
+    set_fe(arr[2], (uint32_t)ctx->q - 1); set_fe(arr[4], (uint32_t)ctx->q - 1); set_fe(arr[5], (uint32_t)ctx->q - 1);
+    set_fe(arr[3], (uint32_t)ctx->p - 1); set_fe(arr[6], (uint32_t)ctx->p - 1); set_fe(arr[7], (uint32_t)ctx->p - 1);
+  }
   return run_pipeline(ctx, B, arr, [&](size_t rows, void **dev) {
     return decrypt_dispatch(ctx, rows, (const int8_t *)dev[0], (const uint8_t *)dev[1], (const uint16_t *)dev[2],
                             (uint8_t *)dev[3], (uint16_t *)dev[4], (uint16_t *)dev[5], (uint8_t *)dev[6],
@@ -514,6 +558,23 @@ int ntru_decrypt_batch_keys(ntru_ctx *ctx, size_t B, const int8_t *f, const uint
                             uint8_t *remainder2) {
   if (!f || !fp) return fail(ctx, NTRU_E_PARAM, "f or fp is NULL");
   return decrypt_host(ctx, B, f, fp, e, value, quotient1, remainder1, quotient2, remainder2);
+}
+
+int ntru_packed_elems(const ntru_ctx *ctx, int mod_q, int width) {
+  if (!ctx || width < 0) return 0;
+  return packed_elems(mod_q ? (uint32_t)ctx->q - 1 : (uint32_t)ctx->p - 1, width);
+}
+
+int ntru_encrypt_batch_packed(ntru_ctx *ctx, size_t B, const void *r, const void *m, void *value, void *quotientE,
+                              void *remainderE, void *r_out) {
+  return encrypt_host(ctx, B, nullptr, (const uint8_t *)r, m, 0, (uint16_t *)value, (uint16_t *)quotientE, (uint16_t *)remainderE,
+                      (uint8_t *)r_out, true);
+}
+
+int ntru_decrypt_batch_packed(ntru_ctx *ctx, size_t B, const void *e, void *value, void *quotient1, void *remainder1,
+                              void *quotient2, void *remainder2) {
+  return decrypt_host(ctx, B, nullptr, nullptr, (const uint16_t *)e, (uint8_t *)value, (uint16_t *)quotient1, (uint16_t *)remainder1,
+                      (uint8_t *)quotient2, (uint8_t *)remainder2, true);
 }
 
 __global__ void k_scale_u16(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, size_t n, uint32_t mul) {
@@ -579,11 +640,6 @@ int ntru_keygen_batch(ntru_ctx *ctx, size_t B, const int8_t *f, const int8_t *g,
   return keygen_batch(ctx, B, f, g, fq, fp, h, valid);
 }
 
-static int bit_length(uint32_t v) {   // floor(log2(v) + 1) for v >= 1 (index.js:573, 601)
-  int b = 0;
-  while (v) { ++b; v >>= 1; }
-  return b;
-}
 
 int ntru_pack_geometry(uint32_t max_val, int data_len, int *max_input_bits, int *inputs_per_output, int *arr_len,
                        int *output_size) {

@@ -646,6 +646,49 @@ __global__ void k_unpack_fields(const uint32_t *__restrict__ data, size_t B, int
   }
 }
 
+// Wire form of unpackInput for the *_batch_packed entry points: B x in_elems field elements -> device rows of pitch P
+// whose first `width` columns are the coefficients (element i, position j -> column i n + j) and whose other columns
+// are zero.  packOutput pads a row to arrLen >= width coefficients (index.js:575-581): the padding must be zero, it is
+// not copied.  One thread per device column.
+template <typename T>
+__global__ void k_wire_unpack(const uint32_t *__restrict__ data, size_t B, int in_elems, int bits, int n, int width, int P,
+                              T *__restrict__ out) {
+  const size_t total = B * (size_t)P;
+  const uint32_t mask = (1u << bits) - 1u;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / P;
+    const int k = (int)(idx % P);
+    uint32_t v = 0;
+    if (k < width) {
+      const int i = k / n, j = k % n;
+      const uint32_t *el = data + (row * in_elems + i) * 8;
+      const int bit0 = j * bits, w = bit0 >> 5, sh = bit0 & 31;
+      uint64_t two = el[w];
+      if (sh + bits > 32) two |= (uint64_t)el[w + 1] << 32;     // w + 1 <= 7: n bits <= 252
+      v = (uint32_t)(two >> sh) & mask;
+    }
+    out[idx] = (T)v;
+  }
+}
+
+int launch_wire_unpack(ntru_ctx *ctx, size_t B, const uint32_t *data, int in_elems, int bits, int n, int width, void *out,
+                       int elem_bytes) {
+  if (B == 0) return NTRU_OK;
+  const size_t total = B * (size_t)ctx->P;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  {
+    LaunchTimer timer(ctx, NTRU_K_PACK);
+    if (elem_bytes == 2)
+      k_wire_unpack<uint16_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>(data, B, in_elems, bits, n, width, ctx->P, (uint16_t *)out);
+    else
+      k_wire_unpack<uint8_t><<<(unsigned)blocks, 256, 0, ctx->stream>>>(data, B, in_elems, bits, n, width, ctx->P, (uint8_t *)out);
+  }
+  NTRU_CUDA(ctx, cudaGetLastError());
+  return NTRU_OK;
+}
+
 // ---- pitch conversion for the host-buffer entry points --------------------------------------------
 // Host rows are packed (N or N+1 elements), device rows are pitched (P elements).  A 2-D DMA copy with ~1 KB
 // rows runs at a fraction of PCIe speed (measured 12 GB/s D2H), so the pipeline moves packed buffers with

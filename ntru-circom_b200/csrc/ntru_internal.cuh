@@ -41,6 +41,7 @@ struct KeyMatrix {
   DevBuf mat;            // [2 parts * nlimbs * covered columns][klen] bytes, K-major, tile-major per 128-byte K block
   alignas(64) unsigned char tmap_half[2][128];   // CUtensorMaps, box = half the B rows of a chunk of width w[i]
   bool ready = false;
+  bool f16 = false;      // DEC1F: 16-bit operands (the first decrypt product on kind::f16 tiles)
   int limbs = 0, nlimbs = 0, klen = 0, nchunks = 0;
   int col0[kMaxChunks + 1] = {};   // chunk c computes output columns [col0[c], col0[c+1])
   int w[2] = {0, 0};               // the (at most two) distinct chunk widths: first chunk's, last chunk's
@@ -73,6 +74,7 @@ struct ntru_ctx {
   uint32_t xchg_epoch = 0;
   size_t chunk_rows = 32768;
   int opt_path = 0;
+  int opt_dec1_form = 0;           // NTRU_OPT_DEC1_FORM: 0 auto, 1 byte limbs, 2 fp16 tiles (256 < q <= 2048 only)
   int umma_attr_set = 0;           // bit per kernel mode: dynamic shared memory attribute applied on this device
   bool sampler_attr_set = false;
   // device CSPRNG for r (ChaCha20, generic_kernels.cu): key words (little-endian), next unused row number (= nonce),
@@ -140,6 +142,8 @@ size_t xchg_window_bytes(const ntru_ctx *ctx, int world);
 int launch_sum_allreduce(ntru_ctx *ctx, size_t B, const uint16_t *e, uint16_t *out);
 int launch_xchg_partial(ntru_ctx *ctx, uint32_t *partial, uint16_t *out);   // exchange of already accumulated column sums
 int launch_sample_r(ntru_ctx *ctx, size_t B, int dr, uint64_t row0, uint8_t *r);
+int launch_wire_unpack(ntru_ctx *ctx, size_t B, const uint32_t *data, int in_elems, int bits, int n, int width, void *out,
+                       int elem_bytes);
 int launch_pack_fields(ntru_ctx *ctx, size_t B, const void *data, int elem_bytes, int data_len, size_t pitch, int bits, int n,
                        int out_elems, uint32_t *out);
 int launch_unpack_fields(ntru_ctx *ctx, size_t B, const uint32_t *data, int in_elems, int bits, int n, size_t pitch, void *out,

@@ -48,7 +48,13 @@ namespace ntru {
 
 namespace {
 
-enum Mode { ENC = 0, DEC1 = 1, DEC2 = 2 };
+// DEC1F: the first decrypt product for 256 < q <= 2048 on kind::f16 tiles.  A uint16 coefficient e < 2048 read as an fp16
+// bit pattern IS the number e * 2^-24 (the subnormals and the first normal binade of fp16 form one linear ramp), so the
+// caller's rows are the A operand as they lie in memory: no byte-limb transform, no transform warps, all sixteen warps
+// drain accumulators.  f is exact in fp16, every partial sum is a multiple of 2^-24 below 2^-2 and therefore exact in
+// the fp32 accumulators, and the integer comes back in the epilogue as the low bits of (acc + 0.75f).  The MMA work
+// and the operand bytes equal those of the two byte limbs (K = 16 per instruction instead of 32, two bytes per entry).
+enum Mode { ENC = 0, DEC1 = 1, DEC2 = 2, DEC1F = 3 };
 
 constexpr int kTileRows = 128;
 constexpr int kAtomK = 128;                      // bytes of K per pipeline slice (one 128B swizzle atom)
@@ -57,6 +63,7 @@ constexpr int kAccCols = 256;                    // TMEM columns per accumulator
 
 struct UmmaArgs {
   int N, P, Kp, atoms;
+  int ea;                 // coefficients per 128-byte K atom: 128 (byte operands), 64 (DEC1F: 16-bit operands)
   int k_last;             // 32-byte MMA steps of the last K atom that hold coefficients below N (1..4)
   int kl;                 // K limbs (DEC1 with q > 256: 2)
   int nl;                 // N limbs (ENC with q > 256: 2)
@@ -142,7 +149,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= col0[c] + 1
 __device__ __forceinline__ int first_atom(const UmmaArgs &a, int part_hi, int c) {
   if (!part_hi) return 0;
-  const int a0 = (a.col0[c] + 1) / kAtomK;
+  const int a0 = (a.col0[c] + 1) / a.ea;
   return a0 < a.atoms ? a0 : a.atoms - 1;
 }
 
@@ -172,7 +179,7 @@ __global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, const Ch
     const int off = rin - nl * ct.col0[c];
     const int ln = off / w, j = off % w;
     const int k = ct.col0[c] + j;
-    const int lk = kb / Kp, i = kb % Kp;
+    const int lk = kb / Kp, i = mode == DEC1F ? (kb % Kp) >> 1 : kb % Kp;   // DEC1F: two bytes per coefficient
     int coef = 0;
     bool nz = k < N && i < N;
     int src = 0;
@@ -187,12 +194,13 @@ __global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, const Ch
     }
     if (nz) {
       if (mode == ENC) coef = reinterpret_cast<const uint16_t *>(poly)[src];
-      else if (mode == DEC1) coef = reinterpret_cast<const int8_t *>(poly)[src];
+      else if (mode == DEC1 || mode == DEC1F) coef = reinterpret_cast<const int8_t *>(poly)[src];
       else coef = reinterpret_cast<const uint8_t *>(poly)[src];
     }
     uint8_t out;
     if (mode == ENC) out = ln == 0 ? (uint8_t)(coef & 0xff) : (uint8_t)(coef >> 8);
     else if (mode == DEC1) out = (uint8_t)(int8_t)(lk == 0 ? coef : coef * 64);
+    else if (mode == DEC1F) out = (kb & 1) ? (coef > 0 ? 0x3C : (coef < 0 ? 0xBC : 0)) : 0;   // fp16 +-1.0 = 0x3C00 / 0xBC00
     else out = (uint8_t)coef;
     // tile-major storage: for each 128-byte K block all rows are contiguous (128-byte pitch), so that the box
     // of one pipeline slice (half a chunk's rows x 128 B) is one contiguous run of global memory
@@ -226,11 +234,11 @@ void geometry(const ntru_ctx *ctx, int mode, int kl, int nl, KeyMatrix &km) {
   const int N = ctx->N;
   km.limbs = kl;
   km.nlimbs = nl;
-  const int Kp = ((N + kAtomK - 1) / kAtomK) * kAtomK;
+  const int Kp = (((mode == DEC1F ? 2 * N : N) + kAtomK - 1) / kAtomK) * kAtomK;   // bytes of K per limb
   km.klen = kl * Kp;
   const int max_out = mode == ENC ? 128 : 256 / nl;
   const bool pu1 = mode == ENC && Kp / kAtomK >= 5;          // launch_product's choice of the one-unit ENC instantiation
-  const int g = mode == ENC ? (pu1 ? 32 : 64) : (mode == DEC1 ? 32 : 128);
+  const int g = mode == ENC ? (pu1 ? 32 : 64) : (mode == DEC1 ? 32 : (mode == DEC1F ? 64 : 128));
   const int T = ((N + g - 1) / g) * g;
   km.nchunks = (T + max_out - 1) / max_out;
   const int base = (T / km.nchunks / g) * g;
@@ -310,7 +318,8 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     ctx->umma_attr_set |= 1 << MODE;
   }
   a.N = ctx->N; a.P = ctx->P; a.kl = km.limbs; a.nl = km.nlimbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
-  a.k_last = (ctx->N - (a.atoms - 1) * kAtomK + 31) / 32;
+  a.ea = MODE == DEC1F ? kAtomK / 2 : kAtomK;
+  a.k_last = (ctx->N - (a.atoms - 1) * a.ea + a.ea / 4 - 1) / (a.ea / 4);
   a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
   for (int c = 0; c <= kMaxChunks; ++c) a.col0[c] = c <= km.nchunks ? km.col0[c] : km.col0[km.nchunks];
   a.w0 = km.w[0];
@@ -346,7 +355,11 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   memset(tmO, 0, sizeof tmO);
   const uint64_t N = (uint64_t)ctx->N, P = (uint64_t)ctx->P;
   int rc;
-  if (MODE != DEC1) {
+  if (MODE == DEC1F) {
+    // the caller's uint16 rows ARE the fp16 operand: 64 coefficients (128 bytes) x 128 rows per slot, SWIZZLE_128B
+    rc = encode_2d_ex(ctx, &tmA, const_cast<void *>(a.a_src), 2, N, (uint64_t)a.B, P * 2, kAtomK / 2, kTileRows, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else if (MODE != DEC1) {
     // byte rows straight into the UMMA layout: inner extent N (columns beyond read as zero), row pitch P
     rc = encode_2d(ctx, &tmA, const_cast<void *>(a_bytes), N, (uint64_t)a.B, P, kAtomK, kTileRows);
     if (rc) return rc;
@@ -364,13 +377,14 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     void *optr[3];
     int oelem[3], obox[3];
     CUtensorMapSwizzle oswz[3];
-    if (MODE == ENC || MODE == DEC1) {
+    if (MODE == ENC || MODE == DEC1 || MODE == DEC1F) {
       const int ob = pu1 ? 16 : 32;
       const CUtensorMapSwizzle osw = pu1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
       optr[0] = a.o16_cyc; oelem[0] = 2; obox[0] = ob; oswz[0] = osw;
       optr[2] = a.o16_hi; oelem[2] = 2; obox[2] = ob; oswz[2] = osw;
       if (MODE == ENC) { optr[1] = a.o16_cyc2; oelem[1] = 2; obox[1] = ob; oswz[1] = osw; }
-      else { optr[1] = a.o8_cyc; oelem[1] = 1; obox[1] = 32; oswz[1] = CU_TENSOR_MAP_SWIZZLE_NONE; }
+      else if (MODE == DEC1) { optr[1] = a.o8_cyc; oelem[1] = 1; obox[1] = 32; oswz[1] = CU_TENSOR_MAP_SWIZZLE_NONE; }
+      else optr[1] = nullptr;                       // DEC1F stores b with plain 16-byte global stores (no staging slot for it)
     } else {
       optr[0] = a.o8_cyc; optr[1] = a.o8_cyc2; optr[2] = a.o8_hi;
       for (int i = 0; i < 3; ++i) { oelem[i] = 1; obox[i] = 64; oswz[i] = CU_TENSOR_MAP_SWIZZLE_64B; }
@@ -402,7 +416,7 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     }
   }
   {
-    LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC1 ? NTRU_K_DEC1_TENSOR : NTRU_K_DEC2_TENSOR));
+    LaunchTimer timer(ctx, MODE == ENC ? NTRU_K_ENC_TENSOR : (MODE == DEC2 ? NTRU_K_DEC2_TENSOR : NTRU_K_DEC1_TENSOR));
     const int clusters = a.npairs < ctx->sm_count / 2 ? a.npairs : ctx->sm_count / 2;
 #ifdef NTRU_TRACE
     const int dbg = getenv("NTRU_DEBUG_EPI") ? atoi(getenv("NTRU_DEBUG_EPI")) : 0;
@@ -423,9 +437,9 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     }
 #else
     if (pu1) {
-      if (!(ctx->umma_attr_set & 8)) {
+      if (!(ctx->umma_attr_set & 16)) {
         NTRU_CUDA(ctx, cudaFuncSetAttribute(k_umma_pair<ENC, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes));
-        ctx->umma_attr_set |= 8;
+        ctx->umma_attr_set |= 16;
       }
       k_umma_pair<ENC, 0, 1><<<2 * clusters, kPairThreads, kPairSmemBytes, ctx->stream>>>(a, tmB, tmB2, tmA, tmM, tmO[0], tmO[1], tmO[2]);
     } else {
@@ -465,7 +479,12 @@ int umma_prepare_public(ntru_ctx *ctx) {
 }
 
 int umma_prepare_private(ntru_ctx *ctx) {
-  int rc = build_keymat(ctx, DEC1, ctx->q > 256 ? 2 : 1, 1, ctx->d_f.ptr, ctx->km_f);
+  // 256 < q <= 2048: the fp16 form of the first product (a uint16 below 2048 is its own fp16 encoding, scaled by 2^-24)
+  // measured on B200 (profiles/r2_dec1_fp16_form.jsonl): faster above N = 512 (streamed A operand), slower up to it
+  const bool f16 = ctx->q > 256 && ctx->q <= 2048 && (ctx->opt_dec1_form == 2 || (ctx->opt_dec1_form == 0 && ctx->N > 512));
+  int rc = f16 ? build_keymat(ctx, DEC1F, 1, 1, ctx->d_f.ptr, ctx->km_f)
+               : build_keymat(ctx, DEC1, ctx->q > 256 ? 2 : 1, 1, ctx->d_f.ptr, ctx->km_f);
+  ctx->km_f.f16 = f16;
   if (rc) return rc;
   return build_keymat(ctx, DEC2, 1, 1, ctx->d_fp.ptr, ctx->km_fp);
 }
@@ -490,7 +509,7 @@ int umma_decrypt(ntru_ctx *ctx, size_t B, const uint16_t *e, uint8_t *value, uin
   a.B = B; a.a_src = e;
   a.with_hi = q1 != nullptr;
   a.o16_cyc = r1; a.o16_hi = q1; a.o8_cyc = (uint8_t *)ctx->d_b.ptr;
-  int rc = launch_product<DEC1>(ctx, ctx->km_f, a, nullptr);
+  int rc = ctx->km_f.f16 ? launch_product<DEC1F>(ctx, ctx->km_f, a, nullptr) : launch_product<DEC1>(ctx, ctx->km_f, a, nullptr);
   if (rc) return rc;
 #ifdef NTRU_TRACE
   if (getenv("NTRU_TRACE_DEC1_ONLY")) return NTRU_OK;   // leaves the DEC1 timeline in g_trace

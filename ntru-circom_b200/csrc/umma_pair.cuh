@@ -83,15 +83,26 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
       : "memory");
 }
-__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (F16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // arrives on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
@@ -127,6 +138,10 @@ __device__ __forceinline__ bool elect_one() {
 __host__ __device__ constexpr uint32_t make_idesc_pair(int a_signed, int b_signed, int n) {
   return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(256 >> 4) << 24);
+}
+// kind::f16: fp16 x fp16 (formats 0) into fp32 accumulators (format 1)
+__host__ __device__ constexpr uint32_t make_idesc_pair_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
 // DBG (timing experiments, instantiated in NTRU_TRACE builds only; results are then wrong on purpose):
@@ -294,7 +309,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 if (elect_one()) {
                   if (leader) mbar_arrive_expect_tx(a_full(sa), a_bytes);
                   else mbar_arrive_cluster(lead_a_full + 8u * sa);
-                  tma_load_2d_pair(a_slot(sa), &tmapA, at * kAtomK, a_row, lead_a_full + 8u * sa);
+                  tma_load_2d_pair(a_slot(sa), &tmapA, at * a.ea, a_row, lead_a_full + 8u * sa);
                 }
                 __syncwarp();
                 if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
@@ -344,7 +359,8 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           const int a0 = first_atom(a, hi, hi ? j - a.nchunks : j);
           const uint32_t nsl = (uint32_t)((a.atoms - a0) * a.kl);            // slices of this chunk
           const int cj = hi ? j - a.nchunks : j;
-          const uint32_t idesc = make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.nl * (a.col0[cj + 1] - a.col0[cj]));
+          const uint32_t idesc = MODE == DEC1F ? make_idesc_pair_f16(a.col0[cj + 1] - a.col0[cj])
+                                               : make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.nl * (a.col0[cj + 1] - a.col0[cj]));
           const uint32_t klast = (uint32_t)a.k_last, kl_u = (uint32_t)a.kl;
           // resident A slot sa is read again later in the tile iff the next chunk reads it: chunks read ever fewer
           // atoms (cyclic chunks read all, hi chunk c reads atoms >= a0(c), a0 non-decreasing)
@@ -374,10 +390,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             // the slices of the last K atom (one per K limb) hold coefficients below N only in their first k_last 32-byte steps
             const uint32_t nk = (nsl - i <= kl_u) ? klast : 4u;
             if (elect_one()) {
-              umma_i8_pair(d_tmem, da, db, idesc, accumulate);
-              if (nk > 1) umma_i8_pair(d_tmem, da + 2, db + 2, idesc, 1u);
-              if (nk > 2) umma_i8_pair(d_tmem, da + 4, db + 4, idesc, 1u);
-              if (nk > 3) umma_i8_pair(d_tmem, da + 6, db + 6, idesc, 1u);
+              umma_pair<MODE == DEC1F>(d_tmem, da, db, idesc, accumulate);
+              if (nk > 1) umma_pair<MODE == DEC1F>(d_tmem, da + 2, db + 2, idesc, 1u);
+              if (nk > 2) umma_pair<MODE == DEC1F>(d_tmem, da + 4, db + 4, idesc, 1u);
+              if (nk > 3) umma_pair<MODE == DEC1F>(d_tmem, da + 6, db + 6, idesc, 1u);
               umma_commit_pair(bempty0 + 8u * sb);
               if (sa < rel_lim) umma_commit_pair(aempty0 + 8u * sa);
               if (i == nsl - 1) umma_commit_pair(tfull);
@@ -679,6 +695,14 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 #pragma unroll
                   for (int i = 0; i < 16; ++i) acc[j][i] += acc1[j][i] << 8;
               }
+              if (MODE == DEC1F) {
+                // fp32 accumulator = S * 2^-24 with the integer |S| < 2^22: 0.75f + S ulps of the binade [0.5, 1) is the
+                // bit pattern 0x3F400000 + S, whose low 16 bits are S mod 2^16 (two's complement for negative S)
+#pragma unroll
+                for (int j = 0; j < kPassUnits; ++j)
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) acc[j][i] = __float_as_uint(__uint_as_float(acc[j][i]) + 0.75f);
+              }
             }
             if (last_pass) {
               tc_fence_before();
@@ -698,7 +722,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 #pragma unroll
             for (int j = 0; j < kPassUnits; ++j) {
               uint32_t (&w)[32] = acc[j];
-              if (MODE == ENC || MODE == DEC1) {
+              if (MODE == ENC || MODE == DEC1 || MODE == DEC1F) {
                 uint32_t *pk = res + 8 * j;
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) pk[jj] = __byte_perm(w[2 * jj], w[2 * jj + 1], 0x5410);
@@ -773,6 +797,19 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                 for (int j = 0; j < kPassUnits; ++j)
                   sts128(stage + 2048u + (uint32_t)lane * 32u + (uint32_t)j * 16u,
                          make_uint4(bres[4 * j], bres[4 * j + 1], bres[4 * j + 2], bres[4 * j + 3]));
+              }
+              if (MODE == DEC1F && !hi && a.o8_cyc) {
+                // b goes straight to global memory, 16 bytes per unit and lane (whole 32-byte sectors per pass): a
+                // staged tile for it would cost the third staging slot, i.e. a B-ring stage
+                const size_t grow = (size_t)(out_row + lane);
+                const int col = col0c + u0 * 16;
+                if (grow < a.B) {
+#pragma unroll
+                  for (int j = 0; j < kPassUnits; ++j)
+                    if (col + 16 * j < a.P)
+                      *reinterpret_cast<uint4 *>(a.o8_cyc + grow * (size_t)a.P + col + 16 * j) =
+                          make_uint4(bres[4 * j], bres[4 * j + 1], bres[4 * j + 2], bres[4 * j + 3]);
+                }
               }
             }
             if (lane == 0 && ew == 0) TRACE(2, 6, cc);

@@ -74,6 +74,10 @@ class Engine:
     def set_path(self, path: int):
         self.set_option(_lib.NTRU_OPT_PATH, path)
 
+    def set_dec1_form(self, form: int):
+        """tcgen05 schedule, first decrypt product at 256 < q <= 2048: 0 auto (fp16 above N = 512), 1 byte limbs, 2 fp16 tiles."""
+        self.set_option(_lib.NTRU_OPT_DEC1_FORM, int(form))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ntru_launch_count(self._h))
@@ -175,6 +179,53 @@ class Engine:
             rc = self.lib.ntru_decrypt_batch(self._h, B, _ptr(e), _ptr(value), _ptr(q1), _ptr(r1), _ptr(q2),
                                              _ptr(r2))
         self._check(rc)
+        return {"value": value, "quotient1": q1, "remainder1": r1, "quotient2": q2, "remainder2": r2}
+
+    # -- the same two calls with every array as BN254 field elements on the wire (packOutput form) ------------
+    def packed_elems(self, mod_q: bool, width: int) -> int:
+        """Field elements per row of an array of `width` coefficients: packOutput(q - 1 or p - 1, width, .).outputSize."""
+        return int(self.lib.ntru_packed_elems(self._h, 1 if mod_q else 0, int(width)))
+
+    def _fe(self, arr, mod_q, width, B):
+        return _host(np.ascontiguousarray(arr, dtype=np.uint32), np.uint32, (B, self.packed_elems(mod_q, width), 8))
+
+    def encrypt_batch_packed(self, r, m, *, witness=True, out=None, dr=None, return_r=False):
+        """encrypt_batch with r, m and every result as rows of field elements, (B, elems, 8) uint32 words:
+        row = packOutput(maxVal, width, coefficients).expected (index.js:572-596), maxVal = p - 1 for r / m and q - 1
+        for value / quotientE / remainderE.  Bits are packed and unpacked on the device."""
+        N = self.N
+        m = np.ascontiguousarray(m, dtype=np.uint32)
+        B = m.shape[0]
+        m = self._fe(m, False, N, B)
+        if r is not None:
+            r = self._fe(r, False, N, B)
+        elif dr is not None:
+            self.set_dr(dr)
+        out = out or {}
+        value = out.get("value", np.empty((B, self.packed_elems(True, N), 8), dtype=np.uint32))
+        quo = out.get("quotientE", np.empty((B, self.packed_elems(True, N + 1), 8), dtype=np.uint32)) if witness else None
+        rem = out.get("remainderE", np.empty((B, self.packed_elems(True, N + 1), 8), dtype=np.uint32)) if witness else None
+        r_out = out.get("r", np.empty((B, self.packed_elems(False, N), 8), dtype=np.uint32)) if (return_r or r is None) else None
+        self._check(self.lib.ntru_encrypt_batch_packed(self._h, B, _ptr(r), _ptr(m), _ptr(value), _ptr(quo), _ptr(rem), _ptr(r_out)))
+        res = {"value": value, "quotientE": quo, "remainderE": rem}
+        if r_out is not None:
+            res["r"] = r_out
+        return res
+
+    def decrypt_batch_packed(self, e, *, witness=True, out=None):
+        """decrypt_batch with e and every result as rows of field elements (maxVal = q - 1 for e / quotient1 /
+        remainder1, p - 1 for value / quotient2 / remainder2)."""
+        N = self.N
+        e = np.ascontiguousarray(e, dtype=np.uint32)
+        B = e.shape[0]
+        e = self._fe(e, True, N, B)
+        out = out or {}
+        value = out.get("value", np.empty((B, self.packed_elems(False, N), 8), dtype=np.uint32))
+        q1 = out.get("quotient1", np.empty((B, self.packed_elems(True, N + 1), 8), dtype=np.uint32)) if witness else None
+        r1 = out.get("remainder1", np.empty((B, self.packed_elems(True, N + 1), 8), dtype=np.uint32)) if witness else None
+        q2 = out.get("quotient2", np.empty((B, self.packed_elems(False, N + 1), 8), dtype=np.uint32)) if witness else None
+        r2 = out.get("remainder2", np.empty((B, self.packed_elems(False, N + 1), 8), dtype=np.uint32)) if witness else None
+        self._check(self.lib.ntru_decrypt_batch_packed(self._h, B, _ptr(e), _ptr(value), _ptr(q1), _ptr(r1), _ptr(q2), _ptr(r2)))
         return {"value": value, "quotient1": q1, "remainder1": r1, "quotient2": q2, "remainder2": r2}
 
     def verify_keys_batch(self, f, fq, fp, g):

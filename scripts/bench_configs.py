@@ -28,6 +28,8 @@ def setup(cfg):
     eng = nb.Engine(N, p, q, 0)
     eng.set_public_key(g["h"]); eng.set_private_key(g["f"], g["fp"])
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    if os.environ.get("DEC1_FORM"):                    # first decrypt product at q <= 2048: 0 auto, 1 byte limbs, 2 fp16 tiles
+        eng.set_dec1_form(int(os.environ["DEC1_FORM"]))
     return g, eng, N, q, dr
 
 

@@ -861,3 +861,105 @@ def test_host_buffer_pack_unpack_and_sum_allreduce(nb, engines, golden):
         e = rng.integers(0, q, size=(B, N)).astype(np.uint16)
         assert np.array_equal(eng.sum_allreduce(e), o.sum_batch(e, q) if B else np.zeros(N, dtype=np.uint16)), B
         assert np.array_equal(eng.sum(e), o.sum_batch(e, q) if B else np.zeros(N, dtype=np.uint16)), B
+
+
+@pytest.mark.parametrize("key", ["random", "all_plus", "all_minus"])
+@pytest.mark.parametrize("N,q", [(191, 512), (193, 1024), (509, 2048), (512, 2048), (513, 2048), (677, 2048), (1024, 2048)])
+def test_first_decrypt_product_fp16_form(N, q, key, nb):
+    """256 < q <= 2048: the tcgen05 schedule runs the first decrypt product on kind::f16 tiles (the caller's uint16
+    coefficients are their own fp16 encodings, scaled by 2^-24; umma_kernels.cu, DEC1F).  Checked against the byte-limb
+    int8 form bit for bit (pad columns included) on uniformly random ciphertext rows over several tiles per CTA pair, and
+    against the oracle on rows that drive the fp32 accumulators to their largest magnitude (e = q - 1 everywhere under
+    f = +1 / -1 everywhere: |sum| = N (q - 1)), i.e. exactness of the subnormal inputs and of the accumulation."""
+    torch = pytest.importorskip("torch")
+    p, dev = 3, "cuda"
+    rng = np.random.default_rng(31 * N + q)
+    f = {"random": rng.integers(-1, 2, size=N), "all_plus": np.ones(N, dtype=np.int64), "all_minus": -np.ones(N, dtype=np.int64)}[key]
+    fp = rng.integers(0, p, size=N)
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_private_key(f.astype(np.int8), fp.astype(np.uint8))
+    eng.set_path(nb.PATH_TENSOR)
+    P, B = eng.pitch, 74 * 256 * 2 + 77
+    gen = torch.Generator(device=dev).manual_seed(N + q)
+    e = torch.zeros((B, P), dtype=torch.int16, device=dev)
+    e[:, :N] = torch.randint(0, q, (B, N), generator=gen, device=dev, dtype=torch.int16)
+    e[0, :N] = q - 1
+    e[1, :N] = 0
+    e[2, :N:2] = q - 1
+    e[3, :N] = 1
+    e[B - 1, :N] = q - 1
+    outs = []
+    for form in (2, 1):
+        eng.set_dec1_form(form)
+        bufs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(2)] + \
+               [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+        q1, r1, pv, q2 = bufs
+        eng.decrypt_dev(B, e, value=pv, quotient1=q1, remainder1=r1, quotient2=q2)
+        eng.sync()
+        outs.append(bufs)
+    for x, y in zip(*outs):
+        assert torch.equal(x, y), (N, q, key)
+    idx = [0, 1, 2, 3, 255, 256, 74 * 256 + 5, B - 1]
+    want = o.decrypt_batch(f, fp, e[idx, :N].cpu().numpy().view(np.uint16).astype(np.int64), q, p)
+    q1, r1, pv, q2 = outs[0]
+    assert np.array_equal(r1[idx].cpu().numpy().view(np.uint16)[:, : N + 1], want["remainder1"])
+    assert np.array_equal(q1[idx].cpu().numpy().view(np.uint16)[:, : N + 1], want["quotient1"])
+    assert np.array_equal(pv[idx].cpu().numpy()[:, :N], want["value"])
+    assert np.array_equal(q2[idx].cpu().numpy()[:, : N + 1], want["quotient2"])
+    eng.close()
+
+
+@pytest.mark.parametrize("cfg,B", [("default167", 333), ("hps509", 70001), ("hps821", 4500), ("hrss701", 1031)])
+def test_field_element_wire_format(cfg, B, nb, engines, golden):
+    """ntru_encrypt_batch_packed / ntru_decrypt_batch_packed: every array crosses the host link as
+    packOutput(maxVal, width, row).expected (index.js:572-596; maxVal = q - 1 modulo q, p - 1 for the small arrays).
+    Rows are checked against the oracle's BigInt packOutput of the oracle's own encrypt / decrypt results; the whole
+    batch (70001 rows = three pipeline chunks, ragged) against the plain-array calls through the numpy form of the
+    packing that tests/test_host.py pins to the oracle.  Includes r drawn on the device and NULL outputs."""
+    g, eng = golden(cfg), engines(cfg)
+    N, q, p, dr = int(g["N"]), int(g["q"]), int(g["p"]), int(g["dr"])
+    rng = np.random.default_rng(B)
+    r = o.sample_ternary_rows(B, N, dr, dr, rng).astype(np.uint8)
+    m = rng.integers(0, 2, size=(B, N)).astype(np.uint8)
+    w = nb.wire
+    eng.set_path(nb.PATH_AUTO)
+    plain = eng.encrypt_batch(r, m)
+    enc = eng.encrypt_batch_packed(w.pack_rows(p - 1, r), w.pack_rows(p - 1, m), return_r=True)
+    for k in ENC_KEYS:
+        assert np.array_equal(enc[k], w.pack_rows(q - 1, plain[k])), k
+    assert np.array_equal(enc["r"], w.pack_rows(p - 1, r))
+    dplain = eng.decrypt_batch(plain["value"])
+    dec = eng.decrypt_batch_packed(enc["value"])
+    for k in DEC_KEYS:
+        assert np.array_equal(dec[k], w.pack_rows(p - 1 if k in ("value", "quotient2", "remainder2") else q - 1, dplain[k])), k
+    # (not compared with m: at q = 4096 with the golden dr the centred lift wraps for some rows, in the reference too)
+    assert np.array_equal(w.unpack_rows(p - 1, N, dec["value"], np.uint8), dplain["value"])
+    # straight against the oracle, BigInt for BigInt
+    idx = [0, 1, B // 2, B - 1]
+    want_e = o.encrypt_batch(g["h"].astype(np.int64), r[idx], m[idx], q)
+    want_d = o.decrypt_batch(g["f"].astype(np.int64), g["fp"].astype(np.int64), want_e["value"], q, p)
+
+    def big(words):
+        return [sum(int(words[e, x]) << (32 * x) for x in range(8)) for e in range(words.shape[0])]
+
+    for i, b in enumerate(idx):
+        for k in ENC_KEYS:
+            row = [int(x) for x in want_e[k][i]]
+            assert big(enc[k][b]) == o.pack_output(q - 1, len(row), row)["expected"], (k, b)
+        for k in DEC_KEYS:
+            row = [int(x) for x in want_d[k][i]]
+            mv = p - 1 if k in ("value", "quotient2", "remainder2") else q - 1
+            assert big(dec[k][b]) == o.pack_output(mv, len(row), row)["expected"], (k, b)
+    # value only (NULL witness pointers), and r drawn on the device: r_out is the packed form of the rows the plain call
+    # draws under the same key and row numbers
+    v_only = eng.encrypt_batch_packed(w.pack_rows(p - 1, r[:300]), w.pack_rows(p - 1, m[:300]), witness=False)
+    assert v_only["quotientE"] is None and np.array_equal(v_only["value"], enc["value"][:300])
+    key = bytes(range(32))
+    eng.set_rng_key(key, 1000)
+    a = eng.encrypt_batch(None, m[:300], dr=dr)
+    eng.set_rng_key(key, 1000)
+    bpk = eng.encrypt_batch_packed(None, w.pack_rows(p - 1, m[:300]), dr=dr)
+    assert np.array_equal(bpk["r"], w.pack_rows(p - 1, a["r"])) and np.array_equal(bpk["value"], w.pack_rows(q - 1, a["value"]))
+    with pytest.raises(IndexError):
+        eng.encrypt_batch_packed(w.pack_rows(p - 1, r[:4]), w.pack_rows(q - 1, m[:4].astype(np.uint16) * 0 + 5))   # wrong element count

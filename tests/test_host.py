@@ -63,6 +63,34 @@ def test_napi_shim_type_checks_and_binds_every_host_buffer_entry_point():
     assert "Uint16Array.from(red)" in js and "Uint8Array.from(mExp" not in js
 
 
+def test_wire_helpers_match_pack_output_and_unpack_input():
+    """The numpy forms of the field-element wire format (ntru_circom_b200.wire) against the oracle's BigInt restatement
+    of packOutput / unpackInput (index.js:572-620) at every bit width the engine uses, widths N and N + 1, including the
+    three-element minimum."""
+    rng = np.random.default_rng(5)
+    for max_val, width in [(127, 167), (127, 168), (2047, 509), (2047, 510), (4095, 821), (8191, 702), (2, 509), (2, 510),
+                           (2, 167), (2, 1025), (2047, 20), (1, 509)]:
+        bits, n, elems = nb.wire.geometry(max_val, width)
+        rows = rng.integers(0, max_val + 1, size=(5, width))
+        rows[0] = max_val
+        rows[1] = 0
+        packed = nb.wire.pack_rows(max_val, rows)
+        assert packed.shape == (5, elems, 8)
+        for b in range(5):
+            want = o.pack_output(max_val, width, [int(x) for x in rows[b]])
+            assert want["outputSize"] == elems and want["maxInputBits"] == bits
+            got = [sum(int(packed[b, e, w]) << (32 * w) for w in range(8)) for e in range(elems)]
+            assert got == want["expected"], (max_val, width, b)
+            un = o.unpack_input(max_val, n * bits, want["expected"])
+            back = nb.wire.unpack_rows(max_val, width, packed[b:b + 1])[0]
+            assert o.trim_polynomial([int(x) for x in back]) == un["unpacked"]
+            assert np.array_equal(back, rows[b])
+    with pytest.raises(ValueError):
+        nb.wire.pack_rows(2, np.array([[3]]) + 1)                  # 4 does not fit two bits
+    with pytest.raises(IndexError):
+        nb.wire.unpack_rows(2047, 509, np.zeros((1, 23, 8), dtype=np.uint32))
+
+
 def test_shipped_library_reads_no_debug_environment_switches():
     """The timing experiments (NTRU_DEBUG_*: skip loads / stores, results wrong on purpose) exist in NTRU_TRACE builds
     only; a stray environment variable cannot change what the shipped library computes."""
