@@ -63,7 +63,7 @@ constexpr int kAccCols = 256;                    // TMEM columns per accumulator
 
 struct UmmaArgs {
   int N, P, Kp, atoms;
-  int ea;                 // coefficients per 128-byte K atom: 128 (byte operands), 64 (DEC1F: 16-bit operands)
+  int ea, ea_shift;       // coefficients per 128-byte K atom and its log2: 128 (byte operands), 64 (DEC1F: 16-bit operands)
   int k_last;             // 32-byte MMA steps of the last K atom that hold coefficients below N (1..4)
   int kl;                 // K limbs (DEC1 with q > 256: 2)
   int nl;                 // N limbs (ENC with q > 256: 2)
@@ -149,7 +149,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= col0[c] + 1
 __device__ __forceinline__ int first_atom(const UmmaArgs &a, int part_hi, int c) {
   if (!part_hi) return 0;
-  const int a0 = (a.col0[c] + 1) / a.ea;
+  const int a0 = (a.col0[c] + 1) >> a.ea_shift;
   return a0 < a.atoms ? a0 : a.atoms - 1;
 }
 
@@ -319,6 +319,7 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   }
   a.N = ctx->N; a.P = ctx->P; a.kl = km.limbs; a.nl = km.nlimbs; a.Kp = km.klen / km.limbs; a.atoms = a.Kp / kAtomK;
   a.ea = MODE == DEC1F ? kAtomK / 2 : kAtomK;
+  a.ea_shift = MODE == DEC1F ? 6 : 7;
   a.k_last = (ctx->N - (a.atoms - 1) * a.ea + a.ea / 4 - 1) / (a.ea / 4);
   a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
   for (int c = 0; c <= kMaxChunks; ++c) a.col0[c] = c <= km.nchunks ? km.col0[c] : km.col0[km.nchunks];
