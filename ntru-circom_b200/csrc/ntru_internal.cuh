@@ -38,7 +38,7 @@ constexpr int kMaxChunks = 8;   // accumulator chunks per product and part (ENC 
 
 // Operand matrices of the tcgen05 schedule for one fixed key polynomial (see umma_kernels.cu).
 struct KeyMatrix {
-  DevBuf mat;            // [2 parts * nlimbs * covered columns][klen] bytes, K-major, tile-major per 128-byte K block
+  DevBuf mat;            // [3 parts (cyc, hi, lo) * nlimbs * covered columns][klen] bytes, K-major, tile-major per 128-byte K block
   alignas(64) unsigned char tmap_half[2][128];   // CUtensorMaps, box = half the B rows of a chunk of width w[i]
   bool ready = false;
   bool f16 = false;      // DEC1F: 16-bit operands (the first decrypt product on kind::f16 tiles)
@@ -74,6 +74,7 @@ struct ntru_ctx {
   uint32_t xchg_epoch = 0;
   size_t chunk_rows = 32768;
   int opt_path = 0;
+  int opt_lohi = 0;                // NTRU_OPT_SCHEDULE: 0 = lo + hi phases (default), 1 = the cyc + hi order of round 1
   int opt_dec1_form = 0;           // NTRU_OPT_DEC1_FORM: 0 auto, 1 byte limbs, 2 fp16 tiles (256 < q <= 2048 only)
   int umma_attr_set = 0;           // bit per kernel mode: dynamic shared memory attribute applied on this device
   bool sampler_attr_set = false;

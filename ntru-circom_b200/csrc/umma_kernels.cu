@@ -61,7 +61,27 @@ constexpr int kAtomK = 128;                      // bytes of K per pipeline slic
 constexpr int kABytes = kTileRows * kAtomK;      // 16 KB
 constexpr int kAccCols = 256;                    // TMEM columns per accumulator buffer
 
+// One tile (256 rows of a CTA pair) is a list of PHASES, each a run of MMAs into one TMEM accumulator buffer followed by
+// one epilogue read of it; phase j of a tile uses buffer (running phase count) & 1.
+//   PH_CYC: the cyclic matrix over every K atom, fresh accumulator           -> remainder epilogue
+//   PH_HI : the hi matrix over the atoms that hold i > k, fresh accumulator   -> quotient epilogue
+//   PH_LO : the lo matrix (i <= k) over the atoms up to the chunk's last column, ACCUMULATED ON TOP of the hi product the
+//           same buffer still holds (cyc = lo + hi; the quotient epilogue only read it)  -> remainder epilogue
+// With the quotient witness, chunks are taken in pairs [HI a, HI b, LO a, LO b] (two buffers in flight; a LO phase finds
+// its HI product two phases back in the same buffer): lo + hi is N^2 + the diagonal blocks instead of the 1.5 N^2 of
+// cyc + hi -- 12 instead of 14 slices per tile and K limb at N = 509, 35 instead of 44 at N = 821.  An odd last chunk
+// runs [CYC, HI] (its lo product spans every atom anyway).  Without the witness: [CYC ...] only.
+constexpr int kMaxPhases = 2 * kMaxChunks;
+enum PhaseKind { PH_CYC = 0, PH_HI = 1, PH_LO = 2 };
+struct Phase {
+  int8_t c, kind, a0, a1;   // chunk, kind, K atoms [a0, a1)
+  uint16_t first, rel;      // resident A operand: atoms whose first / last read of the tile happens in this phase
+};
+
 struct UmmaArgs {
+  int nph;                // phases per tile
+  Phase ph[kMaxPhases];
+  int8_t a_order[16];     // resident A operand: the K atoms in the order of their first use in a tile
   int N, P, Kp, atoms;
   int ea, ea_shift;       // coefficients per 128-byte K atom and its log2: 128 (byte operands), 64 (DEC1F: 16-bit operands)
   int k_last;             // 32-byte MMA steps of the last K atom that hold coefficients below N (1..4)
@@ -81,7 +101,7 @@ struct UmmaArgs {
   int a_rel;              // commits that free an A slot: 2 (both MMA issuers) for resident A, else 1
   int two_issuers;        // second MMA issuer warp enabled (needs slices per chunk < B ring stages)
   int debug_flags;        // NTRU_TRACE builds only (NTRU_DEBUG_NOB: bit 0 = skip the B operand loads)
-  int mat_rows;           // rows of the key matrix (2 parts * nl * covered columns); K block kb starts at row kb * mat_rows
+  int mat_rows;           // rows of the key matrix (3 parts * nl * covered columns); K block kb starts at row kb * mat_rows
   int out_mask;           // which outputs exist: bit0 = cyc #1, bit1 = cyc #2, bit2 = hi
   const void *a_src;      // DEC1: e rows (uint16), pitch P elements
   const uint8_t *m;       // ENC: message rows
@@ -146,17 +166,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// first 128-byte K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= col0[c] + 1
-__device__ __forceinline__ int first_atom(const UmmaArgs &a, int part_hi, int c) {
-  if (!part_hi) return 0;
-  const int a0 = (a.col0[c] + 1) >> a.ea_shift;
-  return a0 < a.atoms ? a0 : a.atoms - 1;
-}
-
 #include "umma_pair.cuh"
 
 // ---- key matrix ---------------------------------------------------------------------------------
-// Mat[row][kb]: row = part * (nl * T) + nl * col0[c] + ln * w_c + j   (part 0 = cyc, 1 = hi; output k = col0[c] + j,
+// Mat[row][kb]: row = part * (nl * T) + nl * col0[c] + ln * w_c + j   (part 0 = cyc, 1 = hi, 2 = lo; output k = col0[c] + j,
 //               w_c = width of chunk c, T = col0[nchunks] = covered columns),   kb = lk * Kp + i.
 struct ChunkTable {
   int nchunks;
@@ -166,7 +179,7 @@ struct ChunkTable {
 __global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, const ChunkTable ct, const void *poly, uint8_t *mat) {
   const int klen = kl * Kp;
   const int T = ct.col0[ct.nchunks];
-  const size_t rows_total = (size_t)2 * nl * T;
+  const size_t rows_total = (size_t)3 * nl * T;
   const size_t total = rows_total * klen;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int kb = (int)(idx % klen);
@@ -184,12 +197,13 @@ __global__ void k_build_keymat(int mode, int N, int Kp, int kl, int nl, const Ch
     bool nz = k < N && i < N;
     int src = 0;
     if (nz) {
-      if (part == 0) {
-        src = k - i;
-        if (src < 0) src += N;
-      } else {
+      if (part == PH_HI) {
         nz = i > k;
         src = k + N - i;
+      } else {
+        nz = part == PH_CYC || i <= k;
+        src = k - i;
+        if (src < 0) src += N;
       }
     }
     if (nz) {
@@ -288,7 +302,7 @@ int encode_2d(ntru_ctx *ctx, void *out, void *base, uint64_t inner, uint64_t row
 int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyMatrix &km) {
   geometry(ctx, mode, kl, nl, km);
   const int T = km.col0[km.nchunks];
-  const int rows = 2 * nl * T;
+  const int rows = 3 * nl * T;
   const int Kp = km.klen / kl;
   const size_t bytes = (size_t)rows * km.klen;
   NTRU_CUDA(ctx, km.mat.reserve(bytes));
@@ -311,6 +325,47 @@ int build_keymat(ntru_ctx *ctx, int mode, int kl, int nl, const void *poly, KeyM
   return NTRU_OK;
 }
 
+// The phase list of one tile (see struct Phase).  lohi = false: the round-1 order [CYC of every chunk, HI of every chunk].
+void build_schedule(UmmaArgs &a, bool lohi) {
+  auto hi_a0 = [&](int c) {   // first K atom that can hold a non-zero entry of the hi matrix for chunk c: i >= col0[c] + 1
+    const int v = (a.col0[c] + 1) >> a.ea_shift;
+    return v < a.atoms ? v : a.atoms - 1;
+  };
+  auto lo_a1 = [&](int c) {   // one past the last K atom of the lo matrix: i <= k <= min(col0[c + 1], N) - 1
+    const int last = (a.col0[c + 1] < a.N ? a.col0[c + 1] : a.N) - 1;
+    return (last >> a.ea_shift) + 1;
+  };
+  a.nph = 0;
+  auto push = [&](int c, int kind) {
+    Phase &p = a.ph[a.nph++];
+    p.c = (int8_t)c; p.kind = (int8_t)kind;
+    p.a0 = (int8_t)(kind == PH_HI ? hi_a0(c) : 0);
+    p.a1 = (int8_t)(kind == PH_LO ? lo_a1(c) : a.atoms);
+    p.first = p.rel = 0;
+  };
+  if (!a.with_hi) {
+    for (int c = 0; c < a.nchunks; ++c) push(c, PH_CYC);
+  } else if (!lohi) {
+    for (int c = 0; c < a.nchunks; ++c) push(c, PH_CYC);
+    for (int c = 0; c < a.nchunks; ++c) push(c, PH_HI);
+  } else {
+    // from the last chunk down: the phases at the end of a tile read the low atoms only, so the high atoms of a resident
+    // A operand are released early -- and the next tile starts with the chunks that need exactly those
+    int c = a.nchunks - 1;
+    if (a.nchunks & 1) { push(c, PH_CYC); push(c, PH_HI); --c; }
+    for (; c >= 1; c -= 2) { push(c, PH_HI); push(c - 1, PH_HI); push(c, PH_LO); push(c - 1, PH_LO); }
+  }
+  uint32_t seen = 0;
+  int no = 0;
+  for (int j = 0; j < a.nph; ++j)
+    for (int at = a.ph[j].a0; at < a.ph[j].a1; ++at)
+      if (!(seen >> at & 1u)) { seen |= 1u << at; a.ph[j].first |= (uint16_t)(1u << at); if (no < 16) a.a_order[no++] = (int8_t)at; }
+  seen = 0;
+  for (int j = a.nph - 1; j >= 0; --j)
+    for (int at = a.ph[j].a0; at < a.ph[j].a1; ++at)
+      if (!(seen >> at & 1u)) { seen |= 1u << at; a.ph[j].rel |= (uint16_t)(1u << at); }
+}
+
 template <int MODE>
 int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *a_bytes) {
   if (!(ctx->umma_attr_set & (1 << MODE))) {      // per context: function attributes are per device
@@ -324,7 +379,8 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   a.nchunks = km.nchunks; a.q = ctx->q; a.qmask = (uint32_t)ctx->q - 1;
   for (int c = 0; c <= kMaxChunks; ++c) a.col0[c] = c <= km.nchunks ? km.col0[c] : km.col0[km.nchunks];
   a.w0 = km.w[0];
-  a.mat_rows = 2 * a.nl * a.col0[a.nchunks];
+  a.mat_rows = 3 * a.nl * a.col0[a.nchunks];
+  build_schedule(a, ctx->opt_lohi == 0);
   a.npairs = (int)((a.B + 2 * kTileRows - 1) / (2 * kTileRows));
   a.nS = 2;
   a.nM = MODE == ENC ? 2 : 0;

@@ -224,38 +224,35 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     // message loads depend on epilogue progress and live in their own warp (below), otherwise a late epilogue
     // delays the B loads of the next chunk and MMA, epilogue and loads run one after the other (clock trace).
     const uint32_t lead_b_full = lead(b_full(0));
-    const int part_rows = a.mat_rows >> 1;                 // key-matrix rows of one part (cyc / hi)
-    const int parts = a.with_hi ? 2 : 1;
+    const int part_rows = a.mat_rows / 3;                  // key-matrix rows of one part (cyc / hi / lo)
     uint32_t sb = 0, b_par = 0;
     if (lane == 0) { TRACE(3, 10, 0); TRACE_NS(3, 11, 0); }
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
-      for (int part = 0; part < parts; ++part) {
-        const int hi = part == 1;
-        for (int c = 0; c < a.nchunks; ++c) {
-          const int a0 = first_atom(a, hi, c);
-          const int wc = a.col0[c + 1] - a.col0[c];
-          const int half_rows = (a.nl * wc) >> 1;            // B rows of this chunk that this CTA loads
-          const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK;
-          const CUtensorMap *bmap = wc == a.w0 ? &tmapB : &tmapB2;   // box rows = half_rows
-          const int row0 = hi * part_rows + a.nl * a.col0[c] + (int)rank * half_rows;
-          for (int at = a0; at < a.atoms; ++at) {
-            for (int lk = 0; lk < a.kl; ++lk) {
-              mbar_wait(b_empty(sb), b_par ^ 1);
-              if (elect_one()) {
+      for (int j = 0; j < a.nph; ++j) {
+        const Phase ph = a.ph[j];
+        const int c = ph.c;
+        const int wc = a.col0[c + 1] - a.col0[c];
+        const int half_rows = (a.nl * wc) >> 1;            // B rows of this chunk that this CTA loads
+        const uint32_t b_bytes = 2u * (uint32_t)half_rows * kAtomK;
+        const CUtensorMap *bmap = wc == a.w0 ? &tmapB : &tmapB2;   // box rows = half_rows
+        const int row0 = ph.kind * part_rows + a.nl * a.col0[c] + (int)rank * half_rows;
+        for (int at = ph.a0; at < ph.a1; ++at) {
+          for (int lk = 0; lk < a.kl; ++lk) {
+            mbar_wait(b_empty(sb), b_par ^ 1);
+            if (elect_one()) {
 #ifdef NTRU_TRACE
-                if (a.debug_flags & 1) {   // timing experiment: no B traffic at all (operands are stale shared memory)
-                  if (leader) mbar_arrive(b_full(sb)); else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                } else
+              if (a.debug_flags & 1) {   // timing experiment: no B traffic at all (operands are stale shared memory)
+                if (leader) mbar_arrive(b_full(sb)); else mbar_arrive_cluster(lead_b_full + 8u * sb);
+              } else
 #endif
-                {
-                  if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
-                  else mbar_arrive_cluster(lead_b_full + 8u * sb);
-                  tma_load_2d_pair(b_slot(sb), bmap, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
-                }
+              {
+                if (leader) mbar_arrive_expect_tx(b_full(sb), b_bytes);
+                else mbar_arrive_cluster(lead_b_full + 8u * sb);
+                tma_load_2d_pair(b_slot(sb), bmap, 0, (lk * a.atoms + at) * a.mat_rows + row0, lead_b_full + 8u * sb);
               }
-              __syncwarp();
-              if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
             }
+            __syncwarp();
+            if (++sb == (uint32_t)a.nB) { sb = 0; b_par ^= 1; }
           }
         }
       }
@@ -269,23 +266,21 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         // will hold its two byte limbs; the transform warps rewrite it in place.  TMA keeps nA / 2 atoms in flight,
         // which the register prefetch of the transform warps (one atom) could not: a clock trace showed 2000-2500
         // cycles per atom, load latency, against the 1024 cycles of MMA work an atom feeds.
-        const int parts = a.with_hi ? 2 : 1;
         const uint32_t np = (uint32_t)a.nA >> 1;
         uint32_t pj = 0, par = 0;
         for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
           const int a_row = T * 256 + (int)rank * kTileRows;
-          for (int part = 0; part < parts; ++part) {
-            for (int c = 0; c < a.nchunks; ++c) {
-              for (int at = first_atom(a, part == 1, c); at < a.atoms; ++at) {
-                mbar_wait(a_empty(2 * pj), par ^ 1);
-                mbar_wait(a_empty(2 * pj + 1), par ^ 1);
-                if (elect_one()) {
-                  mbar_arrive_expect_tx(a_full(a.nA + pj), 2u * kABytes);
-                  tma_load_2d(a_slot(2 * pj), &tmapA, at * kAtomK, a_row, a_full(a.nA + pj));
-                }
-                __syncwarp();
-                if (++pj == np) { pj = 0; par ^= 1; }
+          for (int j = 0; j < a.nph; ++j) {
+            const int at1 = a.ph[j].a1;
+            for (int at = a.ph[j].a0; at < at1; ++at) {
+              mbar_wait(a_empty(2 * pj), par ^ 1);
+              mbar_wait(a_empty(2 * pj + 1), par ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(a_full(a.nA + pj), 2u * kABytes);
+                tma_load_2d(a_slot(2 * pj), &tmapA, at * kAtomK, a_row, a_full(a.nA + pj));
               }
+              __syncwarp();
+              if (++pj == np) { pj = 0; par ^= 1; }
             }
           }
         }
@@ -293,38 +288,39 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     } else {
       const uint32_t a_bytes = 2u * kABytes;
       const uint32_t lead_a_full = lead(a_full(0));
-      const int parts = a.with_hi ? 2 : 1;
       const bool resident = a.a_resident != 0;
       uint32_t sas = 0, a_par_s = 0, t_par = 0, mc = 0;
+      auto load_a = [&](uint32_t sa, uint32_t par, int at, int a_row) {
+        mbar_wait(a_empty(sa), par ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(a_full(sa), a_bytes);
+          else mbar_arrive_cluster(lead_a_full + 8u * sa);
+          tma_load_2d_pair(a_slot(sa), &tmapA, at * a.ea, a_row, lead_a_full + 8u * sa);
+        }
+        __syncwarp();
+      };
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         const int a_row = T * 256 + (int)rank * kTileRows;
-        for (int part = 0; part < parts; ++part) {
-          const int hi = part == 1;
-          for (int c = 0; c < a.nchunks; ++c) {
-            const int a0 = first_atom(a, hi, c);
-            if (!resident || (part == 0 && c == 0)) {
-              for (int at = a0; at < a.atoms; ++at) {
-                const uint32_t sa = resident ? (uint32_t)at : sas;      // kl == 1 in these modes
-                mbar_wait(a_empty(sa), (resident ? t_par : a_par_s) ^ 1);
-                if (elect_one()) {
-                  if (leader) mbar_arrive_expect_tx(a_full(sa), a_bytes);
-                  else mbar_arrive_cluster(lead_a_full + 8u * sa);
-                  tma_load_2d_pair(a_slot(sa), &tmapA, at * a.ea, a_row, lead_a_full + 8u * sa);
-                }
-                __syncwarp();
-                if (!resident && ++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
-              }
+        if (resident) {                                       // the whole tile once, atoms in the order of their first use (kl == 1 here)
+          for (int k = 0; k < a.atoms; ++k) load_a((uint32_t)a.a_order[k], t_par, a.a_order[k], a_row);
+        }
+        for (int j = 0; j < a.nph; ++j) {
+          const Phase ph = a.ph[j];
+          if (!resident) {
+            for (int at = ph.a0; at < ph.a1; ++at) {
+              load_a(sas, a_par_s, at, a_row);
+              if (++sas == (uint32_t)a.nA) { sas = 0; a_par_s ^= 1; }
             }
-            if (MODE == ENC && PU != 1 && !hi) {   // the chunk's 128 message bytes per row, for this CTA's epilogue
-              const uint32_t ms = mc & 1;
-              mbar_wait(m_empty(ms), ((mc >> 1) & 1) ^ 1);
-              if (elect_one()) {
-                mbar_arrive_expect_tx(m_full(ms), kABytes);
-                tma_load_2d(m_slot(ms), &tmapM, a.col0[c], a_row, m_full(ms));
-              }
-              __syncwarp();
-              ++mc;
+          }
+          if (MODE == ENC && PU != 1 && ph.kind != PH_HI) {   // the chunk's 128 message bytes per row, for this CTA's epilogue
+            const uint32_t ms = mc & 1;
+            mbar_wait(m_empty(ms), ((mc >> 1) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(m_full(ms), kABytes);
+              tma_load_2d(m_slot(ms), &tmapM, a.col0[ph.c], a_row, m_full(ms));
             }
+            __syncwarp();
+            ++mc;
           }
         }
       }
@@ -346,41 +342,34 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       // Slices of a chunk use consecutive resident A slots: sa = (first atom) * kl + i.
       const uint64_t desc_hi = make_smem_desc(0) & ~0x3FFFull;             // everything but the start address
       const uint32_t a_lo0 = smem_base >> 4, b_lo0 = (smem_base + a.nA * kSlotBytes) >> 4;   // 16-byte units
-      const int nct = (a.with_hi ? 2 : 1) * a.nchunks;                     // chunks per tile
       const bool resident = a.a_resident != 0;
       const uint32_t nB = (uint32_t)a.nB, nA = (uint32_t)a.nA;
       const uint32_t bfull0 = b_full(0), bempty0 = b_empty(0), afull0 = a_full(0), aempty0 = a_empty(0);
+      const uint32_t klast = (uint32_t)a.k_last, kl_u = (uint32_t)a.kl;
       uint32_t sb = 0, b_par = 0;           // B ring position / phase parity
       uint32_t sas = 0, a_par_s = 0;        // streaming A ring position / phase parity
-      uint32_t cc = 0, t_par = 0;           // chunk counter, resident-A phase parity (per tile)
+      uint32_t cc = 0, t_par = 0;           // phase counter, resident-A phase parity (per tile)
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
-        for (int j = 0; j < nct; ++j, ++cc) {
-          const int hi = j >= a.nchunks;
-          const int a0 = first_atom(a, hi, hi ? j - a.nchunks : j);
-          const uint32_t nsl = (uint32_t)((a.atoms - a0) * a.kl);            // slices of this chunk
-          const int cj = hi ? j - a.nchunks : j;
-          const uint32_t idesc = MODE == DEC1F ? make_idesc_pair_f16(a.col0[cj + 1] - a.col0[cj])
-                                               : make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.nl * (a.col0[cj + 1] - a.col0[cj]));
-          const uint32_t klast = (uint32_t)a.k_last, kl_u = (uint32_t)a.kl;
-          // resident A slot sa is read again later in the tile iff the next chunk reads it: chunks read ever fewer
-          // atoms (cyclic chunks read all, hi chunk c reads atoms >= a0(c), a0 non-decreasing)
-          const int jn = j + 1;
-          const int next_a0 = jn < nct ? (jn >= a.nchunks ? first_atom(a, 1, jn - a.nchunks) : 0) : a.atoms;
-          const uint32_t rel_lim = resident ? (uint32_t)(next_a0 * a.kl) : 0xffffffffu;   // release slots sa < rel_lim
-          const bool wait_a = !resident || j == 0;
-          const uint32_t a_par = resident ? t_par : a_par_s;
+        for (int j = 0; j < a.nph; ++j, ++cc) {
+          const Phase ph = a.ph[j];
+          const uint32_t nsl = (uint32_t)(ph.a1 - ph.a0) * kl_u;             // slices of this phase
+          const int wc = a.col0[ph.c + 1] - a.col0[ph.c];
+          const uint32_t idesc = MODE == DEC1F ? make_idesc_pair_f16(wc) : make_idesc_pair(0, MODE == DEC1 ? 1 : 0, a.nl * wc);
+          // resident A: atoms read for the first time in the tile are waited for, atoms read for the last time are released
+          const uint32_t first = resident ? ph.first : 0xffffu, rel = resident ? ph.rel : 0xffffu;
           const uint32_t buf = cc & 1;
           if (lane == 0) TRACE(1, 0, cc);
           mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
           if (lane == 0) TRACE(1, 1, cc);
           const uint32_t d_tmem = tmem_base + buf * kAccCols;
           const uint32_t tfull = tfull_bar(buf);
-          uint32_t sa = resident ? (uint32_t)(a0 * a.kl) : sas;
-          uint32_t accumulate = 0;
+          uint32_t sa = resident ? (uint32_t)ph.a0 * kl_u : sas;
+          uint32_t at = (uint32_t)ph.a0, lk = 0;                             // K atom / K limb of the current slice
+          uint32_t accumulate = ph.kind == PH_LO ? 1u : 0u;                  // a LO phase continues on the HI product in this buffer
           for (uint32_t i = 0; i < nsl; ++i) {
             // even lanes poll the B stage, odd lanes the A slot, in ONE try_wait round trip (the trace showed ~180
             // cycles per poll of an already complete barrier, paid once per barrier and slice in the streaming modes)
-            if (wait_a) mbar_wait((lane & 1) ? afull0 + 8u * sa : bfull0 + 8u * sb, (lane & 1) ? (resident ? a_par : a_par_s) : b_par);
+            if ((first >> at) & 1u) mbar_wait((lane & 1) ? afull0 + 8u * sa : bfull0 + 8u * sb, (lane & 1) ? (resident ? t_par : a_par_s) : b_par);
             else mbar_wait(bfull0 + 8u * sb, b_par);
             __syncwarp();
             if (lane == 0) TRACE(1, 3, cc);
@@ -388,20 +377,21 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
             const uint64_t db = desc_hi | (uint64_t)(b_lo0 + sb * (kSlotBytes >> 4));
             // the slices of the last K atom (one per K limb) hold coefficients below N only in their first k_last 32-byte steps
-            const uint32_t nk = (nsl - i <= kl_u) ? klast : 4u;
+            const uint32_t nk = at == (uint32_t)(a.atoms - 1) ? klast : 4u;
             if (elect_one()) {
               umma_pair<MODE == DEC1F>(d_tmem, da, db, idesc, accumulate);
               if (nk > 1) umma_pair<MODE == DEC1F>(d_tmem, da + 2, db + 2, idesc, 1u);
               if (nk > 2) umma_pair<MODE == DEC1F>(d_tmem, da + 4, db + 4, idesc, 1u);
               if (nk > 3) umma_pair<MODE == DEC1F>(d_tmem, da + 6, db + 6, idesc, 1u);
               umma_commit_pair(bempty0 + 8u * sb);
-              if (sa < rel_lim) umma_commit_pair(aempty0 + 8u * sa);
+              if ((rel >> at) & 1u) umma_commit_pair(aempty0 + 8u * sa);
               if (i == nsl - 1) umma_commit_pair(tfull);
             }
             __syncwarp();
             if (lane == 0) TRACE(1, 5, cc);
             accumulate = 1;
             if (++sb == nB) { sb = 0; b_par ^= 1; }
+            if (++lk == kl_u) { lk = 0; ++at; }
             if (resident) {
               ++sa;
             } else {
@@ -420,16 +410,15 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     if (a.a_tma) {
       // in place: raw atom (row r at byte 256 r of the slot pair) -> limb 0 in slot 2 pj, limb 1 in slot 2 pj + 1.
       // Lanes 0-3 / 4-7 of a row read the halves of their 32 bytes in opposite order (no bank conflict).
-      const int parts = a.with_hi ? 2 : 1;
       const uint32_t np = (uint32_t)a.nA >> 1;
       const uint32_t lead_a_full = lead(a_full(0));
       const uint32_t sel = (uint32_t)(chunk >> 2) & 1u;
       uint32_t pj = 0, par = 0;
       int xn = 0;   // atoms built so far (trace tag)
+      int per_tile = 0;                                   // atom visits per tile: every phase streams its own atoms
+      for (int j = 0; j < a.nph; ++j) per_tile += a.ph[j].a1 - a.ph[j].a0;
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
-        for (int part = 0; part < parts; ++part) {
-          for (int c = 0; c < a.nchunks; ++c) {
-            for (int at = first_atom(a, part == 1, c); at < a.atoms; ++at, ++xn) {
+            for (int v = 0; v < per_tile; ++v, ++xn) {
               if (t == 0) TRACE(4, 0, xn);
               mbar_wait(a_full(a.nA + pj), par);
               if (t == 0) TRACE(4, 1, xn);
@@ -465,33 +454,25 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               if (t == 0) TRACE(4, 5, xn);
               if (++pj == np) { pj = 0; par ^= 1; }
             }
-          }
-        }
       }
     } else {
     const uint16_t *src = reinterpret_cast<const uint16_t *>(a.a_src);
     // work list: the atoms whose A slots must be (re)built, in pipeline order
-    struct Item { int T, part, c, at; uint32_t ia; int titer; bool valid; };
-    const int parts = a.with_hi ? 2 : 1;
+    // (resident: the atoms of a tile once, in the order of their first use; streaming: the atoms of every phase)
+    struct Item { int T, j, k, at; uint32_t ia; int titer; bool valid; };
     auto advance = [&](Item &w) {
       if (a.a_resident) {
-        if (++w.at < a.atoms) return;
-        w.at = 0;
+        if (++w.k < a.atoms) { w.at = a.a_order[w.k]; return; }
       } else {
         w.ia += a.kl;
-        if (++w.at < a.atoms) return;
-        if (++w.c == a.nchunks) {
-          w.c = 0;
-          if (++w.part == parts) w.part = 0; else { w.at = first_atom(a, w.part == 1, w.c); return; }
-        } else {
-          w.at = first_atom(a, w.part == 1, w.c);
-          return;
-        }
+        if (++w.at < a.ph[w.j].a1) return;
+        if (++w.j < a.nph) { w.at = a.ph[w.j].a0; return; }
       }
       w.T += gridDim.x >> 1;
       ++w.titer;
       w.valid = w.T < a.npairs;
-      w.at = 0;
+      w.j = 0; w.k = 0;
+      w.at = a.a_resident ? a.a_order[0] : a.ph[0].a0;
     };
     auto load_atom = [&](const Item &w, uint4 (&raw)[8]) {
       const int col = w.at * kAtomK + chunk * 16;        // first coefficient of this thread's chunk
@@ -507,9 +488,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       }
     };
     Item cur;
-    cur.T = blockIdx.x >> 1; cur.part = 0; cur.c = 0; cur.ia = 0; cur.titer = 0;
+    cur.T = blockIdx.x >> 1; cur.j = 0; cur.k = 0; cur.ia = 0; cur.titer = 0;
     cur.valid = cur.T < a.npairs;
-    cur.at = 0;
+    cur.at = a.a_resident ? a.a_order[0] : a.ph[0].a0;
     uint4 raw[8], raw_next[8];
     int xn = 0;   // atoms built so far (trace tag)
     if (cur.valid) load_atom(cur, raw);
@@ -583,7 +564,6 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const int quad = warp & 3;
     const uint32_t grp = (uint32_t)(ew >> 2) & 1u;
     const int sub = ew >> 3;
-    const int parts = a.with_hi ? 2 : 1;
     const uint32_t Q2 = a.qmask | (a.qmask << 16);
     const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;   // x > q/2  <=>  bit log2(q) of x + q/2 - 1
     const int logq = 31 - __clz(a.q);
@@ -601,9 +581,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     bool store_pending = false;
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
       const int out_row = T * 256 + (int)rank * kTileRows + quad * 32;
-      for (int part = 0; part < parts; ++part) {
-        const int hi = part == 1;
-        for (int c = 0; c < a.nchunks; ++c, ++cc) {
+      {
+        for (int jp = 0; jp < a.nph; ++jp, ++cc) {
+          const int c = a.ph[jp].c;
+          const int hi = a.ph[jp].kind == PH_HI;                    // quotient epilogue; CYC and LO phases end in the remainder epilogue
           const uint32_t ms = mc & 1, m_par = (mc >> 1) & 1;
           if (MODE == ENC && !hi) ++mc;
           if ((cc & 1u) != grp) continue;

@@ -78,6 +78,10 @@ class Engine:
         """tcgen05 schedule, first decrypt product at 256 < q <= 2048: 0 auto (fp16 above N = 512), 1 byte limbs, 2 fp16 tiles."""
         self.set_option(_lib.NTRU_OPT_DEC1_FORM, int(form))
 
+    def set_schedule(self, cyc_plus_hi: bool):
+        """tcgen05 schedule with the quotient witness: lo + hi phases (default) or the round-1 cyc + hi order."""
+        self.set_option(_lib.NTRU_OPT_SCHEDULE, 1 if cyc_plus_hi else 0)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ntru_launch_count(self._h))

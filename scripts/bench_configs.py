@@ -30,6 +30,8 @@ def setup(cfg):
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     if os.environ.get("DEC1_FORM"):                    # first decrypt product at q <= 2048: 0 auto, 1 byte limbs, 2 fp16 tiles
         eng.set_dec1_form(int(os.environ["DEC1_FORM"]))
+    if os.environ.get("SCHEDULE"):                     # 1: the round-1 phase order (cyc + hi) instead of hi, then lo on top
+        eng.set_schedule(bool(int(os.environ["SCHEDULE"])))
     return g, eng, N, q, dr
 
 
@@ -50,7 +52,8 @@ def same_key(cfg, B):
         eng.decrypt_dev(B, val, value=out, quotient1=q1, remainder1=r1, quotient2=q2)
     kt = {k: round(v[0] / v[1], 4) for k, v in eng.timing_read().items() if v[1]}
     eng.set_timing(False)
-    print(json.dumps({"config": cfg, "mode": "same-key tcgen05", "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
+    print(json.dumps({"config": cfg, "mode": "same-key tcgen05", "schedule": "cyc + hi" if os.environ.get("SCHEDULE") == "1" else "hi, then lo on top",
+                      "rows": B, "enc_ms": t_enc, "dec_ms": t_dec,
                       "kernel_ms": kt,
                       "ct_per_s": B / (tot * 1e-3), "GBps_14N": 14 * N * B / (tot * 1e-3) / 1e9, "frac_hbm": 14 * N * B / (tot * 1e-3) / 1e9 / HBM,
                       "int8_TOPs_10N2": (10 if q > 256 else 6) * N * N * B / (tot * 1e-3) / 1e12, "roundtrip_equals_message": ok}))

@@ -316,8 +316,19 @@ def test_many_tiles_per_cluster_outside_baseline(N, q, nb):
     for path in paths[1:]:
         for x, y in zip(outs[nb.PATH_TENSOR], outs[path]):   # pad columns included: every schedule writes them as zero
             assert torch.equal(x, y), (N, q, path)
-    # value-only mode (no hi chunks: other loop counts and ring phases), same ciphertexts and plaintexts
+    # the round-1 phase order (full cyclic product, then the hi product) against the default (hi, then lo on top of it)
     eng.set_path(nb.PATH_TENSOR)
+    eng.set_schedule(True)
+    bufs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
+           [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+    eng.encrypt_dev(B, r, m, value=bufs[0], quotientE=bufs[1])
+    eng.decrypt_dev(B, bufs[0], value=bufs[4], quotient1=bufs[2], remainder1=bufs[3], quotient2=bufs[5])
+    eng.sync()
+    eng.set_schedule(False)
+    for x, y in zip(outs[nb.PATH_TENSOR], bufs):
+        assert torch.equal(x, y), (N, q, "cyc + hi order")
+    del bufs
+    # value-only mode (no hi chunks: other loop counts and ring phases), same ciphertexts and plaintexts
     val2 = torch.full((B, P), 7, dtype=torch.int16, device=dev)
     pv2 = torch.full((B, P), 7, dtype=torch.uint8, device=dev)
     eng.encrypt_dev(B, r, m, value=val2)
