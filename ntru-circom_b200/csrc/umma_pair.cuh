@@ -377,7 +377,11 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
             const uint64_t db = desc_hi | (uint64_t)(b_lo0 + sb * (kSlotBytes >> 4));
             // the slices of the last K atom (one per K limb) hold coefficients below N only in their first k_last 32-byte steps
+#ifdef NTRU_TRACE
+            const uint32_t nk = (a.debug_flags & 2) ? 1u : (at == (uint32_t)(a.atoms - 1) ? klast : 4u);   // timing experiment: one MMA per slice
+#else
             const uint32_t nk = at == (uint32_t)(a.atoms - 1) ? klast : 4u;
+#endif
             if (elect_one()) {
               umma_pair<MODE == DEC1F>(d_tmem, da, db, idesc, accumulate);
               if (nk > 1) umma_pair<MODE == DEC1F>(d_tmem, da + 2, db + 2, idesc, 1u);
