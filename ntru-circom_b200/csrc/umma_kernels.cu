@@ -456,7 +456,8 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
 #ifdef NTRU_TRACE   // timing experiments exist in trace builds only: the shipped library reads no environment variable
     if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // results are not written
     if (getenv("NTRU_DEBUG_NOB")) a.debug_flags |= 1;
-    if (getenv("NTRU_DEBUG_ONE_MMA")) a.debug_flags |= 2;   // one of the four 32-byte MMA steps per slice: what does an issued slice cost without tensor work?
+    if (getenv("NTRU_DEBUG_ONE_MMA")) a.debug_flags |= 2;
+    if (getenv("NTRU_TRACE_SLICES")) a.debug_flags |= 4;    // per-slice events of the issuer and the producer, tagged with the running slice number   // one of the four 32-byte MMA steps per slice: what does an issued slice cost without tensor work?
 #endif
   }
   // The accumulator chunks cover col0[nchunks] >= N output columns (N rounded up to the epilogue's granularity); where

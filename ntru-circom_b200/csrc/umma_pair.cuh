@@ -226,6 +226,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const uint32_t lead_b_full = lead(b_full(0));
     const int part_rows = a.mat_rows / 3;                  // key-matrix rows of one part (cyc / hi / lo)
     uint32_t sb = 0, b_par = 0;
+#ifdef NTRU_TRACE
+    int gs = 0;   // running slice number (trace tag)
+#endif
     if (lane == 0) { TRACE(3, 10, 0); TRACE_NS(3, 11, 0); }
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
       for (int j = 0; j < a.nph; ++j) {
@@ -238,7 +241,14 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
         const int row0 = ph.kind * part_rows + a.nl * a.col0[c] + (int)rank * half_rows;
         for (int at = ph.a0; at < ph.a1; ++at) {
           for (int lk = 0; lk < a.kl; ++lk) {
+#ifdef NTRU_TRACE
+            if (lane == 0 && (a.debug_flags & 4)) TRACE(3, 0, gs);
+#endif
             mbar_wait(b_empty(sb), b_par ^ 1);
+#ifdef NTRU_TRACE
+            if (lane == 0 && (a.debug_flags & 4)) TRACE(3, 1, gs);
+            ++gs;
+#endif
             if (elect_one()) {
 #ifdef NTRU_TRACE
               if (a.debug_flags & 1) {   // timing experiment: no B traffic at all (operands are stale shared memory)
@@ -349,6 +359,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       uint32_t sb = 0, b_par = 0;           // B ring position / phase parity
       uint32_t sas = 0, a_par_s = 0;        // streaming A ring position / phase parity
       uint32_t cc = 0, t_par = 0;           // phase counter, resident-A phase parity (per tile)
+#ifdef NTRU_TRACE
+      int gs = 0;   // running slice number (trace tag of the per-slice events when debug flag 4 is set)
+#endif
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         for (int j = 0; j < a.nph; ++j, ++cc) {
           const Phase ph = a.ph[j];
@@ -372,7 +385,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
             if ((first >> at) & 1u) mbar_wait((lane & 1) ? afull0 + 8u * sa : bfull0 + 8u * sb, (lane & 1) ? (resident ? t_par : a_par_s) : b_par);
             else mbar_wait(bfull0 + 8u * sb, b_par);
             __syncwarp();
-            if (lane == 0) TRACE(1, 3, cc);
+#ifdef NTRU_TRACE
+            if (lane == 0) TRACE(1, 3, (a.debug_flags & 4) ? gs : (int)cc);
+#endif
             tc_fence_after();
             const uint64_t da = desc_hi | (uint64_t)(a_lo0 + sa * (kSlotBytes >> 4));
             const uint64_t db = desc_hi | (uint64_t)(b_lo0 + sb * (kSlotBytes >> 4));
@@ -392,7 +407,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               if (i == nsl - 1) umma_commit_pair(tfull);
             }
             __syncwarp();
-            if (lane == 0) TRACE(1, 5, cc);
+#ifdef NTRU_TRACE
+            if (lane == 0) TRACE(1, 5, (a.debug_flags & 4) ? gs : (int)cc);
+            ++gs;
+#endif
             accumulate = 1;
             if (++sb == nB) { sb = 0; b_par ^= 1; }
             if (++lk == kl_u) { lk = 0; ++at; }

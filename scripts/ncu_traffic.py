@@ -43,18 +43,32 @@ def geometry(mode):
 
 
 def executed_macs(mode):
-    """int8 MACs per ciphertext the kernel issues: per chunk (cyclic + hi part) columns x K bytes actually multiplied"""
+    """int8 MACs per ciphertext the kernel issues: the phase list of umma_kernels.cu:build_schedule() (hi product, then the
+    lo product on top of it, chunks in pairs; an odd last chunk as cyclic + hi), columns x K bytes actually multiplied"""
     nl, kp, c0 = geometry(mode)
     kl = 2 if (mode == "dec1" and q > 256) else 1
     atoms = kp // 128
     k_last = (N - (atoms - 1) * 128 + 31) // 32 * 32
-    total = 0
-    for part in (0, 1):
-        for c in range(len(c0) - 1):
-            a0 = min((c0[c] + 1) // 128, atoms - 1) if part else 0
-            kbytes = (atoms - 1 - a0) * 128 + k_last
-            total += nl * (c0[c + 1] - c0[c]) * kbytes * kl
-    return total
+    n = len(c0) - 1
+
+    def kbytes(a0, a1):           # atoms [a0, a1): the last atom of the operand holds k_last bytes
+        return sum(k_last if at == atoms - 1 else 128 for at in range(a0, a1))
+
+    def hi_a0(c):
+        return min((c0[c] + 1) // 128, atoms - 1)
+
+    def lo_a1(c):
+        return (min(c0[c + 1], N) - 1) // 128 + 1
+
+    phases = []
+    c = n - 1
+    if n & 1:
+        phases += [(c, 0, atoms), (c, hi_a0(c), atoms)]
+        c -= 1
+    while c >= 1:
+        phases += [(c, hi_a0(c), atoms), (c - 1, hi_a0(c - 1), atoms), (c, 0, lo_a1(c)), (c - 1, 0, lo_a1(c - 1))]
+        c -= 2
+    return sum(nl * (c0[c + 1] - c0[c]) * kbytes(a0, a1) * kl for c, a0, a1 in phases)
 
 
 limbs = 2 if q > 256 else 1
