@@ -605,7 +605,11 @@ def test_encrypt_with_device_drawn_r(cfg, nb, golden):
     for x in (a, b):
         assert (np.count_nonzero(x["r"] == 1, axis=1) == dr).all() and (np.count_nonzero(x["r"] == 2, axis=1) == dr).all()
         assert x["r"].max() <= 2
-        assert np.array_equal(eng.decrypt_batch(x["value"], witness=False)["value"], m)
+        # decrypts as the oracle decrypts it; NOT compared with m row for row: r comes from OS entropy here, and at the
+        # default parameters (q = 128) about one random r in 3000 wraps the centred lift ("this test may fail" upstream)
+        dec = eng.decrypt_batch(x["value"], witness=False)["value"]
+        assert np.array_equal(dec, o.decrypt_batch(g["f"].astype(np.int64), g["fp"].astype(np.int64), x["value"], q, p)["value"])
+        assert (dec == m).all(axis=1).mean() > 0.99
     assert not np.array_equal(a["r"], b["r"]) and not np.array_equal(a["value"], b["value"])
     # 2. a known key: replay through the oracle, on every schedule, with chunked pipelining (128-row chunks)
     key = bytes(range(100, 132))
