@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_int8, c_long, c_size_t, c_uint8, c_uint16, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libntru_b200.so")
+#: NTRU_B200_LIB points the harness at another build of the library (A/B runs, the NTRU_TRACE build)
+LIB_PATH = os.environ.get("NTRU_B200_LIB") or os.path.join(_HERE, "libntru_b200.so")
 
 NTRU_OK = 0
 NTRU_E_PARAM, NTRU_E_LENGTH, NTRU_E_NOKEY, NTRU_E_CUDA = -1, -2, -3, -4
