@@ -457,7 +457,9 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
     if (getenv("NTRU_DEBUG_NOSTORE")) a.out_mask = 0;   // results are not written
     if (getenv("NTRU_DEBUG_NOB")) a.debug_flags |= 1;
     if (getenv("NTRU_DEBUG_ONE_MMA")) a.debug_flags |= 2;
-    if (getenv("NTRU_TRACE_SLICES")) a.debug_flags |= 4;    // per-slice events of the issuer and the producer, tagged with the running slice number   // one of the four 32-byte MMA steps per slice: what does an issued slice cost without tensor work?
+    if (getenv("NTRU_TRACE_SLICES")) a.debug_flags |= 4;
+    if (getenv("NTRU_TRACE_LIGHT")) a.debug_flags |= 16;    // cycle sums of the issuer in registers instead of per-event stores
+    if (getenv("NTRU_DEBUG_DOUBLE_MMA")) a.debug_flags |= 32;   // eight MMAs per slice: does the trip cost hide behind more tensor work?    // per-slice events of the issuer and the producer, tagged with the running slice number   // one of the four 32-byte MMA steps per slice: what does an issued slice cost without tensor work?
 #endif
   }
   // The accumulator chunks cover col0[nchunks] >= N output columns (N rounded up to the epilogue's granularity); where

@@ -26,14 +26,14 @@ constexpr int kTraceLanes = 4, kTraceCap = 2048;   // MMA issuer 0, epilogue war
 __device__ unsigned long long g_trace[kTraceLanes * kTraceCap];
 #define TRACE(role, ev, idx)                                                                      \
   do {                                                                                            \
-    if (blockIdx.x == 0 && trace_n[role - 1] < kTraceCap) {                                       \
+    if (blockIdx.x == 0 && !(a.debug_flags & 16) && trace_n[role - 1] < kTraceCap) {              \
       g_trace[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                     \
           ((unsigned long long)(((ev) << 12) | ((idx) & 0xfff)) << 40) | (clock64() & 0xffffffffffull); \
     }                                                                                             \
   } while (0)
 #define TRACE_NS(role, ev, idx)                                                                   \
   do {                                                                                            \
-    if (blockIdx.x == 0 && trace_n[role - 1] < kTraceCap) {                                       \
+    if (blockIdx.x == 0 && !(a.debug_flags & 16) && trace_n[role - 1] < kTraceCap) {              \
       unsigned long long _ns;                                                                     \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_ns));                                     \
       g_trace[(role - 1) * kTraceCap + trace_n[role - 1]++] =                                     \
@@ -361,6 +361,14 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
       uint32_t cc = 0, t_par = 0;           // phase counter, resident-A phase parity (per tile)
 #ifdef NTRU_TRACE
       int gs = 0;   // running slice number (trace tag of the per-slice events when debug flag 4 is set)
+      // debug flag 16: light profile -- no per-event stores, only cycle sums in registers (three 32-bit clock reads per slice)
+      const bool light = (a.debug_flags & 16) != 0;
+      unsigned long long lp_tmem = 0, lp_ops = 0, lp_issue = 0, lp_other = 0, lp_slices = 0, lp_phases = 0;
+      uint32_t lp_t = light ? (uint32_t)clock() : 0u;
+#define LP_ADD(acc) do { if (light) { const uint32_t now_ = (uint32_t)clock(); acc += now_ - lp_t; lp_t = now_; } } while (0)
+      const long long lp_start = clock64();
+#else
+#define LP_ADD(acc) do {} while (0)
 #endif
       for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1, t_par ^= 1) {
         for (int j = 0; j < a.nph; ++j, ++cc) {
@@ -372,7 +380,12 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           const uint32_t first = resident ? ph.first : 0xffffu, rel = resident ? ph.rel : 0xffffu;
           const uint32_t buf = cc & 1;
           if (lane == 0) TRACE(1, 0, cc);
+          LP_ADD(lp_other);
           mbar_wait(tempty_bar(buf), ((cc >> 1) & 1) ^ 1);
+          LP_ADD(lp_tmem);
+#ifdef NTRU_TRACE
+          ++lp_phases;
+#endif
           if (lane == 0) TRACE(1, 1, cc);
           const uint32_t d_tmem = tmem_base + buf * kAccCols;
           const uint32_t tfull = tfull_bar(buf);
@@ -382,9 +395,11 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           for (uint32_t i = 0; i < nsl; ++i) {
             // even lanes poll the B stage, odd lanes the A slot, in ONE try_wait round trip (the trace showed ~180
             // cycles per poll of an already complete barrier, paid once per barrier and slice in the streaming modes)
+            LP_ADD(lp_other);
             if ((first >> at) & 1u) mbar_wait((lane & 1) ? afull0 + 8u * sa : bfull0 + 8u * sb, (lane & 1) ? (resident ? t_par : a_par_s) : b_par);
             else mbar_wait(bfull0 + 8u * sb, b_par);
             __syncwarp();
+            LP_ADD(lp_ops);
 #ifdef NTRU_TRACE
             if (lane == 0) TRACE(1, 3, (a.debug_flags & 4) ? gs : (int)cc);
 #endif
@@ -402,14 +417,24 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
               if (nk > 1) umma_pair<MODE == DEC1F>(d_tmem, da + 2, db + 2, idesc, 1u);
               if (nk > 2) umma_pair<MODE == DEC1F>(d_tmem, da + 4, db + 4, idesc, 1u);
               if (nk > 3) umma_pair<MODE == DEC1F>(d_tmem, da + 6, db + 6, idesc, 1u);
+#ifdef NTRU_TRACE
+              if (a.debug_flags & 32) {   // timing experiment: the four MMAs of the slice once more (twice the tensor work per trip, results wrong)
+                umma_pair<MODE == DEC1F>(d_tmem, da, db, idesc, 1u);
+                umma_pair<MODE == DEC1F>(d_tmem, da + 2, db + 2, idesc, 1u);
+                umma_pair<MODE == DEC1F>(d_tmem, da + 4, db + 4, idesc, 1u);
+                umma_pair<MODE == DEC1F>(d_tmem, da + 6, db + 6, idesc, 1u);
+              }
+#endif
               umma_commit_pair(bempty0 + 8u * sb);
               if ((rel >> at) & 1u) umma_commit_pair(aempty0 + 8u * sa);
               if (i == nsl - 1) umma_commit_pair(tfull);
             }
             __syncwarp();
+            LP_ADD(lp_issue);
 #ifdef NTRU_TRACE
             if (lane == 0) TRACE(1, 5, (a.debug_flags & 4) ? gs : (int)cc);
             ++gs;
+            ++lp_slices;
 #endif
             accumulate = 1;
             if (++sb == nB) { sb = 0; b_par ^= 1; }
@@ -423,6 +448,13 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           }
         }
       }
+#ifdef NTRU_TRACE
+      if (light && blockIdx.x == 0 && lane == 0) {     // lane 0 of the trace buffer: the light profile of this launch
+        g_trace[0] = 0x4c50ull << 48;                   // "LP"
+        g_trace[1] = (unsigned long long)(clock64() - lp_start);
+        g_trace[2] = lp_tmem; g_trace[3] = lp_ops; g_trace[4] = lp_issue; g_trace[5] = lp_other; g_trace[6] = lp_slices; g_trace[7] = lp_phases;
+      }
+#endif
   }
   } else if (MODE == DEC1 && warp < kPairEpiWarp0Dec1) {
     // ===================== DEC1 transform (both CTAs): e (uint16, global) -> byte-limb A slots =====
@@ -844,7 +876,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
   }
 
 #ifdef NTRU_TRACE
-  if (blockIdx.x == 0 && lane == 0) {   // terminate the lanes this launch wrote
+  if (blockIdx.x == 0 && lane == 0 && !(a.debug_flags & 16)) {   // terminate the lanes this launch wrote
     const int role = warp == kPairProducerWarp ? 3 : (warp == kPairMmaWarp ? 1 : (warp == (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0) ? 2 : (MODE == DEC1 && warp == 0 ? 4 : 0)));
     if (role && trace_n[role - 1] < kTraceCap) g_trace[(role - 1) * kTraceCap + trace_n[role - 1]] = 0ull;
   }
