@@ -64,10 +64,14 @@ enum {
                                two-byte-limb int8 form used at every other q, 0 (default) = whichever measured faster on B200:
                                fp16 above N = 512 (DEC1 at N = 677: 1.49 against 1.65 ms), byte limbs up to it (0.85 against
                                0.89 ms at N = 509).  Both forms are exact; each is the other's cross-check in the tests. */
-  NTRU_OPT_SCHEDULE = 7     /* tcgen05 schedule with the quotient witness: 0 (default) = the hi product of a chunk, then the lo
+  NTRU_OPT_SCHEDULE = 7,    /* tcgen05 schedule with the quotient witness: 0 (default) = the hi product of a chunk, then the lo
                                product accumulated on top of it in the same TMEM buffer (remainder = lo + hi: N^2 multiply-adds
                                plus the diagonal blocks); 1 = the full cyclic product and the hi product separately (1.5 N^2,
                                the round-1 order).  Same results bit for bit; each is the other's cross-check in the tests. */
+  NTRU_OPT_EPILOGUE = 8     /* tcgen05 schedule: 1 = two groups of epilogue warps, one per TMEM accumulator buffer; 2 = one group,
+                               every warp drains every phase (the buffer goes back to the MMAs after half the time); 0 (default)
+                               = one group where it measured faster (first and second decrypt product up to N = 512).  Same
+                               results bit for bit. */
 };
 
 /* kernel kinds reported by ntru_timing_read */

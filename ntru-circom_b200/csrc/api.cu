@@ -370,6 +370,14 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
       if (value < 0 || value > 1) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_SCHEDULE must be 0 or 1");
       ctx->opt_lohi = (int)value;
       return NTRU_OK;
+    case NTRU_OPT_EPILOGUE:
+      if (value < 0 || value > 2) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_EPILOGUE must be 0, 1 or 2");
+      ctx->opt_epilogue = (int)value;
+      if (ctx->tensor_ok) {       // the chunk tables depend on it: rebuild the operand matrices
+        if (ctx->has_pub) { int rc = umma_prepare_public(ctx); if (rc) return rc; }
+        if (ctx->has_priv) { int rc = umma_prepare_private(ctx); if (rc) return rc; }
+      }
+      return NTRU_OK;
     case NTRU_OPT_DEC1_FORM:
       if (value < 0 || value > 2) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_DEC1_FORM must be 0, 1 or 2");
       ctx->opt_dec1_form = (int)value;

@@ -100,6 +100,7 @@ struct UmmaArgs {
   int nM, nS;             // message slots (ENC), store-staging slots
   int a_rel;              // commits that free an A slot: 2 (both MMA issuers) for resident A, else 1
   int two_issuers;        // second MMA issuer warp enabled (needs slices per chunk < B ring stages)
+  int one_group;          // every epilogue warp drains every phase (instead of two groups, one per TMEM buffer)
   int debug_flags;        // NTRU_TRACE builds only (NTRU_DEBUG_NOB: bit 0 = skip the B operand loads)
   int mat_rows;           // rows of the key matrix (3 parts * nl * covered columns); K block kb starts at row kb * mat_rows
   int out_mask;           // which outputs exist: bit0 = cyc #1, bit1 = cyc #2, bit2 = hi
@@ -244,6 +245,20 @@ EncodeTiledFn get_encode_fn() {
 // ceil(T / max_out) chunks whose widths differ by at most g (wider chunks first): at most two distinct widths.
 // max_out: a 256-column accumulator holds 256 / nl outputs; ENC is capped at 128 so that a chunk's message bytes are
 // one 128-byte TMA atom per row.
+// Which kernels run their epilogue as ONE group (every epilogue warp drains every phase) instead of two groups, one per
+// TMEM buffer.  One group hands a buffer back after half the time but pays the fixed cost of a phase in every warp; it
+// doubles the column granularity of the chunk table.  Measured (profiles/r2_one_group.txt): it pays for the byte-limb
+// first decrypt product with its eight epilogue warps (DEC1 at N = 509 0.841 -> 0.814 ms, N = 167 0.311 -> 0.297) and,
+// marginally, for DEC2 up to N = 512 (0.347 -> 0.342); ENC loses 3-15 % at every N.  NTRU_OPT_EPILOGUE overrides.
+bool one_group_mode(const ntru_ctx *ctx, int mode) {
+  if (ctx->opt_epilogue == 1) return false;
+  if (ctx->opt_epilogue == 2) return true;
+  const int N = ctx->N;
+  if (mode == DEC1) return N <= 768;                                            // (N = 701: 1.535 -> 1.49 ms; N = 821: 1.99 -> 2.04)
+  if (mode == DEC2) return N <= 512 && (N + 255) / 256 * 256 == (N + 127) / 128 * 128;   // no extra accumulator columns
+  return false;
+}
+
 void geometry(const ntru_ctx *ctx, int mode, int kl, int nl, KeyMatrix &km) {
   const int N = ctx->N;
   km.limbs = kl;
@@ -252,7 +267,7 @@ void geometry(const ntru_ctx *ctx, int mode, int kl, int nl, KeyMatrix &km) {
   km.klen = kl * Kp;
   const int max_out = mode == ENC ? 128 : 256 / nl;
   const bool pu1 = mode == ENC && Kp / kAtomK >= 5;          // launch_product's choice of the one-unit ENC instantiation
-  const int g = mode == ENC ? (pu1 ? 32 : 64) : (mode == DEC1 ? 32 : (mode == DEC1F ? 64 : 128));
+  const int g = (mode == ENC ? (pu1 ? 32 : 64) : (mode == DEC1 ? 32 : (mode == DEC1F ? 64 : 128))) * (one_group_mode(ctx, mode) ? 2 : 1);
   const int T = ((N + g - 1) / g) * g;
   km.nchunks = (T + max_out - 1) / max_out;
   const int base = (T / km.nchunks / g) * g;
@@ -404,6 +419,7 @@ int launch_product(ntru_ctx *ctx, const KeyMatrix &km, UmmaArgs &a, const void *
   // resident A slots are read by both MMA issuer warps (alternating chunks) whenever a tile has >= 2 chunks
   a.two_issuers = 0;   // a second issuer warp was tried: the B ring is too short for two chunks in flight
   a.a_rel = (a.a_resident && a.two_issuers) ? 2 : 1;
+  a.one_group = one_group_mode(ctx, MODE) ? 1 : 0;
   CUtensorMap tmB, tmB2, tmA, tmM, tmO[3];
   memcpy(&tmB, km.tmap_half[0], sizeof tmB);
   memcpy(&tmB2, km.tmap_half[1], sizeof tmB2);

@@ -199,9 +199,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), kEpiWarps);           // the epilogue group of this buffer, both CTAs (2 x kEpiWarps / 2)
+      mbar_init(tempty_bar(b), a.one_group ? 2 * kEpiWarps : kEpiWarps);   // the epilogue warps that drain this buffer, both CTAs
       mbar_init(m_full(b), 1);                       // this CTA's producer (+ transaction bytes)
-      mbar_init(m_empty(b), kEpiWarps / 2);          // the epilogue group that drains the chunk, this CTA
+      mbar_init(m_empty(b), a.one_group ? kEpiWarps : kEpiWarps / 2);   // the epilogue warps that drain the chunk, this CTA
     }
     fence_barrier_init();
   }
@@ -608,8 +608,10 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     // Inside a group a warp owns 32 rows (its TMEM lane quadrant) and a contiguous run of 16-coefficient units;
     // results are staged in a per-warp shared-memory tile and written with cp.async.bulk.tensor stores (per-lane
     // row stores cost 32 cache lines per warp instruction).  ENC reads the message bytes from a TMA-loaded tile.
-    constexpr int kGroupWarps = kEpiWarps / 2;                     // 8 (ENC, DEC2) or 4 (DEC1)
-    constexpr int kSub = kGroupWarps / 4;                          // warps per TMEM lane quadrant within a group
+    // a.one_group: ALL epilogue warps drain every phase (half the columns per warp, the buffer is handed back after half
+    // the time; every warp pays the fixed cost of every phase) -- for kernels whose epilogue is much longer than the
+    // MMAs of a phase, where the hand-over chain of the two buffers, (M + E) / 2 per phase, is what a tile takes.
+    const int kSub = (a.one_group ? kEpiWarps : kEpiWarps / 2) / 4;   // warps per TMEM lane quadrant that share a phase
     // ENC with PU = 1 (large N) also reads its message bytes from global memory instead of a TMA-loaded tile: no message
     // slots, so the B ring gets them (launch_product).
     constexpr bool kMsgGlobal = MODE == ENC && PU == 1;
@@ -617,7 +619,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const int ew = warp - (MODE == DEC1 ? kPairEpiWarp0Dec1 : 0);
     const int quad = warp & 3;
     const uint32_t grp = (uint32_t)(ew >> 2) & 1u;
-    const int sub = ew >> 3;
+    const int sub = a.one_group ? ew >> 2 : ew >> 3;
     const uint32_t Q2 = a.qmask | (a.qmask << 16);
     const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;   // x > q/2  <=>  bit log2(q) of x + q/2 - 1
     const int logq = 31 - __clz(a.q);
@@ -629,8 +631,8 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
     const uint32_t st_x = kRowBytes == 64 ? (uint32_t)(lane >> 1) & 3u : (uint32_t)(lane >> 2) & 1u;
     const int row_in_tile = quad * 32 + lane;
     const uint32_t m_row = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128), m_x = (uint32_t)row_in_tile & 7u;
-    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + grp * kAccCols;
-    const uint32_t my_tfull = tfull_bar(grp), lead_tempty = lead(tempty_bar(grp));
+    const uint32_t t_addr0 = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tfull0 = tfull_bar(0), lead_tempty0 = lead(tempty_bar(0));
     uint32_t cc = 0, mc = 0;
     bool store_pending = false;
     for (int T = blockIdx.x >> 1; T < a.npairs; T += gridDim.x >> 1) {
@@ -641,7 +643,9 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
           const int hi = a.ph[jp].kind == PH_HI;                    // quotient epilogue; CYC and LO phases end in the remainder epilogue
           const uint32_t ms = mc & 1, m_par = (mc >> 1) & 1;
           if (MODE == ENC && !hi) ++mc;
-          if ((cc & 1u) != grp) continue;
+          if (!a.one_group && (cc & 1u) != grp) continue;
+          const uint32_t buf = cc & 1u;
+          const uint32_t t_addr = t_addr0 + buf * kAccCols, my_tfull = tfull0 + 8u * buf, lead_tempty = lead_tempty0 + 8u * buf;
           const int col0c = a.col0[c], wc = a.col0[c + 1] - col0c;
           const int upw = (wc >> 4) / kSub;                        // units per warp in this chunk
           const int npass = upw / kPassUnits;

@@ -82,6 +82,10 @@ class Engine:
         """tcgen05 schedule with the quotient witness: lo + hi phases (default) or the round-1 cyc + hi order."""
         self.set_option(_lib.NTRU_OPT_SCHEDULE, 1 if cyc_plus_hi else 0)
 
+    def set_epilogue(self, mode: int):
+        """tcgen05 schedule: 0 auto, 1 two epilogue groups (one per TMEM buffer), 2 one group on every phase."""
+        self.set_option(_lib.NTRU_OPT_EPILOGUE, int(mode))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ntru_launch_count(self._h))

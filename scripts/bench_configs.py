@@ -30,6 +30,8 @@ def setup(cfg):
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     if os.environ.get("DEC1_FORM"):                    # first decrypt product at q <= 2048: 0 auto, 1 byte limbs, 2 fp16 tiles
         eng.set_dec1_form(int(os.environ["DEC1_FORM"]))
+    if os.environ.get("EPILOGUE"):                     # 0 auto, 1 two epilogue groups everywhere, 2 one group everywhere
+        eng.set_epilogue(int(os.environ["EPILOGUE"]))
     if os.environ.get("SCHEDULE"):                     # 1: the round-1 phase order (cyc + hi) instead of hi, then lo on top
         eng.set_schedule(bool(int(os.environ["SCHEDULE"])))
     return g, eng, N, q, dr

@@ -327,6 +327,17 @@ def test_many_tiles_per_cluster_outside_baseline(N, q, nb):
     eng.set_schedule(False)
     for x, y in zip(outs[nb.PATH_TENSOR], bufs):
         assert torch.equal(x, y), (N, q, "cyc + hi order")
+    # both arrangements of the epilogue warps (two groups, one per TMEM buffer / one group on every phase: other chunk tables)
+    for mode in (1, 2):
+        eng.set_epilogue(mode)
+        for b in bufs:
+            b.fill_(7)
+        eng.encrypt_dev(B, r, m, value=bufs[0], quotientE=bufs[1])
+        eng.decrypt_dev(B, bufs[0], value=bufs[4], quotient1=bufs[2], remainder1=bufs[3], quotient2=bufs[5])
+        eng.sync()
+        for x, y in zip(outs[nb.PATH_TENSOR], bufs):
+            assert torch.equal(x, y), (N, q, "epilogue arrangement", mode)
+    eng.set_epilogue(0)
     del bufs
     # value-only mode (no hi chunks: other loop counts and ring phases), same ciphertexts and plaintexts
     val2 = torch.full((B, P), 7, dtype=torch.int16, device=dev)
