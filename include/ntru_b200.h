@@ -61,9 +61,9 @@ enum {
   NTRU_OPT_DR = 5,          /* dr of new NTRU({..., dr}) (index.js:15): weights of the r the device draws when r == NULL */
   NTRU_OPT_DEC1_FORM = 6,   /* tcgen05 schedule, first decrypt product at 256 < q <= 2048: 2 = fp16 tiles (a uint16 coefficient
                                below 2048 is its own fp16 encoding: no operand transform, sixteen epilogue warps), 1 = the
-                               two-byte-limb int8 form used at every other q, 0 (default) = whichever measured faster on B200:
-                               fp16 above N = 512 (DEC1 at N = 677: 1.49 against 1.65 ms), byte limbs up to it (0.85 against
-                               0.89 ms at N = 509).  Both forms are exact; each is the other's cross-check in the tests. */
+                               two-byte-limb int8 form used at every other q, 0 (default) = the faster one as measured on B200: fp16
+                               (DEC1 at N = 677: 1.43 against 1.61 ms; at N = 509: 0.796 against 0.819 ms).  Both forms are exact;
+                               each is the other's cross-check in the tests. */
   NTRU_OPT_SCHEDULE = 7,    /* tcgen05 schedule with the quotient witness: 0 (default) = the hi product of a chunk, then the lo
                                product accumulated on top of it in the same TMEM buffer (remainder = lo + hi: N^2 multiply-adds
                                plus the diagonal blocks); 1 = the full cyclic product and the hi product separately (1.5 N^2,

@@ -255,6 +255,7 @@ bool one_group_mode(const ntru_ctx *ctx, int mode) {
   if (ctx->opt_epilogue == 2) return true;
   const int N = ctx->N;
   if (mode == DEC1) return N <= 768;                                            // (N = 701: 1.535 -> 1.49 ms; N = 821: 1.99 -> 2.04)
+  if (mode == DEC1F) return N <= 512;                                           // 0.836 -> 0.796 ms at N = 509; no change at N = 677
   if (mode == DEC2) return N <= 512 && (N + 255) / 256 * 256 == (N + 127) / 128 * 128;   // no extra accumulator columns
   return false;
 }
@@ -557,8 +558,9 @@ int umma_prepare_public(ntru_ctx *ctx) {
 
 int umma_prepare_private(ntru_ctx *ctx) {
   // 256 < q <= 2048: the fp16 form of the first product (a uint16 below 2048 is its own fp16 encoding, scaled by 2^-24)
-  // measured on B200 (profiles/r2_dec1_fp16_form.jsonl): faster above N = 512 (streamed A operand), slower up to it
-  const bool f16 = ctx->q > 256 && ctx->q <= 2048 && (ctx->opt_dec1_form == 2 || (ctx->opt_dec1_form == 0 && ctx->N > 512));
+  // measured on B200: faster above N = 512 (streamed A operand: 1.43 against 1.61 ms at N = 677, profiles/r2_dec1_fp16_form.jsonl)
+  // and, with the one-group epilogue, up to it (0.796 against 0.819 ms at N = 509, profiles/r2_one_group.txt)
+  const bool f16 = ctx->q > 256 && ctx->q <= 2048 && ctx->opt_dec1_form != 1;
   int rc = f16 ? build_keymat(ctx, DEC1F, 1, 1, ctx->d_f.ptr, ctx->km_f)
                : build_keymat(ctx, DEC1, ctx->q > 256 ? 2 : 1, 1, ctx->d_f.ptr, ctx->km_f);
   ctx->km_f.f16 = f16;

@@ -75,7 +75,7 @@ class Engine:
         self.set_option(_lib.NTRU_OPT_PATH, path)
 
     def set_dec1_form(self, form: int):
-        """tcgen05 schedule, first decrypt product at 256 < q <= 2048: 0 auto (fp16 above N = 512), 1 byte limbs, 2 fp16 tiles."""
+        """tcgen05 schedule, first decrypt product at 256 < q <= 2048: 0 auto (fp16), 1 byte limbs, 2 fp16 tiles."""
         self.set_option(_lib.NTRU_OPT_DEC1_FORM, int(form))
 
     def set_schedule(self, cyc_plus_hi: bool):
