@@ -25,13 +25,31 @@ def num(r, name):
         return None
 
 
+def fp16_dec1():
+    """the first decrypt product runs on kind::f16 tiles (umma_prepare_private: 256 < q <= 2048, default form)"""
+    return 256 < q <= 2048
+
+
+def one_group(mode):
+    """umma_kernels.cu:one_group_mode(), default NTRU_OPT_EPILOGUE"""
+    if mode == "dec1":
+        return N <= 512 if fp16_dec1() else N <= 768
+    if mode == "dec2":
+        return N <= 512 and (N + 255) // 256 * 256 == (N + 127) // 128 * 128
+    return False
+
+
 def geometry(mode):
-    """chunk table of umma_kernels.cu:geometry()"""
+    """chunk table of umma_kernels.cu:geometry(); ea = coefficients per 128-byte K atom"""
+    f16 = mode == "dec1" and fp16_dec1()
     nl = 2 if (mode == "enc" and q > 256) else 1
-    kp = (N + 127) // 128 * 128
+    ea = 64 if f16 else 128
+    atoms = (N + ea - 1) // ea
     max_out = 128 if mode == "enc" else 256 // nl
-    pu1 = mode == "enc" and kp // 128 >= 5
-    g = (32 if pu1 else 64) if mode == "enc" else (32 if mode == "dec1" else 128)
+    pu1 = mode == "enc" and atoms >= 5
+    g = (32 if pu1 else 64) if mode == "enc" else ((64 if f16 else 32) if mode == "dec1" else 128)
+    if one_group(mode):
+        g *= 2
     T = (N + g - 1) // g * g
     n = (T + max_out - 1) // max_out
     base = T // n // g * g
@@ -39,26 +57,28 @@ def geometry(mode):
     c0 = [0]
     for c in range(n):
         c0.append(c0[-1] + base + (g if c < wide else 0))
-    return nl, kp, c0
+    return nl, ea, atoms, c0
 
 
 def executed_macs(mode):
-    """int8 MACs per ciphertext the kernel issues: the phase list of umma_kernels.cu:build_schedule() (hi product, then the
-    lo product on top of it, chunks in pairs; an odd last chunk as cyclic + hi), columns x K bytes actually multiplied"""
-    nl, kp, c0 = geometry(mode)
-    kl = 2 if (mode == "dec1" and q > 256) else 1
-    atoms = kp // 128
-    k_last = (N - (atoms - 1) * 128 + 31) // 32 * 32
+    """int8 MACs (int8-equivalents for the fp16 form: one fp16 MAC takes the tensor time of two int8 MACs) per ciphertext
+    the kernel issues: the phase list of umma_kernels.cu:build_schedule() (hi product, then the lo product on top of it,
+    chunks in pairs; an odd last chunk as cyclic + hi), columns x K coefficients actually multiplied, in 32-byte steps"""
+    nl, ea, atoms, c0 = geometry(mode)
+    f16 = mode == "dec1" and fp16_dec1()
+    kl = 2 if (mode == "dec1" and q > 256 and not f16) else 1
+    step = ea // 4
+    k_last = (N - (atoms - 1) * ea + step - 1) // step * step
     n = len(c0) - 1
 
-    def kbytes(a0, a1):           # atoms [a0, a1): the last atom of the operand holds k_last bytes
-        return sum(k_last if at == atoms - 1 else 128 for at in range(a0, a1))
+    def kcoef(a0, a1):           # atoms [a0, a1): the last atom of the operand holds k_last coefficients
+        return sum(k_last if at == atoms - 1 else ea for at in range(a0, a1))
 
     def hi_a0(c):
-        return min((c0[c] + 1) // 128, atoms - 1)
+        return min((c0[c] + 1) // ea, atoms - 1)
 
     def lo_a1(c):
-        return (min(c0[c + 1], N) - 1) // 128 + 1
+        return (min(c0[c + 1], N) - 1) // ea + 1
 
     phases = []
     c = n - 1
@@ -68,13 +88,13 @@ def executed_macs(mode):
     while c >= 1:
         phases += [(c, hi_a0(c), atoms), (c - 1, hi_a0(c - 1), atoms), (c, 0, lo_a1(c)), (c - 1, 0, lo_a1(c - 1))]
         c -= 2
-    return sum(nl * (c0[c + 1] - c0[c]) * kbytes(a0, a1) * kl for c, a0, a1 in phases)
+    return sum(nl * (c0[c + 1] - c0[c]) * kcoef(a0, a1) * kl for c, a0, a1 in phases) * (2 if f16 else 1)
 
 
 limbs = 2 if q > 256 else 1
 alg_bytes = {"enc": 6 * N, "dec1": 6 * N, "dec2": 2 * N}
 alg_macs = {"enc": N * N * limbs, "dec1": N * N * limbs, "dec2": N * N}
-modes = {"ILi0E": "enc", "ILi1E": "dec1", "ILi2E": "dec2"}
+modes = {"ILi0E": "enc", "ILi1E": "dec1", "ILi2E": "dec2", "ILi3E": "dec1"}
 res = {"source": f"ncu --set full --clock-control none, {rep}, {rows} rows per launch (inputs + outputs exceed the 126 MB L2)", "label": label,
        "N": N, "q": q, "rows": rows, "kernels": {}, "bytes_per_ciphertext": {}}
 for r in data:
@@ -82,7 +102,9 @@ for r in data:
     if "k_umma_pair" not in name:
         continue
     mode = None
-    for tag, m in (("k_umma_pair<0", "enc"), ("k_umma_pair<1", "dec1"), ("k_umma_pair<2", "dec2"), ("(Mode)0", "enc"), ("(Mode)1", "dec1"), ("(Mode)2", "dec2")):
+    for tag, m in (("k_umma_pair<0", "enc"), ("k_umma_pair<1", "dec1"), ("k_umma_pair<2", "dec2"), ("k_umma_pair<3", "dec1"),
+                   ("k_umma_pair<(int)0", "enc"), ("k_umma_pair<(int)1", "dec1"), ("k_umma_pair<(int)2", "dec2"), ("k_umma_pair<(int)3", "dec1"),
+                   ("(Mode)0", "enc"), ("(Mode)1", "dec1"), ("(Mode)2", "dec2"), ("(Mode)3", "dec1")):
         if tag in name.replace(" ", ""):
             mode = m
             break
