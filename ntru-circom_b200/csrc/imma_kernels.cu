@@ -54,8 +54,14 @@ __device__ __forceinline__ void imma_u8s8(int (&c)[4], const uint32_t (&a)[4], u
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ uint32_t mod3_16(uint32_t v) {   // v < 65536
-  return v - 3u * ((v * 0xAAABu) >> 17);
+__device__ __forceinline__ void imma_u8u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t mod3_16(uint32_t v) {   // two instructions: floor(v / 3) = umulhi(v, (2^32 + 2) / 3) for v < 2^31
+  return v - 3u * __umulhi(v, 0x55555556u);
 }
 
 // Column blocks visited per K step: jn = (s >> 2) + d, d = 0 .. kDMax.  Some K1 - t of block (jn, s) lies in [0, I1)
@@ -64,6 +70,17 @@ __device__ __forceinline__ uint32_t mod3_16(uint32_t v) {   // v < 65536
 template <int NJ> struct ImmaShape {
   static constexpr int kDMax = (6 + 4 * NJ) >> 3;
   static constexpr int kSGroups = (2 * NJ + 1 + 3) / 4;     // S <= 2 NJ + 1 K steps, four per group
+  // resident CTAs (of four warps) per SM the encrypt / decrypt kernels are compiled for.  Two warps per scheduler
+  // already reach the issue-bound rate (conv_merged); four leave the compiler 128 registers and nothing spills
+  // (at five or six it spills 50 - 150 words and every variant measured slower, profiles/r2_imma_merged.txt).
+#ifndef NTRU_IMMA_SGC
+#define NTRU_IMMA_SGC 3
+#endif
+#ifndef NTRU_IMMA_MINB
+#define NTRU_IMMA_MINB 4
+#endif
+  static constexpr int kMinBlocks = NJ <= 3 ? 8 : NTRU_IMMA_MINB;
+  static constexpr int kSgChunk = NTRU_IMMA_SGC < kSGroups ? NTRU_IMMA_SGC : kSGroups;
 };
 
 // acc[jn][l] = Toeplitz(y limb l) x Hankel(x).  Fully unrolled over (s, jn): every shared-memory address is
@@ -134,6 +151,101 @@ __device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, 
   }
 }
 
+// The encrypt / decrypt form of the product (round 2): ONE accumulator set for both limbs of y, every operand fragment
+// read from shared memory once, no run-time condition inside the product.
+//  * What the kernels are bound by (scripts/imma_pattern_probe.cu, profiles/r2_imma_pattern_probe.txt and the
+//    occupancy sweep in profiles/r2_imma_merged.txt): a scheduler spends 8.4 cycles per IMMA.16832 and about one more
+//    cycle for every other instruction of its warps -- cycles per ciphertext and scheduler = 8.4 IMMAs + the rest, reached
+//    with two warps per scheduler and unchanged by a third or fourth.  The tensor pipe never waits for a free warp, it
+//    waits while the issue port handles loads, shifts and address arithmetic.  So every instruction next to the MMAs
+//    counts like an eighth of an MMA, and the whole kernel is written to that rule.
+//  * y = y0 + 256 y1 with y1 < 64 (q <= 8192, ntru_create).  The staged high limb is 4 y1 and its multiplier 64 x
+//    (x in {-1, 0, 1} signed or {0, 1, 2} unsigned: |64 x| fits the byte), so  y0 x + (4 y1)(64 x) = y x  lands in the
+//    same int32 accumulator: 4 NJ accumulator registers instead of 8 NJ and half the accumulator traffic afterwards.
+//    64 x is a second staged array (x6), not a shift next to the MMAs.
+//  * Loop order (s4) -> A fragments of a group of steps -> (d) -> one B fragment per limb -> (sg): the B fragment of
+//    (column block sg + d, step 4 sg + s4) does not depend on sg.
+//  * I1X = ceil(N / 16) as a template argument for the BASELINE parameter sets: blocks whose K1 - t lies outside [0, I1)
+//    -- d > (2 s4 + I1) >> 3 -- and steps beyond S are dropped at compile time (a warp-uniform run-time branch around
+//    an mma.sync costs a WARPSYNC and a BRA per instruction).  I1X = 0, any N of the bucket: every (step, block) of the
+//    bucket runs; the limb arrays are zero below their first coefficient as far as the last step of the bucket reads
+//    (make_layout), the x arrays are zero outside [0, N).
+template <int NJ, int LIMBS, bool XU8, int I1X>
+__device__ __forceinline__ void conv_merged(int Z, const uint8_t *y0, const uint8_t *y1, const uint8_t *x0, const uint8_t *x6, int lane,
+                                            int (&acc)[NJ][4]) {
+  constexpr int SG = ImmaShape<NJ>::kSGroups, DM = ImmaShape<NJ>::kDMax, SGC = ImmaShape<NJ>::kSgChunk;
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int jn = 0; jn < NJ; ++jn) acc[jn][0] = acc[jn][1] = acc[jn][2] = acc[jn][3] = 0;
+  // A fragment: bytes z0-1 .. z0+7 of the reversed array, z0 = Z - 32 s - 16 (t'>>1) - 2 g + 8 (t'&1):
+  // a1 = [z0-1, z0+3)  a0 = [z0, z0+4)  a3 = [z0+3, z0+7)  a2 = [z0+4, z0+8)
+  const int zfirst = Z - 16 * (tq >> 1) - 2 * g + 8 * (tq & 1) - 1;
+  const int zb = zfirst & ~3;
+  const uint32_t sh0 = 8u * (uint32_t)(zfirst - zb), sh1 = sh0 + 8u;
+  const uint8_t *pa0 = y0 + zb, *pa1 = y1 + zb;
+  const int boff = 16 * (g - (tq >> 1)) + 8 * (tq & 1);
+  const uint8_t *pb0 = x0 + boff, *pb1 = x6 + boff;
+#pragma unroll
+  for (int s4 = 0; s4 < 4; ++s4) {
+    const int dlim = I1X ? (2 * s4 + I1X) >> 3 : DM;
+    const int nsg = I1X ? (I1X / 2 + 1 - s4 + 3) >> 2 : SG;      // step groups with 4 sg + s4 < S = I1 / 2 + 1
+#pragma unroll
+    for (int c0 = 0; c0 < SG; c0 += SGC) {                // SGC step groups at a time: 4 SGC LIMBS A-fragment registers
+      if (c0 < nsg) {
+        uint32_t a[LIMBS][SGC][4];
+#pragma unroll
+        for (int l = 0; l < LIMBS; ++l) {
+#pragma unroll
+          for (int i = 0; i < SGC; ++i) {
+            const int sg = c0 + i;
+            if (sg < SG && sg < nsg) {
+              const uint32_t *w = reinterpret_cast<const uint32_t *>((l ? pa1 : pa0) - 32 * (4 * sg + s4));
+              const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+              a[l][i][0] = __funnelshift_rc(w0, w1, sh1);
+              a[l][i][1] = __funnelshift_r(w0, w1, sh0);
+              a[l][i][2] = __funnelshift_rc(w1, w2, sh1);
+              a[l][i][3] = __funnelshift_r(w1, w2, sh0);
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 0; d <= DM; ++d) {
+          if (d <= dlim && c0 + d < NJ) {
+            uint2 b[LIMBS];
+#pragma unroll
+            for (int l = 0; l < LIMBS; ++l) b[l] = *reinterpret_cast<const uint2 *>((l ? pb1 : pb0) + 128 * d - 32 * s4);
+#pragma unroll
+            for (int i = 0; i < SGC; ++i) {
+              const int sg = c0 + i;
+              if (sg < SG && sg + d < NJ && sg < nsg) {
+#pragma unroll
+                for (int l = 0; l < LIMBS; ++l) {
+                  if (XU8) imma_u8u8(acc[sg + d], a[l][i], b[l].x, b[l].y);
+                  else imma_u8s8(acc[sg + d], a[l][i], b[l].x, b[l].y);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// accumulators -> product buffer: cbuf[k] = c[k] mod 2^16, k = 16 (8 jn + 2 t' + {0,1}) + 2 g + {0,1}
+template <int NJ>
+__device__ __forceinline__ void store_merged(int nj, int lane, const int (&acc)[NJ][4], uint16_t *cbuf) {
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t *dst = reinterpret_cast<uint32_t *>(cbuf) + 16 * tq + g;      // u16 index 32 t' + 2 g
+#pragma unroll
+  for (int jn = 0; jn < NJ; ++jn) {
+    if (jn < nj) {
+      dst[64 * jn] = __byte_perm((uint32_t)acc[jn][0], (uint32_t)acc[jn][2], 0x5410);
+      dst[64 * jn + 8] = __byte_perm((uint32_t)acc[jn][1], (uint32_t)acc[jn][3], 0x5410);
+    }
+  }
+}
+
 // accumulators -> product buffer: cbuf[k] = c[k] mod 2^16, k = 16 (8 jn + 2 t' + {0,1}) + 2 g + {0,1}
 template <int NJ, int LIMBS>
 __device__ __forceinline__ void store_product(const ImmaGeom &G, int lane, const int (&acc)[NJ][LIMBS][4], uint16_t *cbuf) {
@@ -156,10 +268,13 @@ __device__ __forceinline__ void store_product(const ImmaGeom &G, int lane, const
 }
 
 // y (uint16, mod q) -> reversed byte-limb arrays: yrev_l[Z - j] = limb l of y[j]
-template <int LIMBS>
+// MERGED: the coefficients are reduced mod q first and the high limb is stored as 4 * (y >> 8) (conv_merged)
+template <int LIMBS, bool MERGED = false>
 __device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__restrict__ src, uint8_t *y0, uint8_t *y1, int lane) {
+  const uint32_t Q2 = G.qmask | (G.qmask << 16);
   for (int j0 = 8 * lane; j0 < G.N; j0 += 256) {
     uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
+    if (MERGED) v = make_uint4(v.x & Q2, v.y & Q2, v.z & Q2, v.w & Q2);
     const int nv = G.N - j0;                                     // valid coefficients in this vector
     if (nv < 8) {
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -169,7 +284,11 @@ __device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__r
     }
     const int z = G.Z - j0 - 7;                                  // multiple of 8
     *reinterpret_cast<uint2 *>(y0 + z) = make_uint2(__byte_perm(v.w, v.z, 0x4602), __byte_perm(v.y, v.x, 0x4602));
-    if (LIMBS == 2) *reinterpret_cast<uint2 *>(y1 + z) = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
+    if (LIMBS == 2) {
+      uint2 hi = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
+      if (MERGED) hi = make_uint2(hi.x << 2, hi.y << 2);      // every byte < 64: no carry into the next one
+      *reinterpret_cast<uint2 *>(y1 + z) = hi;
+    }
   }
 }
 
@@ -244,8 +363,107 @@ __device__ __forceinline__ void mask_lanes(uint32_t (&v)[4], int nv) {
   for (int i = 0; i < 4; ++i) v[i] = 2 * i + 1 < nv ? v[i] : (2 * i < nv ? (v[i] & 0xffffu) : 0u);
 }
 
+// ---- encrypt / decrypt: shared-memory layout of one ciphertext (one warp) --------------------------------------------
+// [y0 | y1 | (y2) | x6 | (xb) | cbuf | in[0] | in[1]]
+//   y0, y1  reversed limb arrays of h (encrypt) or e (decrypt); y2 reversed fp (decrypt)
+//   x6      64 x behind kXPad zero bytes (x = r or f); xb the lifted polynomial b of decrypt, same shape
+//   cbuf    the 2N - 1 product coefficients mod 2^16
+//   in[2]   the row's inputs as cp.async delivers them, double buffered: [kXPad zeros | x : P | zeros up to Lx] [y : 2P] [m or fp : P]
+//           -- the x part is laid out so that the B fragments of the low limb are read from it in place.
+struct ImmaLayout {
+  int N, P, I1, S, NJ, Z, Ly, Lx, Lc, Lin;
+  int o_y1, o_y2, o_x6, o_xb, o_c, o_in, warp_bytes;
+};
+
+__host__ __device__ constexpr ImmaLayout make_layout(int N, int nj_bucket, bool exact, bool dec) {
+  ImmaLayout L{};
+  L.N = N;
+  L.P = ((N + 1 + 15) / 16) * 16;
+  L.I1 = (N + 15) / 16;
+  L.S = ((N + 14) / 16) / 2 + 1;
+  L.NJ = ((2 * N - 1 + 15) / 16 + 7) / 8;
+  // exact: the kernel is instantiated for this N, the limb arrays end at the last step that is run; otherwise they are
+  // zero-padded down to the last step of the bucket
+  const int s_alloc = exact ? L.S : 4 * ((2 * nj_bucket + 1 + 3) / 4);
+  L.Z = 32 * s_alloc + 15;
+  L.Ly = 32 * s_alloc + 48;
+  // x is read at block indices K1 - t in [-7, 8 kDMax + 7]
+  const int dmax = (6 + 4 * nj_bucket) >> 3;
+  L.Lx = kXPad + (128 * (dmax + 1) > L.P ? 128 * (dmax + 1) : L.P);
+  L.Lc = 2 * (128 * L.NJ + 32);
+  L.Lin = L.Lx + 3 * L.P;
+  int o = L.Ly;
+  L.o_y1 = o; o += L.Ly;
+  L.o_y2 = o; if (dec) o += L.Ly;
+  L.o_x6 = o; o += L.Lx;
+  L.o_xb = o; if (dec) o += L.Lx;
+  L.o_c = o; o += L.Lc;
+  L.o_in = o; o += 2 * L.Lin;
+  L.warp_bytes = o;
+  return L;
+}
+
+// u16 coefficients (reduced mod q here) -> reversed byte-limb arrays: y0[Z - j] = y[j] & 255, y1[Z - j] = 4 (y[j] >> 8)
+template <int LIMBS>
+__device__ __forceinline__ void stage_limbs(int N, int Z, uint32_t Q2, const uint8_t *src, uint8_t *y0, uint8_t *y1, int lane) {
+#pragma unroll 4
+  for (int j0 = 8 * lane; j0 < N; j0 += 256) {
+    uint4 v = *reinterpret_cast<const uint4 *>(src + 2 * j0);
+    v = make_uint4(v.x & Q2, v.y & Q2, v.z & Q2, v.w & Q2);
+    const int z = Z - j0 - 7;                                  // multiple of 8
+    *reinterpret_cast<uint2 *>(y0 + z) = make_uint2(__byte_perm(v.w, v.z, 0x4602), __byte_perm(v.y, v.x, 0x4602));
+    if (LIMBS == 2)      // every high byte < 64: the shift carries nothing into the next byte
+      *reinterpret_cast<uint2 *>(y1 + z) = make_uint2(__byte_perm(v.w, v.z, 0x5713) << 2, __byte_perm(v.y, v.x, 0x5713) << 2);
+  }
+}
+
+// bytes -> reversed array
+__device__ __forceinline__ void stage_rev8(int N, int Z, const uint8_t *src, uint8_t *y, int lane) {
+#pragma unroll 2
+  for (int j0 = 16 * lane; j0 < N; j0 += 512) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
+    *reinterpret_cast<uint4 *>(y + (Z - j0 - 15)) =
+        make_uint4(__byte_perm(v.w, 0u, 0x0123), __byte_perm(v.z, 0u, 0x0123), __byte_perm(v.y, 0u, 0x0123), __byte_perm(v.x, 0u, 0x0123));
+  }
+}
+
+// x6 = 64 x per byte (x in {0, 1, 2} or {-1, 0, 1}: only the two low bits of a byte matter)
+__device__ __forceinline__ void stage_x6(int N, const uint8_t *x, uint8_t *x6, int lane) {
+#pragma unroll 2
+  for (int j0 = 16 * lane; j0 < N; j0 += 512) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(x + j0);
+    *reinterpret_cast<uint4 *>(x6 + j0) =
+        make_uint4((v.x << 6) & 0xC0C0C0C0u, (v.y << 6) & 0xC0C0C0C0u, (v.z << 6) & 0xC0C0C0C0u, (v.w << 6) & 0xC0C0C0C0u);
+  }
+}
+
+// lo = c[k0 .. k0+8), hi = c[k0+N .. k0+N+8) as packed uint16 pairs
+__device__ __forceinline__ void load_lo_hi2(int N, const uint16_t *cbuf, int k0, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
+  const uint4 l = *reinterpret_cast<const uint4 *>(cbuf + k0);
+  lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; lo[3] = l.w;
+  const int kh = k0 + N;
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(cbuf + (kh & ~1));
+  if (N & 1) {
+    uint32_t x[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x[i] = w[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hi[i] = __byte_perm(x[i], x[i + 1], 0x5432);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hi[i] = w[i];
+  }
+}
+
+// zeroes the packed uint16 lanes k0 + i >= N of an 8-coefficient vector (branch-free)
+__device__ __forceinline__ void mask_tail(uint32_t (&v)[4], int nv) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] &= (2 * i < nv ? 0xffffu : 0u) | (2 * i + 1 < nv ? 0xffff0000u : 0u);
+}
+
 struct ImmaEncArgs {
-  ImmaGeom G;
+  ImmaLayout L;
+  uint32_t qmask;
   size_t B;
   const uint16_t *h;
   size_t h_stride;
@@ -254,55 +472,68 @@ struct ImmaEncArgs {
   uint16_t *value, *quo, *rem;
 };
 
-template <int NJ, int LIMBS>
-__global__ void __launch_bounds__(kImmaWarps * 32) k_encrypt_imma(const ImmaEncArgs a) {
+#define NTRU_LF(f) (NX ? LX.f : a.L.f)
+
+template <int NJ, int LIMBS, int NX>
+__global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_encrypt_imma(const ImmaEncArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const ImmaGeom &G = a.G;
+  constexpr ImmaLayout LX = make_layout(NX ? NX : 16, NJ, true, false);
+  constexpr int I1X = NX ? (NX + 15) / 16 : 0;
+  const int N = NTRU_LF(N), P = NTRU_LF(P), Z = NTRU_LF(Z), Lx = NTRU_LF(Lx), Lin = NTRU_LF(Lin);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
-  uint8_t *y0 = base, *y1 = base + G.Ly, *xb = base + 2 * G.Ly;
-  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 2 * G.Ly + G.Lx);
-  uint8_t *raw = base + 2 * G.Ly + G.Lx + G.Lc;       // [h: 2P][r: P][m: P] of the NEXT row (cp.async)
-  uint8_t *mcur = raw + G.Lraw;                       // message of the current row
-  for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
+  uint8_t *base = smem_raw + (size_t)warp * NTRU_LF(warp_bytes);
+  uint8_t *y0 = base, *y1 = base + NTRU_LF(o_y1), *x6 = base + NTRU_LF(o_x6);
+  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + NTRU_LF(o_c));
+  uint8_t *in0 = base + NTRU_LF(o_in);
+  for (int i = lane * 16; i < NTRU_LF(warp_bytes); i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  const uint32_t Q2 = G.qmask | (G.qmask << 16);
+  const uint32_t Q2 = a.qmask | (a.qmask << 16);
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  auto prefetch = [&](size_t row) {
-    prefetch_row(raw, a.h + row * a.h_stride, 2 * G.P, lane);
-    prefetch_row(raw + 2 * G.P, a.r + row * (size_t)G.P, G.P, lane);
-    prefetch_row(raw + 3 * G.P, a.m + row * (size_t)G.P, G.P, lane);
+  auto prefetch = [&](size_t row, uint8_t *in) {
+    prefetch_row(in + kXPad, a.r + row * (size_t)P, P, lane);
+    prefetch_row(in + Lx, a.h + row * a.h_stride, 2 * P, lane);
+    prefetch_row(in + Lx + 2 * P, a.m + row * (size_t)P, P, lane);
     prefetch_commit();
   };
   size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
-  if (row < a.B) prefetch(row);
-  for (; row < a.B; row += nwarps) {
+  if (row < a.B) prefetch(row, in0);
+  int cur = 0;
+  for (; row < a.B; row += nwarps, cur ^= 1) {
+    uint8_t *in = in0 + cur * Lin;
+    uint8_t *xr = in + kXPad, *hr = in + Lx, *mr = in + Lx + 2 * P;
     prefetch_wait();
-    stage_y16<LIMBS>(G, reinterpret_cast<const uint16_t *>(raw), y0, y1, lane);
-    stage_x8(G, raw + 2 * G.P, xb, lane);
-    for (int o = 16 * lane; o < G.P; o += 512) *reinterpret_cast<uint4 *>(mcur + o) = *reinterpret_cast<const uint4 *>(raw + 3 * G.P + o);
-    __syncwarp();
-    if (row + nwarps < a.B) prefetch(row + nwarps);    // the next row's loads fly during this row's products
-    {
-      int acc[NJ][LIMBS][4];
-      conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
-      store_product<NJ, LIMBS>(G, lane, acc, cbuf);
+    if (lane < P - N) {        // the caller's pad columns may hold anything
+      xr[N + lane] = 0;
+      reinterpret_cast<uint16_t *>(hr)[N + lane] = 0;
     }
     __syncwarp();
-    const size_t rbase = row * (size_t)G.P;
-    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+    stage_limbs<LIMBS>(N, Z, Q2, hr, y0, y1, lane);
+    if (LIMBS == 2) stage_x6(N, xr, x6 + kXPad, lane);
+    __syncwarp();
+    if (row + nwarps < a.B) prefetch(row + nwarps, in0 + (cur ^ 1) * Lin);    // in flight during this row's products
+    {
+      int acc[NJ][4];
+      conv_merged<NJ, LIMBS, true, I1X>(Z, y0, y1, xr, x6 + kXPad, lane, acc);      // r in {0, 1, 2}: unsigned multiplier
+      store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
+    }
+    __syncwarp();
+    const size_t rbase = row * (size_t)P;
+#pragma unroll 4
+    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
       uint32_t lo[4], hi[4], rem[4], quo[4];
-      load_lo_hi(G, cbuf, k0, lo, hi);
-      const uint2 mm = *reinterpret_cast<const uint2 *>(mcur + k0);
+      load_lo_hi2(N, cbuf, k0, lo, hi);
+      const uint2 mm = *reinterpret_cast<const uint2 *>(mr + k0);
       const uint32_t mp[4] = {__byte_perm(mm.x, 0u, 0x4140), __byte_perm(mm.x, 0u, 0x4342), __byte_perm(mm.y, 0u, 0x4140),
                               __byte_perm(mm.y, 0u, 0x4342)};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        rem[i] = ((lo[i] & Q2) + (hi[i] & Q2) + mp[i]) & Q2;
-        quo[i] = ((~hi[i] & Q2) + 0x00010001u) & Q2;
+        rem[i] = __vadd2(__vadd2(lo[i], hi[i]), mp[i]) & Q2;
+        quo[i] = __vsub2(0u, hi[i]) & Q2;
       }
-      mask_lanes(rem, G.N - k0);
-      mask_lanes(quo, G.N - k0);
+      if (k0 - 8 * lane + 256 > N) {       // warp-uniform: only the last pass holds columns beyond N
+        mask_tail(rem, N - k0);
+        mask_tail(quo, N - k0);
+      }
       const uint4 rv = make_uint4(rem[0], rem[1], rem[2], rem[3]);
       if (a.value) *reinterpret_cast<uint4 *>(a.value + rbase + k0) = rv;
       if (a.rem) *reinterpret_cast<uint4 *>(a.rem + rbase + k0) = rv;
@@ -313,7 +544,9 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_encrypt_imma(const ImmaEncA
 }
 
 struct ImmaDecArgs {
-  ImmaGeom G;
+  ImmaLayout L;
+  uint32_t qmask;
+  int q, logq;
   size_t B;
   const int8_t *f;
   const uint8_t *fp;
@@ -323,83 +556,98 @@ struct ImmaDecArgs {
   uint16_t *q1, *r1;
 };
 
-template <int NJ, int LIMBS>
-__global__ void __launch_bounds__(kImmaWarps * 32) k_decrypt_imma(const ImmaDecArgs a) {
+template <int NJ, int LIMBS, int NX>
+__global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_decrypt_imma(const ImmaDecArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const ImmaGeom &G = a.G;
+  constexpr ImmaLayout LX = make_layout(NX ? NX : 16, NJ, true, true);
+  constexpr int I1X = NX ? (NX + 15) / 16 : 0;
+  const int N = NTRU_LF(N), P = NTRU_LF(P), Z = NTRU_LF(Z), Lx = NTRU_LF(Lx), Lin = NTRU_LF(Lin);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
-  uint8_t *y0 = base, *y1 = base + G.Ly, *y2 = base + 2 * G.Ly, *xb = base + 3 * G.Ly;
-  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 3 * G.Ly + G.Lx);
-  uint8_t *raw = base + 3 * G.Ly + G.Lx + G.Lc;       // [e: 2P][f: P][fp: P] of the NEXT row (cp.async)
-  for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
+  uint8_t *base = smem_raw + (size_t)warp * NTRU_LF(warp_bytes);
+  uint8_t *y0 = base, *y1 = base + NTRU_LF(o_y1), *y2 = base + NTRU_LF(o_y2), *x6 = base + NTRU_LF(o_x6), *xb = base + NTRU_LF(o_xb);
+  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + NTRU_LF(o_c));
+  uint8_t *in0 = base + NTRU_LF(o_in);
+  for (int i = lane * 16; i < NTRU_LF(warp_bytes); i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  const uint32_t Q2 = G.qmask | (G.qmask << 16);
-  const uint32_t LA2 = (((uint32_t)G.q >> 1) - 1u) * 0x00010001u;       // x > q/2  <=>  bit logq of x + q/2 - 1
+  const uint32_t Q2 = a.qmask | (a.qmask << 16);
+  const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;       // x > q/2  <=>  bit logq of x + q/2 - 1
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  auto prefetch = [&](size_t row) {
-    prefetch_row(raw, a.e + row * (size_t)G.P, 2 * G.P, lane);
-    prefetch_row(raw + 2 * G.P, a.f + row * a.key_stride, G.P, lane);
-    prefetch_row(raw + 3 * G.P, a.fp + row * a.key_stride, G.P, lane);
+  auto prefetch = [&](size_t row, uint8_t *in) {
+    prefetch_row(in + kXPad, a.f + row * a.key_stride, P, lane);
+    prefetch_row(in + Lx, a.e + row * (size_t)P, 2 * P, lane);
+    prefetch_row(in + Lx + 2 * P, a.fp + row * a.key_stride, P, lane);
     prefetch_commit();
   };
   size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
-  if (row < a.B) prefetch(row);
-  for (; row < a.B; row += nwarps) {
-    const size_t rbase = row * (size_t)G.P;
+  if (row < a.B) prefetch(row, in0);
+  int cur = 0;
+  for (; row < a.B; row += nwarps, cur ^= 1) {
+    const size_t rbase = row * (size_t)P;
+    uint8_t *in = in0 + cur * Lin;
+    uint8_t *fr = in + kXPad, *er = in + Lx, *fpr = in + Lx + 2 * P;
     prefetch_wait();
-    stage_y16<LIMBS>(G, reinterpret_cast<const uint16_t *>(raw), y0, y1, lane);
-    stage_x8(G, raw + 2 * G.P, xb, lane);
-    stage_y8(G, raw + 3 * G.P, y2, lane);
-    __syncwarp();
-    if (row + nwarps < a.B) prefetch(row + nwarps);    // the next row's loads fly during this row's products
-    {   // product 1: a = lin(f, e) mod q
-      int acc[NJ][LIMBS][4];
-      conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
-      store_product<NJ, LIMBS>(G, lane, acc, cbuf);
+    if (lane < P - N) {        // the caller's pad columns may hold anything
+      fr[N + lane] = 0;
+      reinterpret_cast<uint16_t *>(er)[N + lane] = 0;
+      fpr[N + lane] = 0;
     }
     __syncwarp();
-    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+    stage_limbs<LIMBS>(N, Z, Q2, er, y0, y1, lane);
+    if (LIMBS == 2) stage_x6(N, fr, x6 + kXPad, lane);
+    stage_rev8(N, Z, fpr, y2, lane);
+    __syncwarp();
+    if (row + nwarps < a.B) prefetch(row + nwarps, in0 + (cur ^ 1) * Lin);    // in flight during this row's products
+    {   // product 1: a = lin(f, e) mod q  (f in {-1, 0, 1}: signed multiplier)
+      int acc[NJ][4];
+      conv_merged<NJ, LIMBS, false, I1X>(Z, y0, y1, fr, x6 + kXPad, lane, acc);
+      store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
       uint32_t lo[4], hi[4], rem[4], quo[4];
-      load_lo_hi(G, cbuf, k0, lo, hi);
+      load_lo_hi2(N, cbuf, k0, lo, hi);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        rem[i] = ((lo[i] & Q2) + (hi[i] & Q2)) & Q2;
-        quo[i] = ((~hi[i] & Q2) + 0x00010001u) & Q2;
+        rem[i] = __vadd2(lo[i], hi[i]) & Q2;
+        quo[i] = __vsub2(0u, hi[i]) & Q2;
       }
-      mask_lanes(rem, G.N - k0);
-      mask_lanes(quo, G.N - k0);
+      if (k0 - 8 * lane + 256 > N) {
+        mask_tail(rem, N - k0);
+        mask_tail(quo, N - k0);
+      }
       if (a.r1) *reinterpret_cast<uint4 *>(a.r1 + rbase + k0) = make_uint4(rem[0], rem[1], rem[2], rem[3]);
       if (a.q1) *reinterpret_cast<uint4 *>(a.q1 + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
       // b = (remainder1 + [remainder1 > q/2]) mod 3  (index.js:117), the multiplier of product 2
       uint32_t bw[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint32_t p0 = rem[2 * i] + (((rem[2 * i] + LA2) >> G.logq) & 0x00010001u);
-        const uint32_t p1 = rem[2 * i + 1] + (((rem[2 * i + 1] + LA2) >> G.logq) & 0x00010001u);
+        const uint32_t p0 = rem[2 * i] + (((rem[2 * i] + LA2) >> a.logq) & 0x00010001u);
+        const uint32_t p1 = rem[2 * i + 1] + (((rem[2 * i + 1] + LA2) >> a.logq) & 0x00010001u);
         bw[i] = mod3_16(p0 & 0xffffu) | (mod3_16(p0 >> 16) << 8) | (mod3_16(p1 & 0xffffu) << 16) | (mod3_16(p1 >> 16) << 24);
       }
       *reinterpret_cast<uint2 *>(xb + kXPad + k0) = make_uint2(bw[0], bw[1]);
     }
     __syncwarp();
     {   // product 2: c = lin(fp, b) mod 3
-      int acc[NJ][1][4];
-      conv_imma<NJ, 1>(G, y2, y2, xb, lane, acc);
-      store_product<NJ, 1>(G, lane, acc, cbuf);
+      int acc[NJ][4];
+      conv_merged<NJ, 1, false, I1X>(Z, y2, y2, xb + kXPad, xb + kXPad, lane, acc);
+      store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
-    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+#pragma unroll 4
+    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
       uint32_t lo[4], hi[4];
-      load_lo_hi(G, cbuf, k0, lo, hi);
+      load_lo_hi2(N, cbuf, k0, lo, hi);
       // remainder2 = (lo + hi) mod 3, quotient2 = -hi = 2 hi (mod 3): one reduction each, on sums that stay below
       // 2^16 (lo, hi <= 4 N); the additions run on packed 16-bit pairs
       uint32_t rem[2] = {0, 0}, quo[2] = {0, 0};
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t s2 = lo[w] + hi[w], d2 = hi[w] << 1;
-        const bool in0 = k0 + 2 * w < G.N, in1 = k0 + 2 * w + 1 < G.N;
-        const uint32_t r0 = in0 ? mod3_16(s2 & 0xffffu) : 0u, r1 = in1 ? mod3_16(s2 >> 16) : 0u;
-        const uint32_t q0 = in0 ? mod3_16(d2 & 0xffffu) : 0u, q1 = in1 ? mod3_16(d2 >> 16) : 0u;
+        const bool v0 = k0 + 2 * w < N, v1 = k0 + 2 * w + 1 < N;
+        const uint32_t r0 = v0 ? mod3_16(s2 & 0xffffu) : 0u, r1 = v1 ? mod3_16(s2 >> 16) : 0u;
+        const uint32_t q0 = v0 ? mod3_16(d2 & 0xffffu) : 0u, q1 = v1 ? mod3_16(d2 >> 16) : 0u;
         rem[w >> 1] |= (r0 | (r1 << 8)) << (16 * (w & 1));
         quo[w >> 1] |= (q0 | (q1 << 8)) << (16 * (w & 1));
       }
@@ -515,23 +763,28 @@ ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays, int nj_bucket) {
 }
 
 template <class K, class A>
-int launch_imma(ntru_ctx *ctx, K kernel, const A &args, int kind, size_t B, int regs_hint) {
-  const size_t smem = (size_t)kImmaWarps * args.G.warp_bytes;
-  // shared-memory attribute and occupancy: once per (context, kernel, footprint), not per launch
+int launch_imma(ntru_ctx *ctx, K kernel, const A &args, int kind, size_t B, int warp_bytes) {
+  const size_t smem = (size_t)kImmaWarps * warp_bytes;
+  // occupancy: once per (context, kernel, footprint), not per launch
   int per_sm = 0;
   for (const auto &c : ctx->imma_cfg)
     if (c.fn == (const void *)kernel && c.smem == smem) per_sm = c.per_sm;
-  // four warps need at most 43 KB (N = 832): below the 48 KB that need no opt-in.  (The opt-in attribute is per
-  // function and device, shared by every context: it must not be cached per context.)
-  if (smem > 48 * 1024) return fail(ctx, NTRU_E_UNSUPPORTED, "IMMA schedule: shared-memory footprint above 48 KB");
   if (per_sm == 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kImmaWarps * 32, smem);
+    // The opt-in is per function and device, shared by every context: always the same value (the largest footprint of
+    // any instantiation, decrypt at N = 832), so contexts cannot undercut each other.
+    constexpr int kMaxSmem = 72 * 1024;
+    if (smem > kMaxSmem) return fail(ctx, NTRU_E_UNSUPPORTED, "IMMA schedule: shared-memory footprint above 72 KB");
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(imma, MaxDynamicSharedMemorySize)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kImmaWarps * 32, smem);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(imma)");
     if (per_sm < 1) per_sm = 1;
     ctx->imma_cfg.push_back({(const void *)kernel, smem, per_sm});
   }
-  (void)regs_hint;
   const size_t want = (B + kImmaWarps - 1) / kImmaWarps;
+#ifdef NTRU_IMMA_CTA_CAP      // occupancy experiments only
+  if (per_sm > NTRU_IMMA_CTA_CAP) per_sm = NTRU_IMMA_CTA_CAP;
+#endif
   const size_t cap = (size_t)ctx->sm_count * per_sm;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   {
@@ -554,14 +807,32 @@ bool imma_supported(const ntru_ctx *ctx) {
   return ((2 * ctx->N - 1 + 15) / 16 + 7) / 8 <= 13 && ctx->q <= 65536;
 }
 
+// N of the instantiations with compile-time geometry (the BASELINE parameter sets), 0 = the bucket's generic one
+static int imma_exact_n(const ntru_ctx *ctx) {
+  const bool two = ctx->q > 256;
+  switch (ctx->N) {
+    case 167: return two ? 0 : 167;
+    case 509: case 677: case 701: case 821: return two ? ctx->N : 0;
+    default: return 0;
+  }
+}
+
 #define NTRU_IMMA_DISPATCH(KERNEL, ARGS, KIND)                                                        \
   do {                                                                                                \
-    const int nj = (ARGS).G.NJ;                                                                       \
+    const int nj = (ARGS).L.NJ, wb = (ARGS).L.warp_bytes;                                             \
     const bool two = ctx->q > 256;                                                                    \
-    if (nj <= 3) return two ? launch_imma(ctx, KERNEL<3, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<3, 1>, ARGS, KIND, B, 0);   \
-    if (nj <= 8) return two ? launch_imma(ctx, KERNEL<8, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<8, 1>, ARGS, KIND, B, 0);   \
-    if (nj <= 11) return two ? launch_imma(ctx, KERNEL<11, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<11, 1>, ARGS, KIND, B, 0); \
-    return two ? launch_imma(ctx, KERNEL<13, 2>, ARGS, KIND, B, 0) : launch_imma(ctx, KERNEL<13, 1>, ARGS, KIND, B, 0);              \
+    switch (imma_exact_n(ctx)) {                                                                      \
+      case 167: return launch_imma(ctx, KERNEL<3, 1, 167>, ARGS, KIND, B, wb);                        \
+      case 509: return launch_imma(ctx, KERNEL<8, 2, 509>, ARGS, KIND, B, wb);                        \
+      case 677: return launch_imma(ctx, KERNEL<11, 2, 677>, ARGS, KIND, B, wb);                       \
+      case 701: return launch_imma(ctx, KERNEL<11, 2, 701>, ARGS, KIND, B, wb);                       \
+      case 821: return launch_imma(ctx, KERNEL<13, 2, 821>, ARGS, KIND, B, wb);                       \
+      default: break;                                                                                 \
+    }                                                                                                 \
+    if (nj <= 3) return two ? launch_imma(ctx, KERNEL<3, 2, 0>, ARGS, KIND, B, wb) : launch_imma(ctx, KERNEL<3, 1, 0>, ARGS, KIND, B, wb);   \
+    if (nj <= 8) return two ? launch_imma(ctx, KERNEL<8, 2, 0>, ARGS, KIND, B, wb) : launch_imma(ctx, KERNEL<8, 1, 0>, ARGS, KIND, B, wb);   \
+    if (nj <= 11) return two ? launch_imma(ctx, KERNEL<11, 2, 0>, ARGS, KIND, B, wb) : launch_imma(ctx, KERNEL<11, 1, 0>, ARGS, KIND, B, wb); \
+    return two ? launch_imma(ctx, KERNEL<13, 2, 0>, ARGS, KIND, B, wb) : launch_imma(ctx, KERNEL<13, 1, 0>, ARGS, KIND, B, wb);              \
   } while (0)
 
 int launch_muldiv_imma(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, int mod_p, void *quo, void *rem) {
@@ -572,15 +843,15 @@ int launch_muldiv_imma(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, 
   a.B = B; a.x = x; a.y = y; a.quo = quo; a.rem = rem;
   const int nj = a.G.NJ;
   if (mod_p) {
-    if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, true>, a, NTRU_K_MULDIV, B, 0);
-    if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, true>, a, NTRU_K_MULDIV, B, 0);
-    if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, true>, a, NTRU_K_MULDIV, B, 0);
-    return launch_imma(ctx, k_muldiv_imma<13, true>, a, NTRU_K_MULDIV, B, 0);
+    if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+    if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+    if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+    return launch_imma(ctx, k_muldiv_imma<13, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
   }
-  if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, false>, a, NTRU_K_MULDIV, B, 0);
-  if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, false>, a, NTRU_K_MULDIV, B, 0);
-  if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, false>, a, NTRU_K_MULDIV, B, 0);
-  return launch_imma(ctx, k_muldiv_imma<13, false>, a, NTRU_K_MULDIV, B, 0);
+  if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+  if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+  if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+  return launch_imma(ctx, k_muldiv_imma<13, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
 }
 
 int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r, const uint8_t *m,
@@ -588,7 +859,8 @@ int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_str
   if (B == 0) return NTRU_OK;
   if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
   ImmaEncArgs a;
-  a.G = make_geom(ctx, 2, imma_bucket(ctx));
+  a.L = make_layout(ctx->N, imma_bucket(ctx), imma_exact_n(ctx) != 0, false);
+  a.qmask = (uint32_t)ctx->q - 1;
   a.B = B; a.h = h; a.h_stride = h_stride; a.r = r; a.m = m; a.value = value; a.quo = quo; a.rem = rem;
   NTRU_IMMA_DISPATCH(k_encrypt_imma, a, NTRU_K_ENC_IMMA);
 }
@@ -598,7 +870,8 @@ int launch_decrypt_imma(ntru_ctx *ctx, size_t B, const int8_t *f, const uint8_t 
   if (B == 0) return NTRU_OK;
   if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
   ImmaDecArgs a;
-  a.G = make_geom(ctx, 3, imma_bucket(ctx));
+  a.L = make_layout(ctx->N, imma_bucket(ctx), imma_exact_n(ctx) != 0, true);
+  a.qmask = (uint32_t)ctx->q - 1; a.q = ctx->q; a.logq = ctx->logq;
   a.B = B; a.f = f; a.fp = fp; a.key_stride = key_stride; a.e = e;
   a.value = value; a.q1 = q1; a.r1 = r1; a.q2 = q2; a.r2 = r2;
   NTRU_IMMA_DISPATCH(k_decrypt_imma, a, NTRU_K_DEC_IMMA);
