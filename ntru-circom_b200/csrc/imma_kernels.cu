@@ -10,10 +10,9 @@
 //     D[k0][K1] = sum_{(t,i0)} A[k0][(t,i0)] * B[(t,i0)][K1]      A = Toeplitz(y) (16 rows),  B = Hankel blocks of x
 //
 // One mma.sync covers 16 outputs k0 x 8 blocks K1 x 32 positions (two t values).  The A fragment of a K step is
-// the same for every column block, so it is loaded once per step: 9 consecutive bytes of the REVERSED y limb
-// array per lane (three aligned LDS.32 + funnel shifts).  The B fragment is one aligned LDS.64 of the zero-padded
-// x array per (column block, step), shared by both limbs of y.  Blocks with K1 - t outside [0, ceil(N/16)) are
-// all zero and skipped (warp-uniform), which leaves 1.25 N^2 executed MACs per limb product.
+// the same for every column block: 9 consecutive bytes of the REVERSED y limb array per lane (three aligned LDS.32 +
+// funnel shifts).  The B fragment is one aligned LDS.64 of the zero-padded x array per (column block, step).  Blocks
+// with K1 - t outside [0, ceil(N/16)) are all zero and skipped: 1.16 N^2 executed MACs per limb product.
 // Index maps (chosen so that every shared-memory access is aligned and the accumulator pairs pack into words):
 //     row m = g + 8 rh  <->  k0 = 2 g + rh          (g = lane / 4, t' = lane % 4)
 //     K slot (hf, t', j) <-> t = 2 s + (t' >> 1),  i0 = 8 (t' & 1) + 4 hf + j
@@ -23,6 +22,11 @@
 // (index.js:358-401): remainder = lo + hi, quotient = -hi, then the message add (encrypt) or
 // the reference's lift (index.js:117) and the second product (decrypt).  All global accesses are 16-byte vectors
 // of the packed uint16 / byte rows.
+//
+// Two forms of the product live here.  conv_merged (encrypt, decrypt: q <= 8192, small multiplier) accumulates both
+// limbs of y in one accumulator set and is the one tuned to the instruction-issue bound described above it;
+// conv_imma (k_muldiv_imma: verifyKeysInputs and the key generation, where y may be any uint16) keeps one accumulator
+// set per limb.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -71,13 +75,13 @@ template <int NJ> struct ImmaShape {
   static constexpr int kDMax = (6 + 4 * NJ) >> 3;
   static constexpr int kSGroups = (2 * NJ + 1 + 3) / 4;     // S <= 2 NJ + 1 K steps, four per group
   // resident CTAs (of four warps) per SM the encrypt / decrypt kernels are compiled for.  Two warps per scheduler
-  // already reach the issue-bound rate (conv_merged); four leave the compiler 128 registers and nothing spills
+  // already reach the issue-bound rate (conv_merged); three leave the compiler 168 registers and nothing spills
   // (at five or six it spills 50 - 150 words and every variant measured slower, profiles/r2_imma_merged.txt).
 #ifndef NTRU_IMMA_SGC
-#define NTRU_IMMA_SGC 3
+#define NTRU_IMMA_SGC 2
 #endif
 #ifndef NTRU_IMMA_MINB
-#define NTRU_IMMA_MINB 4
+#define NTRU_IMMA_MINB 3
 #endif
   static constexpr int kMinBlocks = NJ <= 3 ? 8 : NTRU_IMMA_MINB;
   static constexpr int kSgChunk = NTRU_IMMA_SGC < kSGroups ? NTRU_IMMA_SGC : kSGroups;
@@ -268,13 +272,10 @@ __device__ __forceinline__ void store_product(const ImmaGeom &G, int lane, const
 }
 
 // y (uint16, mod q) -> reversed byte-limb arrays: yrev_l[Z - j] = limb l of y[j]
-// MERGED: the coefficients are reduced mod q first and the high limb is stored as 4 * (y >> 8) (conv_merged)
-template <int LIMBS, bool MERGED = false>
+template <int LIMBS>
 __device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__restrict__ src, uint8_t *y0, uint8_t *y1, int lane) {
-  const uint32_t Q2 = G.qmask | (G.qmask << 16);
   for (int j0 = 8 * lane; j0 < G.N; j0 += 256) {
     uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
-    if (MERGED) v = make_uint4(v.x & Q2, v.y & Q2, v.z & Q2, v.w & Q2);
     const int nv = G.N - j0;                                     // valid coefficients in this vector
     if (nv < 8) {
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -284,11 +285,7 @@ __device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__r
     }
     const int z = G.Z - j0 - 7;                                  // multiple of 8
     *reinterpret_cast<uint2 *>(y0 + z) = make_uint2(__byte_perm(v.w, v.z, 0x4602), __byte_perm(v.y, v.x, 0x4602));
-    if (LIMBS == 2) {
-      uint2 hi = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
-      if (MERGED) hi = make_uint2(hi.x << 2, hi.y << 2);      // every byte < 64: no carry into the next one
-      *reinterpret_cast<uint2 *>(y1 + z) = hi;
-    }
+    if (LIMBS == 2) *reinterpret_cast<uint2 *>(y1 + z) = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
   }
 }
 
@@ -455,6 +452,34 @@ __device__ __forceinline__ void load_lo_hi2(int N, const uint16_t *cbuf, int k0,
   }
 }
 
+// residues mod 3 of both 16-bit lanes of v (each lane < 2^14), the lanes stay packed: floor(x / 3) = (x * 0x5556) >> 16 below
+// 26 000, and the low lane adds less than 2^-4 to the high lane's quotient before the floor.  Five instructions for two
+// coefficients.
+__device__ __forceinline__ uint32_t mod3_2x16(uint32_t v) {
+  const uint32_t qh = __umulhi(v, 0x5556u), ql = __umulhi(v << 16, 0x5556u);
+  return v - 3u * (ql + (qh << 16));
+}
+
+// keeps the first n (of 4) bytes of a word, n any integer
+__device__ __forceinline__ uint32_t keep_bytes(uint32_t v, int n) {
+  return n >= 4 ? v : (n <= 0 ? 0u : v & (0xffffffffu >> (32 - 8 * n)));
+}
+
+// one array of a row by cp.async: `bytes` (multiple of 16), 16 per lane and step; dst and src already point at the lane's
+// first 16 bytes.  BX != 0: the byte count as a compile-time constant (no loop, no address arithmetic).
+template <int BX>
+__device__ __forceinline__ void prefetch_lane(uint32_t dst, const char *src, int bytes, int lane) {
+  if (BX) {
+#pragma unroll
+    for (int o = 0; o < BX; o += 512)
+      if (o + 512 <= BX || o + 16 * lane < BX)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+  } else {
+    for (int o = 0; o + 16 * lane < bytes; o += 512)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+  }
+}
+
 // zeroes the packed uint16 lanes k0 + i >= N of an 8-coefficient vector (branch-free)
 __device__ __forceinline__ void mask_tail(uint32_t (&v)[4], int nv) {
 #pragma unroll
@@ -489,14 +514,18 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
   __syncwarp();
   const uint32_t Q2 = a.qmask | (a.qmask << 16);
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  auto prefetch = [&](size_t row, uint8_t *in) {
-    prefetch_row(in + kXPad, a.r + row * (size_t)P, P, lane);
-    prefetch_row(in + Lx, a.h + row * a.h_stride, 2 * P, lane);
-    prefetch_row(in + Lx + 2 * P, a.m + row * (size_t)P, P, lane);
+  constexpr int PX = NX ? LX.P : 0;
+  const uint32_t in_lane = (uint32_t)__cvta_generic_to_shared(in0) + 16 * lane;
+  auto prefetch = [&](size_t row, int buf) {     // source addresses from the kernel arguments each time: no registers held across the products
+    const uint32_t d = in_lane + buf * Lin;
+    const size_t o = row * (size_t)P + 16 * lane;
+    prefetch_lane<PX>(d + kXPad, reinterpret_cast<const char *>(a.r) + o, P, lane);
+    prefetch_lane<2 * PX>(d + Lx, reinterpret_cast<const char *>(a.h) + (row * a.h_stride * 2 + 16 * lane), 2 * P, lane);
+    prefetch_lane<PX>(d + Lx + 2 * P, reinterpret_cast<const char *>(a.m) + o, P, lane);
     prefetch_commit();
   };
   size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
-  if (row < a.B) prefetch(row, in0);
+  if (row < a.B) prefetch(row, 0);
   int cur = 0;
   for (; row < a.B; row += nwarps, cur ^= 1) {
     uint8_t *in = in0 + cur * Lin;
@@ -510,34 +539,39 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
     stage_limbs<LIMBS>(N, Z, Q2, hr, y0, y1, lane);
     if (LIMBS == 2) stage_x6(N, xr, x6 + kXPad, lane);
     __syncwarp();
-    if (row + nwarps < a.B) prefetch(row + nwarps, in0 + (cur ^ 1) * Lin);    // in flight during this row's products
+    if (row + nwarps < a.B) prefetch(row + nwarps, cur ^ 1);    // in flight during this row's products
     {
       int acc[NJ][4];
       conv_merged<NJ, LIMBS, true, I1X>(Z, y0, y1, xr, x6 + kXPad, lane, acc);      // r in {0, 1, 2}: unsigned multiplier
       store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
-    const size_t rbase = row * (size_t)P;
-#pragma unroll 4
-    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
-      uint32_t lo[4], hi[4], rem[4], quo[4];
-      load_lo_hi2(N, cbuf, k0, lo, hi);
-      const uint2 mm = *reinterpret_cast<const uint2 *>(mr + k0);
-      const uint32_t mp[4] = {__byte_perm(mm.x, 0u, 0x4140), __byte_perm(mm.x, 0u, 0x4342), __byte_perm(mm.y, 0u, 0x4140),
-                              __byte_perm(mm.y, 0u, 0x4342)};
+    // this lane's 8 coefficients of pass 0, per output array
+    const size_t rlane = row * (size_t)P + 8 * lane;
+    uint16_t *const vp = a.value ? a.value + rlane : nullptr, *const rp = a.rem ? a.rem + rlane : nullptr, *const qp = a.quo ? a.quo + rlane : nullptr;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        rem[i] = __vadd2(__vadd2(lo[i], hi[i]), mp[i]) & Q2;
-        quo[i] = __vsub2(0u, hi[i]) & Q2;
+    for (int kb = 0; kb < (NX ? LX.P : 1024); kb += 256) {
+      const int k0 = kb + 8 * lane;
+      if (kb < P && (kb + 256 <= P || k0 < P)) {
+        uint32_t lo[4], hi[4], rem[4], quo[4];
+        load_lo_hi2(N, cbuf, k0, lo, hi);
+        const uint2 mm = *reinterpret_cast<const uint2 *>(mr + k0);
+        const uint32_t mp[4] = {__byte_perm(mm.x, 0u, 0x4140), __byte_perm(mm.x, 0u, 0x4342), __byte_perm(mm.y, 0u, 0x4140),
+                                __byte_perm(mm.y, 0u, 0x4342)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rem[i] = __vadd2(__vadd2(lo[i], hi[i]), mp[i]) & Q2;
+          quo[i] = __vsub2(0u, hi[i]) & Q2;
+        }
+        if (kb + 256 > N) {       // only the last pass holds columns beyond N
+          mask_tail(rem, N - k0);
+          mask_tail(quo, N - k0);
+        }
+        const uint4 rv = make_uint4(rem[0], rem[1], rem[2], rem[3]);
+        if (vp) *reinterpret_cast<uint4 *>(vp + kb) = rv;
+        if (rp) *reinterpret_cast<uint4 *>(rp + kb) = rv;
+        if (qp) *reinterpret_cast<uint4 *>(qp + kb) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
       }
-      if (k0 - 8 * lane + 256 > N) {       // warp-uniform: only the last pass holds columns beyond N
-        mask_tail(rem, N - k0);
-        mask_tail(quo, N - k0);
-      }
-      const uint4 rv = make_uint4(rem[0], rem[1], rem[2], rem[3]);
-      if (a.value) *reinterpret_cast<uint4 *>(a.value + rbase + k0) = rv;
-      if (a.rem) *reinterpret_cast<uint4 *>(a.rem + rbase + k0) = rv;
-      if (a.quo) *reinterpret_cast<uint4 *>(a.quo + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
     }
     __syncwarp();
   }
@@ -572,17 +606,21 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
   const uint32_t Q2 = a.qmask | (a.qmask << 16);
   const uint32_t LA2 = (((uint32_t)a.q >> 1) - 1u) * 0x00010001u;       // x > q/2  <=>  bit logq of x + q/2 - 1
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  auto prefetch = [&](size_t row, uint8_t *in) {
-    prefetch_row(in + kXPad, a.f + row * a.key_stride, P, lane);
-    prefetch_row(in + Lx, a.e + row * (size_t)P, 2 * P, lane);
-    prefetch_row(in + Lx + 2 * P, a.fp + row * a.key_stride, P, lane);
+  constexpr int PX = NX ? LX.P : 0;
+  const uint32_t in_lane = (uint32_t)__cvta_generic_to_shared(in0) + 16 * lane;
+  auto prefetch = [&](size_t row, int buf) {     // source addresses from the kernel arguments each time: no registers held across the products
+    const uint32_t d = in_lane + buf * Lin;
+    const size_t ok = row * a.key_stride + 16 * lane;
+    prefetch_lane<PX>(d + kXPad, reinterpret_cast<const char *>(a.f) + ok, P, lane);
+    prefetch_lane<2 * PX>(d + Lx, reinterpret_cast<const char *>(a.e) + (row * (size_t)(2 * P) + 16 * lane), 2 * P, lane);
+    prefetch_lane<PX>(d + Lx + 2 * P, reinterpret_cast<const char *>(a.fp) + ok, P, lane);
     prefetch_commit();
   };
   size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
-  if (row < a.B) prefetch(row, in0);
+  if (row < a.B) prefetch(row, 0);
   int cur = 0;
   for (; row < a.B; row += nwarps, cur ^= 1) {
-    const size_t rbase = row * (size_t)P;
+    const size_t rlane = row * (size_t)P + 8 * lane;     // this lane's 8 coefficients of pass 0
     uint8_t *in = in0 + cur * Lin;
     uint8_t *fr = in + kXPad, *er = in + Lx, *fpr = in + Lx + 2 * P;
     prefetch_wait();
@@ -596,37 +634,40 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
     if (LIMBS == 2) stage_x6(N, fr, x6 + kXPad, lane);
     stage_rev8(N, Z, fpr, y2, lane);
     __syncwarp();
-    if (row + nwarps < a.B) prefetch(row + nwarps, in0 + (cur ^ 1) * Lin);    // in flight during this row's products
+    if (row + nwarps < a.B) prefetch(row + nwarps, cur ^ 1);    // in flight during this row's products
     {   // product 1: a = lin(f, e) mod q  (f in {-1, 0, 1}: signed multiplier)
       int acc[NJ][4];
       conv_merged<NJ, LIMBS, false, I1X>(Z, y0, y1, fr, x6 + kXPad, lane, acc);
       store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
-#pragma unroll 4
-    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
-      uint32_t lo[4], hi[4], rem[4], quo[4];
-      load_lo_hi2(N, cbuf, k0, lo, hi);
+    {
+      uint16_t *const r1p = a.r1 ? a.r1 + rlane : nullptr, *const q1p = a.q1 ? a.q1 + rlane : nullptr;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        rem[i] = __vadd2(lo[i], hi[i]) & Q2;
-        quo[i] = __vsub2(0u, hi[i]) & Q2;
-      }
-      if (k0 - 8 * lane + 256 > N) {
-        mask_tail(rem, N - k0);
-        mask_tail(quo, N - k0);
-      }
-      if (a.r1) *reinterpret_cast<uint4 *>(a.r1 + rbase + k0) = make_uint4(rem[0], rem[1], rem[2], rem[3]);
-      if (a.q1) *reinterpret_cast<uint4 *>(a.q1 + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
-      // b = (remainder1 + [remainder1 > q/2]) mod 3  (index.js:117), the multiplier of product 2
-      uint32_t bw[2];
+      for (int kb = 0; kb < (NX ? LX.P : 1024); kb += 256) {
+        const int k0 = kb + 8 * lane;
+        if (kb < P && (kb + 256 <= P || k0 < P)) {
+          uint32_t lo[4], hi[4], rem[4], quo[4];
+          load_lo_hi2(N, cbuf, k0, lo, hi);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t p0 = rem[2 * i] + (((rem[2 * i] + LA2) >> a.logq) & 0x00010001u);
-        const uint32_t p1 = rem[2 * i + 1] + (((rem[2 * i + 1] + LA2) >> a.logq) & 0x00010001u);
-        bw[i] = mod3_16(p0 & 0xffffu) | (mod3_16(p0 >> 16) << 8) | (mod3_16(p1 & 0xffffu) << 16) | (mod3_16(p1 >> 16) << 24);
+          for (int i = 0; i < 4; ++i) {
+            rem[i] = __vadd2(lo[i], hi[i]) & Q2;
+            quo[i] = __vsub2(0u, hi[i]) & Q2;
+          }
+          if (kb + 256 > N) {       // only the last pass holds columns beyond N
+            mask_tail(rem, N - k0);
+            mask_tail(quo, N - k0);
+          }
+          if (r1p) *reinterpret_cast<uint4 *>(r1p + kb) = make_uint4(rem[0], rem[1], rem[2], rem[3]);
+          if (q1p) *reinterpret_cast<uint4 *>(q1p + kb) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
+          // b = (remainder1 + [remainder1 > q/2]) mod 3  (index.js:117), the multiplier of product 2; a masked
+          // column gives 0
+          uint32_t b2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) b2[i] = mod3_2x16(rem[i] + (((rem[i] + LA2) >> a.logq) & 0x00010001u));
+          *reinterpret_cast<uint2 *>(xb + kXPad + k0) = make_uint2(__byte_perm(b2[0], b2[1], 0x6420), __byte_perm(b2[2], b2[3], 0x6420));
+        }
       }
-      *reinterpret_cast<uint2 *>(xb + kXPad + k0) = make_uint2(bw[0], bw[1]);
     }
     __syncwarp();
     {   // product 2: c = lin(fp, b) mod 3
@@ -635,26 +676,33 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
       store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
-#pragma unroll 4
-    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
-      uint32_t lo[4], hi[4];
-      load_lo_hi2(N, cbuf, k0, lo, hi);
-      // remainder2 = (lo + hi) mod 3, quotient2 = -hi = 2 hi (mod 3): one reduction each, on sums that stay below
-      // 2^16 (lo, hi <= 4 N); the additions run on packed 16-bit pairs
-      uint32_t rem[2] = {0, 0}, quo[2] = {0, 0};
+    {
+      uint8_t *const vp = a.value ? a.value + rlane : nullptr, *const r2p = a.r2 ? a.r2 + rlane : nullptr, *const q2p = a.q2 ? a.q2 + rlane : nullptr;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t s2 = lo[w] + hi[w], d2 = hi[w] << 1;
-        const bool v0 = k0 + 2 * w < N, v1 = k0 + 2 * w + 1 < N;
-        const uint32_t r0 = v0 ? mod3_16(s2 & 0xffffu) : 0u, r1 = v1 ? mod3_16(s2 >> 16) : 0u;
-        const uint32_t q0 = v0 ? mod3_16(d2 & 0xffffu) : 0u, q1 = v1 ? mod3_16(d2 >> 16) : 0u;
-        rem[w >> 1] |= (r0 | (r1 << 8)) << (16 * (w & 1));
-        quo[w >> 1] |= (q0 | (q1 << 8)) << (16 * (w & 1));
+      for (int kb = 0; kb < (NX ? LX.P : 1024); kb += 256) {
+        const int k0 = kb + 8 * lane;
+        if (kb < P && (kb + 256 <= P || k0 < P)) {
+          uint32_t lo[4], hi[4];
+          load_lo_hi2(N, cbuf, k0, lo, hi);
+          // remainder2 = (lo + hi) mod 3, quotient2 = -hi = 2 hi (mod 3): lo, hi <= 4 N, every sum stays below 2^14 and
+          // the 16-bit lanes never carry into each other
+          uint32_t r3[4], q3[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            r3[i] = mod3_2x16(lo[i] + hi[i]);
+            q3[i] = mod3_2x16(hi[i] << 1);
+          }
+          uint2 rv = make_uint2(__byte_perm(r3[0], r3[1], 0x6420), __byte_perm(r3[2], r3[3], 0x6420));
+          uint2 qv = make_uint2(__byte_perm(q3[0], q3[1], 0x6420), __byte_perm(q3[2], q3[3], 0x6420));
+          if (kb + 256 > N) {       // only the last pass holds columns beyond N
+            rv = make_uint2(keep_bytes(rv.x, N - k0), keep_bytes(rv.y, N - k0 - 4));
+            qv = make_uint2(keep_bytes(qv.x, N - k0), keep_bytes(qv.y, N - k0 - 4));
+          }
+          if (vp) *reinterpret_cast<uint2 *>(vp + kb) = rv;
+          if (r2p) *reinterpret_cast<uint2 *>(r2p + kb) = rv;
+          if (q2p) *reinterpret_cast<uint2 *>(q2p + kb) = qv;
+        }
       }
-      const uint2 rv = make_uint2(rem[0], rem[1]);
-      if (a.value) *reinterpret_cast<uint2 *>(a.value + rbase + k0) = rv;
-      if (a.r2) *reinterpret_cast<uint2 *>(a.r2 + rbase + k0) = rv;
-      if (a.q2) *reinterpret_cast<uint2 *>(a.q2 + rbase + k0) = make_uint2(quo[0], quo[1]);
     }
     __syncwarp();
   }
