@@ -68,10 +68,14 @@ enum {
                                product accumulated on top of it in the same TMEM buffer (remainder = lo + hi: N^2 multiply-adds
                                plus the diagonal blocks); 1 = the full cyclic product and the hi product separately (1.5 N^2,
                                the round-1 order).  Same results bit for bit; each is the other's cross-check in the tests. */
-  NTRU_OPT_EPILOGUE = 8     /* tcgen05 schedule: 1 = two groups of epilogue warps, one per TMEM accumulator buffer; 2 = one group,
+  NTRU_OPT_EPILOGUE = 8,    /* tcgen05 schedule: 1 = two groups of epilogue warps, one per TMEM accumulator buffer; 2 = one group,
                                every warp drains every phase (the buffer goes back to the MMAs after half the time); 0 (default)
                                = one group where it measured faster (first and second decrypt product up to N = 512).  Same
                                results bit for bit. */
+  NTRU_OPT_IMMA_FORM = 9    /* IMMA schedule (distinct keys, small batches): 0 (default) = the instantiation compiled for this N
+                               where there is one (the BASELINE N: exact Toeplitz band, every offset a constant); 1 = always the
+                               generic instantiation of the N bucket.  Same results bit for bit; each is the other's cross-check
+                               in the tests. */
 };
 
 /* kernel kinds reported by ntru_timing_read */

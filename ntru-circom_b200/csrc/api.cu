@@ -378,6 +378,10 @@ int ntru_set_option(ntru_ctx *ctx, int key, long value) {
         if (ctx->has_priv) { int rc = umma_prepare_private(ctx); if (rc) return rc; }
       }
       return NTRU_OK;
+    case NTRU_OPT_IMMA_FORM:
+      if (value < 0 || value > 1) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_IMMA_FORM must be 0 or 1");
+      ctx->opt_imma_form = (int)value;
+      return NTRU_OK;
     case NTRU_OPT_DEC1_FORM:
       if (value < 0 || value > 2) return fail(ctx, NTRU_E_PARAM, "NTRU_OPT_DEC1_FORM must be 0, 1 or 2");
       ctx->opt_dec1_form = (int)value;

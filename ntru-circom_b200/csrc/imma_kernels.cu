@@ -857,6 +857,7 @@ bool imma_supported(const ntru_ctx *ctx) {
 
 // N of the instantiations with compile-time geometry (the BASELINE parameter sets), 0 = the bucket's generic one
 static int imma_exact_n(const ntru_ctx *ctx) {
+  if (ctx->opt_imma_form == 1) return 0;
   const bool two = ctx->q > 256;
   switch (ctx->N) {
     case 167: return two ? 0 : 167;

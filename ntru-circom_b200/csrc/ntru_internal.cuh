@@ -74,6 +74,7 @@ struct ntru_ctx {
   uint32_t xchg_epoch = 0;
   size_t chunk_rows = 32768;
   int opt_path = 0;
+  int opt_imma_form = 0;           // NTRU_OPT_IMMA_FORM: 0 auto (compile-time N where instantiated), 1 the bucket's generic kernel
   int opt_epilogue = 0;            // NTRU_OPT_EPILOGUE: 0 auto, 1 two epilogue groups (one per TMEM buffer), 2 one group
   int opt_lohi = 0;                // NTRU_OPT_SCHEDULE: 0 = lo + hi phases (default), 1 = the cyc + hi order of round 1
   int opt_dec1_form = 0;           // NTRU_OPT_DEC1_FORM: 0 auto, 1 byte limbs, 2 fp16 tiles (256 < q <= 2048 only)

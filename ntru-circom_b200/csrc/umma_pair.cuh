@@ -780,18 +780,33 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
                   for (int jj = 0; jj < 8; ++jj) pk[jj] &= Q2;
                   if (a.o8_cyc) {
                     // multiplier of the second product: any byte congruent to b = (x + [x > q/2]) mod 3 (index.js:117)
-                    // will do, the reduction mod 3 happens on the accumulators of DEC2.  y = x + [x > q/2] <= q, and
-                    // 64 = 1 (mod 3):  b' = (y & 63) + (y >> 6) <= 63 + 128, two coefficients per 32-bit word.
+                    // will do, the reduction mod 3 happens on the accumulators of DEC2.  64 = 1 (mod 3), so a value
+                    // y is folded to (y & 63) + (y >> 6) = y - 63 (y >> 6) <= 63 + 128, two coefficients per word.
+                    if (logq & 1) {
+                      // q = 2 (mod 3) and q/2 = 1:  (x + q/2 - 1) mod q = x + q/2 - 1 - q [x > q/2] = x + [x > q/2] (mod 3):
+                      // the comparison is the carry the mask drops.  Five instructions per word instead of eight.
 #pragma unroll
-                    for (int wd = 0; wd < 4; ++wd) {
-                      uint32_t y2[2];
+                      for (int wd = 0; wd < 4; ++wd) {
+                        uint32_t y2[2];
 #pragma unroll
-                      for (int i = 0; i < 2; ++i) {
-                        const uint32_t x = pk[2 * wd + i];
-                        const uint32_t y = x + (((x + LA2) >> logq) & 0x00010001u);
-                        y2[i] = (y & 0x003F003Fu) + ((y >> 6) & 0x00FF00FFu);
+                        for (int i = 0; i < 2; ++i) {
+                          const uint32_t y = (pk[2 * wd + i] + LA2) & Q2;
+                          y2[i] = y - 63u * ((y >> 6) & 0x00FF00FFu);
+                        }
+                        bres[4 * j + wd] = __byte_perm(y2[0], y2[1], 0x6420);
                       }
-                      bres[4 * j + wd] = __byte_perm(y2[0], y2[1], 0x6420);
+                    } else {
+#pragma unroll
+                      for (int wd = 0; wd < 4; ++wd) {
+                        uint32_t y2[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                          const uint32_t x = pk[2 * wd + i];
+                          const uint32_t y = x + (((x + LA2) >> logq) & 0x00010001u);      // <= q
+                          y2[i] = y - 63u * ((y >> 6) & 0x00FF00FFu);
+                        }
+                        bres[4 * j + wd] = __byte_perm(y2[0], y2[1], 0x6420);
+                      }
                     }
                   }
                 }

@@ -86,6 +86,10 @@ class Engine:
         """tcgen05 schedule: 0 auto, 1 two epilogue groups (one per TMEM buffer), 2 one group on every phase."""
         self.set_option(_lib.NTRU_OPT_EPILOGUE, int(mode))
 
+    def set_imma_form(self, generic: bool):
+        """IMMA schedule: False = the kernel compiled for this N where there is one, True = the N bucket's generic kernel."""
+        self.set_option(_lib.NTRU_OPT_IMMA_FORM, 1 if generic else 0)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ntru_launch_count(self._h))

@@ -811,10 +811,14 @@ def test_pad_columns_of_device_rows_do_not_count(cfg, nb, engines, golden):
     eng.set_path(0)
 
 
-@pytest.mark.parametrize("N,q", [(167, 128), (640, 4096), (677, 2048), (832, 4096)])
+@pytest.mark.parametrize("N,q", [(167, 128), (509, 2048), (640, 4096), (676, 2048), (677, 2048), (701, 8192), (821, 4096),
+                                 (832, 4096)])
 def test_distinct_keys_device_rows_all_schedules_agree(N, q, nb):
     """Distinct keys per row through the device-pointer entry points: the IMMA schedule against the fp32 schedule, bit
-    for bit over whole pitched rows (pad columns written as zero), with a batch that is not a multiple of any tile."""
+    for bit over whole pitched rows (pad columns written as zero), with a batch that is not a multiple of any tile.
+    At the BASELINE N the IMMA kernels are instantiated for that N (exact Toeplitz band, constant offsets): the bucket's
+    generic instantiation (NTRU_OPT_IMMA_FORM = 1) is run as well and must agree bit for bit; and whatever a caller
+    leaves in the pad columns N..P-1 of h, f, fp, r, m and e must not count (the kernels zero them in shared memory)."""
     torch = pytest.importorskip("torch")
     p, dev = 3, "cuda"
     eng = nb.Engine(N, p, q, 0)
@@ -842,6 +846,29 @@ def test_distinct_keys_device_rows_all_schedules_agree(N, q, nb):
         assert not x[:, N:].any(), (N, q)
     want_e = o.encrypt_batch(h[:3, :N].cpu().numpy().astype(np.int64) & 0xFFFF, r[:3, :N].cpu().numpy(), m[:3, :N].cpu().numpy(), q)
     assert np.array_equal(outs[nb.PATH_IMMA][0][:3].cpu().numpy().view(np.uint16)[:, :N], want_e["value"])
+    # generic instantiation of the bucket, then dirty pad columns in every input (both forms)
+    eng.set_path(nb.PATH_IMMA)
+    dirty = [t.clone() for t in (h, f, fp, r, m)]
+    for t, fill in zip(dirty, (0x7ABC, -1, 0xEE, 2, 0xA5)):
+        t[:, N:] = fill
+    hd, fd, fpd, rd, md = dirty
+    for generic in (True, False):
+        eng.set_imma_form(generic)
+        for (h_, f_, fp_, r_, m_, dirty_e) in ((h, f, fp, r, m, False), (hd, fd, fpd, rd, md, True)):
+            if not generic and not dirty_e:
+                continue                                  # that is outs[PATH_IMMA]
+            bufs = [torch.full((B, P), 7, dtype=torch.int16, device=dev) for _ in range(4)] + \
+                   [torch.full((B, P), 7, dtype=torch.uint8, device=dev) for _ in range(2)]
+            val, quo, q1, r1, pv, q2 = bufs
+            eng.encrypt_dev(B, r_, m_, value=val, quotientE=quo, h_rows=h_)
+            eng.sync()
+            e = val.clone()
+            if dirty_e:
+                e[:, N:] = 0x7FFF
+            eng.decrypt_dev(B, e, value=pv, quotient1=q1, remainder1=r1, quotient2=q2, f_rows=f_, fp_rows=fp_)
+            eng.sync()
+            for x, y in zip(outs[nb.PATH_IMMA], bufs):
+                assert torch.equal(x, y), (N, q, generic, dirty_e)
     eng.close()
 
 
