@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of library builds on the distinct-key configs: gpu_call_ap.sh "<configs>" variant...
+# A/B of library builds on the distinct-key configs: gpu_ab_distinct.sh "<configs>" variant...
 cfgs=$1; shift
 for v in "$@"; do
   echo "== $v" | tee -a gpurun_out/r2_imma_ab2.txt
