@@ -329,7 +329,11 @@ def other_configs(rank, world, local_rank, hbm_gbs, which):
                                       f"{B} ciphertexts per GPU, encrypt+decrypt, full witness", "scaling": "weak",
                           "rows_per_gpu": B, "ms": ms, "ct_per_s": world * B / (ms * 1e-3), "kernel_ms": kt, "keygen_s": keygen_s,
                           "GBps_18N_per_gpu": 18 * N * B / (ms * 1e-3) / 1e9, "frac_hbm": 18 * N * B / (ms * 1e-3) / 1e9 / hbm_gbs,
-                          "TMAC_per_s_3N2": macs, "frac_of_imma_peak_570_TMACs": macs / 570.0, "collective": "none",
+                          "TMAC_per_s_3N2": macs, "frac_of_imma_peak_570_TMACs": macs / 570.0,
+                          # byte-limb products the IMMA schedule has to execute: 2 (r*h) + 2 (f*e) + 1 (fp*b) per ciphertext
+                          "byte_TMAC_per_s_5N2": macs * 5 / 3, "frac_of_imma_peak_on_byte_macs": macs * 5 / 3 / 570.0,
+                          "bound": "instruction issue of the schedulers: 8.4 cycles per IMMA.16832 + ~1.2 per other instruction "
+                                   "(DESIGN.md 3.3, profiles/r2_imma_merged.txt)", "collective": "none",
                           "matches_cuda_core_schedule_bit_for_bit": bool(same),
                           "roundtrip_equals_message": bool(torch.equal(pv[:, :N], m[:, :N]))}
         eng.close()
