@@ -250,3 +250,19 @@ def test_seeds_of_the_gpu_class_tests_decrypt_in_the_oracle(golden):
     k.generatePrivateKeyF()
     k.generateNewPublicKeyGH()
     assert k.decryptStr(k.encryptStr("Big polys")) == "Big polys"
+
+
+def test_packed_mod3_identity_of_the_imma_output_passes():
+    """`mod3_2x16` (csrc/imma_kernels.cu): residues mod 3 of two packed 16-bit coefficients from two `umulhi` by 0x5556.
+    The kernels feed it lanes below 2^14 (sums of at most two product coefficients <= 4 N, or remainder1 + 1 <= q <= 8192);
+    the identity is checked here for every low lane against a spread of high lanes, including the extremes."""
+    lo = np.arange(0, 1 << 14, dtype=np.uint64)
+    his = sorted(set(list(range(0, 64)) + list(range((1 << 14) - 64, 1 << 14)) + list(range(0, 1 << 14, 37))))
+    m32 = np.uint64(0xFFFFFFFF)
+    for hi in his:
+        v = (np.uint64(hi) << np.uint64(16)) | lo
+        qh = (v * np.uint64(0x5556)) >> np.uint64(32)
+        ql = (((v << np.uint64(16)) & m32) * np.uint64(0x5556)) >> np.uint64(32)
+        r = (v - np.uint64(3) * (ql + (qh << np.uint64(16)))) & m32
+        assert np.array_equal(r & np.uint64(0xFFFF), lo % np.uint64(3)), hi
+        assert np.all((r >> np.uint64(16)) == np.uint64(hi % 3)), hi
