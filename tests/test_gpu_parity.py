@@ -279,6 +279,42 @@ def test_parameter_sets_outside_baseline(N, q, nb):
     eng.close()
 
 
+def _imma_fuzz_sets():
+    rng = np.random.default_rng(20261019)
+    ns = set(int(x) for x in rng.integers(8, 833, size=22))
+    # geometry edges of the IMMA kernels: N = 0, 1, 2 mod 16 (the last Toeplitz step is one block shorter at N = 1 mod 16),
+    # both sides of every accumulator bucket (3 / 8 / 11 / 13 column blocks: N = 192 / 512 / 704 / 832)
+    ns |= {16, 17, 18, 191, 192, 193, 208, 209, 496, 497, 512, 528, 529, 672, 673, 703, 704, 705, 720, 721, 816, 817, 831, 832}
+    qs = [4, 16, 128, 256, 512, 2048, 4096, 8192]
+    return sorted((n, qs[(n * 7 + n // 16) % len(qs)]) for n in ns)
+
+
+@pytest.mark.parametrize("N,q", _imma_fuzz_sets())
+def test_imma_schedule_generic_geometry_vs_oracle(N, q, nb):
+    """The IMMA kernels of an N bucket run every (step, block) of the bucket on operands zero-padded that far; only the
+    BASELINE N have kernels compiled for them.  Seeded spread of N over all four buckets and the geometry edges, distinct
+    keys, every witness array against the oracle (rows that drive the accumulators to their extremes included)."""
+    p, B = 3, 37
+    rng = np.random.default_rng(7 * N + q)
+    hh = rng.integers(0, q, size=(B, N)); ff = rng.integers(-1, 2, size=(B, N)); pp = rng.integers(0, p, size=(B, N))
+    r = rng.integers(0, 3, size=(B, N)); m = rng.integers(0, 2, size=(B, N))
+    r[0], m[0], hh[0] = 2, (255 if q > 256 else 1), q - 1          # largest product coefficients
+    ff[1], hh[1] = -1, q - 1
+    pp[2] = 2
+    want_e = o.encrypt_batch(hh, r, m, q)
+    want_d = o.decrypt_batch(ff, pp, want_e["value"], q, p)
+    eng = nb.Engine(N, p, q, 0)
+    eng.set_path(nb.PATH_IMMA)
+    enc = eng.encrypt_batch(r.astype(np.uint8), m.astype(np.uint8), h=hh.astype(np.uint16))
+    dec = eng.decrypt_batch(enc["value"], f=ff.astype(np.int8), fp=pp.astype(np.uint8))
+    assert eng.last_path == nb.PATH_IMMA
+    for k in ENC_KEYS:
+        assert np.array_equal(enc[k], want_e[k]), (N, q, k)
+    for k in DEC_KEYS:
+        assert np.array_equal(dec[k], want_d[k]), (N, q, k)
+    eng.close()
+
+
 @pytest.mark.parametrize("N,q", [(167, 128), (509, 2048), (512, 2048), (513, 2048), (545, 2048), (640, 4096), (641, 2048), (677, 2048), (701, 8192),
                                  (768, 8192), (821, 4096), (833, 2048), (897, 2048), (1024, 8192)])
 def test_many_tiles_per_cluster_outside_baseline(N, q, nb):
