@@ -23,10 +23,9 @@
 // the reference's lift (index.js:117) and the second product (decrypt).  All global accesses are 16-byte vectors
 // of the packed uint16 / byte rows.
 //
-// Two forms of the product live here.  conv_merged (encrypt, decrypt: q <= 8192, small multiplier) accumulates both
-// limbs of y in one accumulator set and is the one tuned to the instruction-issue bound described above it;
-// conv_imma (k_muldiv_imma: verifyKeysInputs and the key generation, where y may be any uint16) keeps one accumulator
-// set per limb.
+// One product routine, conv_band, in two forms.  MERGE (encrypt, decrypt: q <= 8192, small multiplier) accumulates both
+// limbs of y in one accumulator set; it is written to the instruction-issue bound described above it.  Without MERGE
+// (k_muldiv_imma: verifyKeysInputs and the key generation, where y may be any uint16) each limb has its accumulator set.
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,18 +38,6 @@ namespace {
 
 constexpr int kImmaWarps = 4;      // warps (= ciphertexts in flight) per CTA
 constexpr int kXPad = 112;         // zero bytes in front of x: block index K1 - t reaches -7
-
-struct ImmaGeom {
-  int N, P, q, logq;
-  uint32_t qmask;
-  int I1;            // 16-blocks of x: ceil(N / 16)
-  int S;             // K steps (two t values each): t = 0 .. floor((N + 14) / 16)
-  int NJ;            // 8-column blocks: ceil(ceil((2N - 1) / 16) / 8)
-  int Z;             // reversed limb arrays: yrev[z] = y[Z - z]
-  int Ly, Lx, Lc;    // bytes of one limb array, of the padded x array, of the product buffer
-  int Lraw;          // bytes of the prefetch area: the next row's inputs as they lie in global memory (4 P)
-  int warp_bytes;
-};
 
 __device__ __forceinline__ void imma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -87,74 +74,6 @@ template <int NJ> struct ImmaShape {
   static constexpr int kSgChunk = NTRU_IMMA_SGC < kSGroups ? NTRU_IMMA_SGC : kSGroups;
 };
 
-// acc[jn][l] = Toeplitz(y limb l) x Hankel(x).  Fully unrolled over (s, jn): every shared-memory address is
-// base register + immediate and the accumulator index is static.
-template <int NJ, int LIMBS>
-__device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, const uint8_t *y1, const uint8_t *xb, int lane,
-                                          int (&acc)[NJ][LIMBS][4]) {
-  const int g = lane >> 2, tq = lane & 3;
-#pragma unroll
-  for (int jn = 0; jn < NJ; ++jn)
-#pragma unroll
-    for (int l = 0; l < LIMBS; ++l) acc[jn][l][0] = acc[jn][l][1] = acc[jn][l][2] = acc[jn][l][3] = 0;
-  // A fragment: bytes z0-1 .. z0+7 of the reversed array, z0 = Z - 32 s - 16 (t'>>1) - 2 g + 8 (t'&1):
-  // a1 = [z0-1, z0+3)  a0 = [z0, z0+4)  a3 = [z0+3, z0+7)  a2 = [z0+4, z0+8)
-  const int zfirst = G.Z - 16 * (tq >> 1) - 2 * g + 8 * (tq & 1) - 1;
-  const int zb = zfirst & ~3;
-  const uint32_t sh0 = 8u * (uint32_t)(zfirst - zb), sh1 = sh0 + 8u;
-  const uint8_t *pa0 = y0 + zb, *pa1 = y1 + zb;
-  const uint8_t *pb = xb + kXPad + 16 * (g - (tq >> 1)) + 8 * (tq & 1);
-  // B fragments: the Hankel block of x that (column block jn, K step s) multiplies starts at 128 jn - 32 s
-  // = 128 d - 32 s4 for jn = sg + d, s = 4 sg + s4 -- it does not depend on the step group sg.  Up to N = 512 the
-  // 4 (kDMax + 1) distinct fragments are loaded ONCE per product and stay in registers (the compiler does not merge
-  // the per-(jn, s) loads: 164 of the 308 shared-memory loads of a product at N = 677).  Above that the 56-64 extra
-  // registers cost a resident CTA per SM and the kernel gets slower (B200, N = 677: 91 against 104 M ct/s; N = 509:
-  // 167 against 161; profiles/r2_imma_bfrag_experiment.jsonl), so the large instantiations keep the loads.
-  constexpr bool kBReg = NJ <= 8;
-  uint2 bf[kBReg ? ImmaShape<NJ>::kDMax + 1 : 1][4];
-  if (kBReg) {
-#pragma unroll
-    for (int d = 0; d <= ImmaShape<NJ>::kDMax; ++d)
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) bf[d][s4] = *reinterpret_cast<const uint2 *>(pb + 128 * d - 32 * s4);
-  }
-#pragma unroll
-  for (int sg = 0; sg < ImmaShape<NJ>::kSGroups; ++sg) {
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-      const int s = 4 * sg + s4;
-      if (s < G.S) {
-        uint32_t a[LIMBS][4];
-        {
-          const uint32_t *w = reinterpret_cast<const uint32_t *>(pa0 - 32 * s);
-          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-          a[0][0] = __funnelshift_rc(w0, w1, sh1);
-          a[0][1] = __funnelshift_r(w0, w1, sh0);
-          a[0][2] = __funnelshift_rc(w1, w2, sh1);
-          a[0][3] = __funnelshift_r(w1, w2, sh0);
-        }
-        if (LIMBS == 2) {
-          const uint32_t *w = reinterpret_cast<const uint32_t *>(pa1 - 32 * s);
-          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-          a[LIMBS - 1][0] = __funnelshift_rc(w0, w1, sh1);
-          a[LIMBS - 1][1] = __funnelshift_r(w0, w1, sh0);
-          a[LIMBS - 1][2] = __funnelshift_rc(w1, w2, sh1);
-          a[LIMBS - 1][3] = __funnelshift_r(w1, w2, sh0);
-        }
-#pragma unroll
-        for (int d = 0; d <= ImmaShape<NJ>::kDMax; ++d) {
-          const int jn = sg + d;
-          if (jn < NJ) {
-            const uint2 b = kBReg ? bf[kBReg ? d : 0][s4] : *reinterpret_cast<const uint2 *>(pb + 128 * jn - 32 * s);
-            imma_u8s8(acc[jn][0], a[0], b.x, b.y);
-            if (LIMBS == 2) imma_u8s8(acc[jn][LIMBS - 1], a[LIMBS - 1], b.x, b.y);
-          }
-        }
-      }
-    }
-  }
-}
-
 // The encrypt / decrypt form of the product (round 2): ONE accumulator set for both limbs of y, every operand fragment
 // read from shared memory once, no run-time condition inside the product.
 //  * What the kernels are bound by (scripts/imma_pattern_probe.cu, profiles/r2_imma_pattern_probe.txt and the
@@ -174,13 +93,18 @@ __device__ __forceinline__ void conv_imma(const ImmaGeom &G, const uint8_t *y0, 
 //    an mma.sync costs a WARPSYNC and a BRA per instruction).  I1X = 0, any N of the bucket: every (step, block) of the
 //    bucket runs; the limb arrays are zero below their first coefficient as far as the last step of the bucket reads
 //    (make_layout), the x arrays are zero outside [0, N).
-template <int NJ, int LIMBS, bool XU8, int I1X>
-__device__ __forceinline__ void conv_merged(int Z, const uint8_t *y0, const uint8_t *y1, const uint8_t *x0, const uint8_t *x6, int lane,
-                                            int (&acc)[NJ][4]) {
+//  * MERGE = false (k_muldiv_imma: y may be any uint16, its high limb does not fit a quarter of a byte): one accumulator
+//    set per limb, both limbs multiply the same B fragment, the limbs are recombined when the product is stored.
+template <int NJ, int LIMBS, bool MERGE, bool XU8, int I1X>
+__device__ __forceinline__ void conv_band(int Z, const uint8_t *y0, const uint8_t *y1, const uint8_t *x0, const uint8_t *x6, int lane,
+                                          int (&acc)[NJ][MERGE ? 1 : LIMBS][4]) {
+  constexpr int NACC = MERGE ? 1 : LIMBS;
   constexpr int SG = ImmaShape<NJ>::kSGroups, DM = ImmaShape<NJ>::kDMax, SGC = ImmaShape<NJ>::kSgChunk;
   const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
-  for (int jn = 0; jn < NJ; ++jn) acc[jn][0] = acc[jn][1] = acc[jn][2] = acc[jn][3] = 0;
+  for (int jn = 0; jn < NJ; ++jn)
+#pragma unroll
+    for (int l = 0; l < NACC; ++l) acc[jn][l][0] = acc[jn][l][1] = acc[jn][l][2] = acc[jn][l][3] = 0;
   // A fragment: bytes z0-1 .. z0+7 of the reversed array, z0 = Z - 32 s - 16 (t'>>1) - 2 g + 8 (t'&1):
   // a1 = [z0-1, z0+3)  a0 = [z0, z0+4)  a3 = [z0+3, z0+7)  a2 = [z0+4, z0+8)
   const int zfirst = Z - 16 * (tq >> 1) - 2 * g + 8 * (tq & 1) - 1;
@@ -217,15 +141,16 @@ __device__ __forceinline__ void conv_merged(int Z, const uint8_t *y0, const uint
           if (d <= dlim && c0 + d < NJ) {
             uint2 b[LIMBS];
 #pragma unroll
-            for (int l = 0; l < LIMBS; ++l) b[l] = *reinterpret_cast<const uint2 *>((l ? pb1 : pb0) + 128 * d - 32 * s4);
+            for (int l = 0; l < LIMBS; ++l)
+              b[l] = (l && !MERGE) ? b[0] : *reinterpret_cast<const uint2 *>((l ? pb1 : pb0) + 128 * d - 32 * s4);
 #pragma unroll
             for (int i = 0; i < SGC; ++i) {
               const int sg = c0 + i;
               if (sg < SG && sg + d < NJ && sg < nsg) {
 #pragma unroll
                 for (int l = 0; l < LIMBS; ++l) {
-                  if (XU8) imma_u8u8(acc[sg + d], a[l][i], b[l].x, b[l].y);
-                  else imma_u8s8(acc[sg + d], a[l][i], b[l].x, b[l].y);
+                  if (XU8) imma_u8u8(acc[sg + d][MERGE ? 0 : l], a[l][i], b[l].x, b[l].y);
+                  else imma_u8s8(acc[sg + d][MERGE ? 0 : l], a[l][i], b[l].x, b[l].y);
                 }
               }
             }
@@ -236,128 +161,22 @@ __device__ __forceinline__ void conv_merged(int Z, const uint8_t *y0, const uint
   }
 }
 
-// accumulators -> product buffer: cbuf[k] = c[k] mod 2^16, k = 16 (8 jn + 2 t' + {0,1}) + 2 g + {0,1}
-template <int NJ>
-__device__ __forceinline__ void store_merged(int nj, int lane, const int (&acc)[NJ][4], uint16_t *cbuf) {
+// accumulators -> product buffer: cbuf[k] = c[k] mod 2^16, k = 16 (8 jn + 2 t' + {0,1}) + 2 g + {0,1};
+// NACC = 2: one accumulator set per limb of y, c = c0 + 256 c1
+template <int NJ, int NACC>
+__device__ __forceinline__ void store_product(int nj, int lane, const int (&acc)[NJ][NACC][4], uint16_t *cbuf) {
   const int g = lane >> 2, tq = lane & 3;
   uint32_t *dst = reinterpret_cast<uint32_t *>(cbuf) + 16 * tq + g;      // u16 index 32 t' + 2 g
 #pragma unroll
   for (int jn = 0; jn < NJ; ++jn) {
     if (jn < nj) {
-      dst[64 * jn] = __byte_perm((uint32_t)acc[jn][0], (uint32_t)acc[jn][2], 0x5410);
-      dst[64 * jn + 8] = __byte_perm((uint32_t)acc[jn][1], (uint32_t)acc[jn][3], 0x5410);
-    }
-  }
-}
-
-// accumulators -> product buffer: cbuf[k] = c[k] mod 2^16, k = 16 (8 jn + 2 t' + {0,1}) + 2 g + {0,1}
-template <int NJ, int LIMBS>
-__device__ __forceinline__ void store_product(const ImmaGeom &G, int lane, const int (&acc)[NJ][LIMBS][4], uint16_t *cbuf) {
-  const int g = lane >> 2, tq = lane & 3;
-  uint32_t *dst = reinterpret_cast<uint32_t *>(cbuf) + 16 * tq + g;      // u16 index 32 t' + 2 g
-#pragma unroll
-  for (int jn = 0; jn < NJ; ++jn) {
-    if (jn < G.NJ) {
       uint32_t v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t x = (uint32_t)acc[jn][0][i];
-        if (LIMBS == 2) x += (uint32_t)acc[jn][LIMBS - 1][i] << 8;
-        v[i] = x;
-      }
+      for (int i = 0; i < 4; ++i) v[i] = (uint32_t)acc[jn][0][i] + (NACC == 2 ? (uint32_t)acc[jn][NACC - 1][i] << 8 : 0u);
       dst[64 * jn] = __byte_perm(v[0], v[2], 0x5410);          // (K1 = 8 jn + 2 t'    ; k0 = 2 g, 2 g + 1)
       dst[64 * jn + 8] = __byte_perm(v[1], v[3], 0x5410);      // (K1 = 8 jn + 2 t' + 1; k0 = 2 g, 2 g + 1)
     }
   }
-}
-
-// y (uint16, mod q) -> reversed byte-limb arrays: yrev_l[Z - j] = limb l of y[j]
-template <int LIMBS>
-__device__ __forceinline__ void stage_y16(const ImmaGeom &G, const uint16_t *__restrict__ src, uint8_t *y0, uint8_t *y1, int lane) {
-  for (int j0 = 8 * lane; j0 < G.N; j0 += 256) {
-    uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
-    const int nv = G.N - j0;                                     // valid coefficients in this vector
-    if (nv < 8) {
-      uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = 2 * i + 1 < nv ? w[i] : (2 * i < nv ? (w[i] & 0xffffu) : 0u);
-      v = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    const int z = G.Z - j0 - 7;                                  // multiple of 8
-    *reinterpret_cast<uint2 *>(y0 + z) = make_uint2(__byte_perm(v.w, v.z, 0x4602), __byte_perm(v.y, v.x, 0x4602));
-    if (LIMBS == 2) *reinterpret_cast<uint2 *>(y1 + z) = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
-  }
-}
-
-// y (bytes) -> reversed array
-__device__ __forceinline__ void stage_y8(const ImmaGeom &G, const uint8_t *__restrict__ src, uint8_t *y0, int lane) {
-  for (int j0 = 16 * lane; j0 < G.N; j0 += 512) {
-    uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
-    const int nv = G.N - j0;
-    if (nv < 16) {
-      uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int nb = nv - 4 * i;
-        w[i] = nb >= 4 ? w[i] : (nb <= 0 ? 0u : (w[i] & (0xffffffffu >> (8 * (4 - nb)))));
-      }
-      v = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    *reinterpret_cast<uint4 *>(y0 + (G.Z - j0 - 15)) =
-        make_uint4(__byte_perm(v.w, 0u, 0x0123), __byte_perm(v.z, 0u, 0x0123), __byte_perm(v.y, 0u, 0x0123), __byte_perm(v.x, 0u, 0x0123));
-  }
-}
-
-// x (bytes) -> zero-padded array
-__device__ __forceinline__ void stage_x8(const ImmaGeom &G, const uint8_t *__restrict__ src, uint8_t *xb, int lane) {
-  for (int j0 = 16 * lane; j0 < G.N; j0 += 512) {
-    uint4 v = *reinterpret_cast<const uint4 *>(src + j0);
-    const int nv = G.N - j0;
-    if (nv < 16) {
-      uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int nb = nv - 4 * i;
-        w[i] = nb >= 4 ? w[i] : (nb <= 0 ? 0u : (w[i] & (0xffffffffu >> (8 * (4 - nb)))));
-      }
-      v = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    *reinterpret_cast<uint4 *>(xb + kXPad + j0) = v;
-  }
-}
-
-// asynchronous copy of `bytes` (multiple of 16) from global to this warp's prefetch area; completion: prefetch_wait
-__device__ __forceinline__ void prefetch_row(uint8_t *dst, const void *src, int bytes, int lane) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  const char *s = reinterpret_cast<const char *>(src);
-  for (int o = 16 * lane; o < bytes; o += 512)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + o), "l"(s + o) : "memory");
-}
-__device__ __forceinline__ void prefetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_wait() {
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-}
-
-// lo = c[k0 .. k0+8), hi = c[k0+N .. k0+N+8) as packed uint16 pairs
-__device__ __forceinline__ void load_lo_hi(const ImmaGeom &G, const uint16_t *cbuf, int k0, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
-  const uint4 l = *reinterpret_cast<const uint4 *>(cbuf + k0);
-  lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; lo[3] = l.w;
-  const int kh = k0 + G.N;
-  const uint32_t *w = reinterpret_cast<const uint32_t *>(cbuf + (kh & ~1));
-  const uint32_t sh = (kh & 1) ? 16u : 0u;
-  uint32_t x[5];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) x[i] = w[i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) hi[i] = __funnelshift_r(x[i], x[i + 1], sh);
-}
-
-// keeps the first nv (of 8) packed uint16 lanes
-__device__ __forceinline__ void mask_lanes(uint32_t (&v)[4], int nv) {
-  if (nv >= 8) return;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = 2 * i + 1 < nv ? v[i] : (2 * i < nv ? (v[i] & 0xffffu) : 0u);
 }
 
 // ---- encrypt / decrypt: shared-memory layout of one ciphertext (one warp) --------------------------------------------
@@ -400,17 +219,21 @@ __host__ __device__ constexpr ImmaLayout make_layout(int N, int nj_bucket, bool 
   return L;
 }
 
-// u16 coefficients (reduced mod q here) -> reversed byte-limb arrays: y0[Z - j] = y[j] & 255, y1[Z - j] = 4 (y[j] >> 8)
-template <int LIMBS>
+// u16 coefficients -> reversed byte-limb arrays: y0[Z - j] = y[j] & 255 and, MERGE (the coefficients are reduced mod q
+// first): y1[Z - j] = 4 (y[j] >> 8), otherwise y1[Z - j] = y[j] >> 8
+template <int LIMBS, bool MERGE>
 __device__ __forceinline__ void stage_limbs(int N, int Z, uint32_t Q2, const uint8_t *src, uint8_t *y0, uint8_t *y1, int lane) {
 #pragma unroll 4
   for (int j0 = 8 * lane; j0 < N; j0 += 256) {
     uint4 v = *reinterpret_cast<const uint4 *>(src + 2 * j0);
-    v = make_uint4(v.x & Q2, v.y & Q2, v.z & Q2, v.w & Q2);
+    if (MERGE) v = make_uint4(v.x & Q2, v.y & Q2, v.z & Q2, v.w & Q2);
     const int z = Z - j0 - 7;                                  // multiple of 8
     *reinterpret_cast<uint2 *>(y0 + z) = make_uint2(__byte_perm(v.w, v.z, 0x4602), __byte_perm(v.y, v.x, 0x4602));
-    if (LIMBS == 2)      // every high byte < 64: the shift carries nothing into the next byte
-      *reinterpret_cast<uint2 *>(y1 + z) = make_uint2(__byte_perm(v.w, v.z, 0x5713) << 2, __byte_perm(v.y, v.x, 0x5713) << 2);
+    if (LIMBS == 2) {
+      uint2 hi = make_uint2(__byte_perm(v.w, v.z, 0x5713), __byte_perm(v.y, v.x, 0x5713));
+      if (MERGE) hi = make_uint2(hi.x << 2, hi.y << 2);        // every high byte < 64: the shift carries nothing into the next byte
+      *reinterpret_cast<uint2 *>(y1 + z) = hi;
+    }
   }
 }
 
@@ -463,6 +286,12 @@ __device__ __forceinline__ uint32_t mod3_2x16(uint32_t v) {
 // keeps the first n (of 4) bytes of a word, n any integer
 __device__ __forceinline__ uint32_t keep_bytes(uint32_t v, int n) {
   return n >= 4 ? v : (n <= 0 ? 0u : v & (0xffffffffu >> (32 - 8 * n)));
+}
+
+__device__ __forceinline__ void prefetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 }
 
 // one array of a row by cp.async: `bytes` (multiple of 16), 16 per lane and step; dst and src already point at the lane's
@@ -536,14 +365,14 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
       reinterpret_cast<uint16_t *>(hr)[N + lane] = 0;
     }
     __syncwarp();
-    stage_limbs<LIMBS>(N, Z, Q2, hr, y0, y1, lane);
+    stage_limbs<LIMBS, true>(N, Z, Q2, hr, y0, y1, lane);
     if (LIMBS == 2) stage_x6(N, xr, x6 + kXPad, lane);
     __syncwarp();
     if (row + nwarps < a.B) prefetch(row + nwarps, cur ^ 1);    // in flight during this row's products
     {
-      int acc[NJ][4];
-      conv_merged<NJ, LIMBS, true, I1X>(Z, y0, y1, xr, x6 + kXPad, lane, acc);      // r in {0, 1, 2}: unsigned multiplier
-      store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
+      int acc[NJ][1][4];
+      conv_band<NJ, LIMBS, true, true, I1X>(Z, y0, y1, xr, x6 + kXPad, lane, acc);      // r in {0, 1, 2}: unsigned multiplier
+      store_product<NJ, 1>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
     // this lane's 8 coefficients of pass 0, per output array
@@ -630,15 +459,15 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
       fpr[N + lane] = 0;
     }
     __syncwarp();
-    stage_limbs<LIMBS>(N, Z, Q2, er, y0, y1, lane);
+    stage_limbs<LIMBS, true>(N, Z, Q2, er, y0, y1, lane);
     if (LIMBS == 2) stage_x6(N, fr, x6 + kXPad, lane);
     stage_rev8(N, Z, fpr, y2, lane);
     __syncwarp();
     if (row + nwarps < a.B) prefetch(row + nwarps, cur ^ 1);    // in flight during this row's products
     {   // product 1: a = lin(f, e) mod q  (f in {-1, 0, 1}: signed multiplier)
-      int acc[NJ][4];
-      conv_merged<NJ, LIMBS, false, I1X>(Z, y0, y1, fr, x6 + kXPad, lane, acc);
-      store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
+      int acc[NJ][1][4];
+      conv_band<NJ, LIMBS, true, false, I1X>(Z, y0, y1, fr, x6 + kXPad, lane, acc);
+      store_product<NJ, 1>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
     {
@@ -671,9 +500,9 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
     }
     __syncwarp();
     {   // product 2: c = lin(fp, b) mod 3
-      int acc[NJ][4];
-      conv_merged<NJ, 1, false, I1X>(Z, y2, y2, xb + kXPad, xb + kXPad, lane, acc);
-      store_merged<NJ>(NTRU_LF(NJ), lane, acc, cbuf);
+      int acc[NJ][1][4];
+      conv_band<NJ, 1, true, false, I1X>(Z, y2, y2, xb + kXPad, xb + kXPad, lane, acc);
+      store_product<NJ, 1>(NTRU_LF(NJ), lane, acc, cbuf);
     }
     __syncwarp();
     {
@@ -714,7 +543,8 @@ __global__ void __launch_bounds__(kImmaWarps * 32, ImmaShape<NJ>::kMinBlocks) k_
 // product is the same modulo q or p), y the wide one: uint16 (any value: p * fq is NOT reduced mod q, index.js:155)
 // in mod-q mode, one byte in mod-p mode.
 struct ImmaMulDivArgs {
-  ImmaGeom G;
+  ImmaLayout L;
+  uint32_t qmask;
   size_t B;
   const int8_t *x;
   const void *y;
@@ -725,41 +555,52 @@ template <int NJ, bool kModP>
 __global__ void __launch_bounds__(kImmaWarps * 32) k_muldiv_imma(const ImmaMulDivArgs a) {
   constexpr int LIMBS = kModP ? 1 : 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const ImmaGeom &G = a.G;
+  const ImmaLayout &L = a.L;
+  const int N = L.N, P = L.P, Z = L.Z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t *base = smem_raw + (size_t)warp * G.warp_bytes;
-  uint8_t *y0 = base, *y1 = base + G.Ly, *xb = base + 2 * G.Ly;
-  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + 2 * G.Ly + G.Lx);
-  uint8_t *raw = base + 2 * G.Ly + G.Lx + G.Lc;       // [y: 2P or P][x: P] of the NEXT row (cp.async)
-  for (int i = lane * 16; i < G.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
+  uint8_t *base = smem_raw + (size_t)warp * L.warp_bytes;
+  uint8_t *y0 = base, *y1 = base + L.o_y1;
+  uint16_t *cbuf = reinterpret_cast<uint16_t *>(base + L.o_c);
+  uint8_t *in0 = base + L.o_in;           // per buffer: [kXPad zeros | x : P | zeros up to Lx] [y : 2P or P]
+  for (int i = lane * 16; i < L.warp_bytes; i += 512) *reinterpret_cast<uint4 *>(base + i) = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  const uint32_t Q2 = G.qmask | (G.qmask << 16);
-  const int ybytes = kModP ? G.P : 2 * G.P;
+  const uint32_t Q2 = a.qmask | (a.qmask << 16);
+  const int ybytes = kModP ? P : 2 * P;
   const size_t nwarps = (size_t)gridDim.x * kImmaWarps;
-  auto prefetch = [&](size_t row) {
-    prefetch_row(raw, reinterpret_cast<const uint8_t *>(a.y) + row * (size_t)ybytes, ybytes, lane);
-    prefetch_row(raw + 2 * G.P, a.x + row * (size_t)G.P, G.P, lane);
+  const uint32_t in_lane = (uint32_t)__cvta_generic_to_shared(in0) + 16 * lane;
+  auto prefetch = [&](size_t row, int buf) {
+    const uint32_t d = in_lane + buf * L.Lin;
+    prefetch_lane<0>(d + kXPad, reinterpret_cast<const char *>(a.x) + (row * (size_t)P + 16 * lane), P, lane);
+    prefetch_lane<0>(d + L.Lx, reinterpret_cast<const char *>(a.y) + (row * (size_t)ybytes + 16 * lane), ybytes, lane);
     prefetch_commit();
   };
   size_t row = (size_t)blockIdx.x * kImmaWarps + warp;
-  if (row < a.B) prefetch(row);
-  for (; row < a.B; row += nwarps) {
+  if (row < a.B) prefetch(row, 0);
+  int cur = 0;
+  for (; row < a.B; row += nwarps, cur ^= 1) {
+    uint8_t *in = in0 + cur * L.Lin;
+    uint8_t *xr = in + kXPad, *yr = in + L.Lx;
     prefetch_wait();
-    if (kModP) stage_y8(G, raw, y0, lane);
-    else stage_y16<2>(G, reinterpret_cast<const uint16_t *>(raw), y0, y1, lane);
-    stage_x8(G, raw + 2 * G.P, xb, lane);
-    __syncwarp();
-    if (row + nwarps < a.B) prefetch(row + nwarps);
-    {
-      int acc[NJ][LIMBS][4];
-      conv_imma<NJ, LIMBS>(G, y0, y1, xb, lane, acc);
-      store_product<NJ, LIMBS>(G, lane, acc, cbuf);
+    if (lane < P - N) {        // the caller's pad columns may hold anything
+      xr[N + lane] = 0;
+      if (kModP) yr[N + lane] = 0;
+      else reinterpret_cast<uint16_t *>(yr)[N + lane] = 0;
     }
     __syncwarp();
-    const size_t rbase = row * (size_t)G.P;
-    for (int k0 = 8 * lane; k0 < G.P; k0 += 256) {
+    if (kModP) stage_rev8(N, Z, yr, y0, lane);
+    else stage_limbs<2, false>(N, Z, Q2, yr, y0, y1, lane);
+    __syncwarp();
+    if (row + nwarps < a.B) prefetch(row + nwarps, cur ^ 1);
+    {
+      int acc[NJ][LIMBS][4];
+      conv_band<NJ, LIMBS, false, false, 0>(Z, y0, y1, xr, xr, lane, acc);       // x in [-1, 2]: signed multiplier
+      store_product<NJ, LIMBS>(L.NJ, lane, acc, cbuf);
+    }
+    __syncwarp();
+    const size_t rbase = row * (size_t)P;
+    for (int k0 = 8 * lane; k0 < P; k0 += 256) {
       uint32_t lo[4], hi[4];
-      load_lo_hi(G, cbuf, k0, lo, hi);
+      load_lo_hi2(N, cbuf, k0, lo, hi);
       if (kModP) {
         uint32_t rem[2] = {0, 0}, quo[2] = {0, 0};
 #pragma unroll
@@ -769,9 +610,9 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_muldiv_imma(const ImmaMulDi
           const uint32_t lw = (lo[i >> 1] >> (16 * (i & 1))) & 0xffffu, hw = (hi[i >> 1] >> (16 * (i & 1))) & 0xffffu;
           const uint32_t l3 = mod3_16(lw + (lw >> 15) * 2u);
           const uint32_t h3 = mod3_16(hw + (hw >> 15) * 2u);
-          const bool in = k0 + i < G.N;
-          rem[i >> 2] |= (in ? mod3_16(l3 + h3) : 0u) << (8 * (i & 3));
-          quo[i >> 2] |= (in ? mod3_16(3u - h3) : 0u) << (8 * (i & 3));
+          const bool valid = k0 + i < N;
+          rem[i >> 2] |= (valid ? mod3_16(l3 + h3) : 0u) << (8 * (i & 3));
+          quo[i >> 2] |= (valid ? mod3_16(3u - h3) : 0u) << (8 * (i & 3));
         }
         if (a.rem) *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.rem) + rbase + k0) = make_uint2(rem[0], rem[1]);
         if (a.quo) *reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(a.quo) + rbase + k0) = make_uint2(quo[0], quo[1]);
@@ -779,35 +620,17 @@ __global__ void __launch_bounds__(kImmaWarps * 32) k_muldiv_imma(const ImmaMulDi
         uint32_t rem[4], quo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          rem[i] = ((lo[i] & Q2) + (hi[i] & Q2)) & Q2;
-          quo[i] = ((~hi[i] & Q2) + 0x00010001u) & Q2;
+          rem[i] = __vadd2(lo[i], hi[i]) & Q2;
+          quo[i] = __vsub2(0u, hi[i]) & Q2;
         }
-        mask_lanes(rem, G.N - k0);
-        mask_lanes(quo, G.N - k0);
+        mask_tail(rem, N - k0);
+        mask_tail(quo, N - k0);
         if (a.rem) *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(a.rem) + rbase + k0) = make_uint4(rem[0], rem[1], rem[2], rem[3]);
         if (a.quo) *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(a.quo) + rbase + k0) = make_uint4(quo[0], quo[1], quo[2], quo[3]);
       }
     }
     __syncwarp();
   }
-}
-
-ImmaGeom make_geom(const ntru_ctx *ctx, int ylimb_arrays, int nj_bucket) {
-  ImmaGeom G;
-  G.N = ctx->N; G.P = ctx->P; G.q = ctx->q; G.logq = ctx->logq; G.qmask = (uint32_t)ctx->q - 1;
-  G.I1 = (G.N + 15) / 16;
-  const int tmax = (G.N + 14) / 16;
-  G.S = tmax / 2 + 1;
-  G.NJ = ((2 * G.N - 1 + 15) / 16 + 7) / 8;
-  G.Z = 32 * G.S + 15;
-  G.Ly = 32 * G.S + 48;
-  // x is read at block indices K1 - t in [-7, 8 kDMax + 7] and, as the lifted polynomial b, written up to P
-  const int dmax = (6 + 4 * nj_bucket) >> 3;
-  G.Lx = kXPad + (128 * (dmax + 1) > G.P ? 128 * (dmax + 1) : G.P);
-  G.Lc = 2 * (128 * G.NJ + 32);
-  G.Lraw = 4 * G.P;
-  G.warp_bytes = ylimb_arrays * G.Ly + G.Lx + G.Lc + G.Lraw + (ylimb_arrays == 2 ? G.P : 0);
-  return G;
 }
 
 template <class K, class A>
@@ -888,19 +711,20 @@ int launch_muldiv_imma(ntru_ctx *ctx, size_t B, const int8_t *x, const void *y, 
   if (B == 0) return NTRU_OK;
   if (!imma_supported(ctx)) return fail(ctx, NTRU_E_UNSUPPORTED, "register-fragment tensor schedule supports N <= 832");
   ImmaMulDivArgs a;
-  a.G = make_geom(ctx, 2, imma_bucket(ctx));
+  a.L = make_layout(ctx->N, imma_bucket(ctx), false, false);
+  a.qmask = (uint32_t)ctx->q - 1;
   a.B = B; a.x = x; a.y = y; a.quo = quo; a.rem = rem;
-  const int nj = a.G.NJ;
+  const int nj = a.L.NJ;
   if (mod_p) {
-    if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
-    if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
-    if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
-    return launch_imma(ctx, k_muldiv_imma<13, true>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+    if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, true>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
+    if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, true>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
+    if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, true>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
+    return launch_imma(ctx, k_muldiv_imma<13, true>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
   }
-  if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
-  if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
-  if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
-  return launch_imma(ctx, k_muldiv_imma<13, false>, a, NTRU_K_MULDIV, B, a.G.warp_bytes);
+  if (nj <= 3) return launch_imma(ctx, k_muldiv_imma<3, false>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
+  if (nj <= 8) return launch_imma(ctx, k_muldiv_imma<8, false>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
+  if (nj <= 11) return launch_imma(ctx, k_muldiv_imma<11, false>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
+  return launch_imma(ctx, k_muldiv_imma<13, false>, a, NTRU_K_MULDIV, B, a.L.warp_bytes);
 }
 
 int launch_encrypt_imma(ntru_ctx *ctx, size_t B, const uint16_t *h, size_t h_stride, const uint8_t *r, const uint8_t *m,
