@@ -10,5 +10,5 @@ echo ncu821 rc=$?
 python bench.py --steps 2 --warmup 3 --no-cpu --configs '' > gpurun_out/plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2c_ncu_launch_list.csv python bench.py --steps 2 --warmup 3 --no-cpu --configs '' > gpurun_out/ncu_bench.log 2>&1
 echo launchlist rc=$?
-tail -3 gpurun_out/ncu509.log gpurun_out/ncu821.log gpurun_out/ncu_bench.log
+for f in gpurun_out/ncu509.log gpurun_out/ncu821.log gpurun_out/ncu_bench.log; do tail -n 3 $f; done
 ls -la gpurun_out/*.ncu-rep
