@@ -773,7 +773,7 @@ k_umma_pair(const UmmaArgs a, const __grid_constant__ CUtensorMap tmapB, const _
 #pragma unroll
                   for (int jj = 0; jj < 8; ++jj) {
                     const uint32_t mp = __byte_perm(mw[jj >> 1], 0u, (jj & 1) ? 0x4342 : 0x4140);
-                    pk[jj] = ((pk[jj] & Q2) + mp) & Q2;
+                    pk[jj] = __vadd2(pk[jj], mp) & Q2;     // VIADD.16x2: the lanes wrap mod 2^16, q divides it
                   }
                 } else {
 #pragma unroll
