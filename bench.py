@@ -537,7 +537,18 @@ def run_ours(args, rank, world, local_rank):
     # Two wire formats of the same two calls: "field_elements" -- every array as packOutput(maxVal, width, row).expected
     # (index.js:572-596, the form CombineArray / UnpackArray take; bits packed and unpacked on the device) -- and
     # "plain_arrays" (uint16 / uint8 coefficient rows).  Same rows, same results (checked below after unpacking).
-    Be = min(args.e2e_rows, B)
+    # rows per end-to-end step: the whole batch when the host can pin it (both wire formats are measured one after the
+    # other, ~20 KB of host buffers per row at the peak), else a half or a quarter of it -- longer steps amortise the fill and
+    # drain of the copy pipeline (0.92 / 0.95 / 0.96 of the PCIe roof at 2^18 / 2^19 / 10^6 rows)
+    if args.e2e_rows:
+        Be = min(args.e2e_rows, B)
+    else:
+        try:
+            import psutil
+            per_rank_gb = psutil.virtual_memory().total / world / 2 ** 30
+        except Exception:
+            per_rank_gb = 0.0
+        Be = min(B, 1_000_000 if per_rank_gb >= 64 else (524_288 if per_rank_gb >= 32 else 262_144))
     eng2 = nb.Engine(N, p, q, local_rank)
     eng2.set_public_key(g["h"])
     eng2.set_private_key(g["f"], g["fp"])
@@ -708,7 +719,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000, help="ciphertexts per GPU per step")
-    ap.add_argument("--e2e-rows", type=int, default=262_144)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows per end-to-end step; 0 = by host memory per rank (10^6, 2^19 or 2^18)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 fp32 CUDA-core schedule, 2 tcgen05 schedule, 3 register-fragment IMMA schedule")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
